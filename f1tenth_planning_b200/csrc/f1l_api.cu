@@ -1,0 +1,1064 @@
+// f1l_api.cu -- C-ABI (include/f1l.h) over the sm_100a kernels.  No torch types, no exceptions
+// across the boundary; every launch goes on the handle's (or the caller's) stream.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "f1l_common.cuh"
+#include "f1l_lattice.cuh"
+#include "f1l_peaks.cuh"
+#include "f1l_pp.cuh"
+
+#define N_PIPE 3  // streams of the host-buffer batch pipeline
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct PipeSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    DevBuf poses, opp, nopp, ctx, centres, best, idx, cost, traj, costs, flags, ss;
+};
+
+}  // namespace
+
+struct f1l_ctx {
+    int device = 0;
+    f1l_config cfg;
+    cudaStream_t stream = nullptr;
+    char err[512] = {0};
+    int64_t launches = 0;
+    int timing = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float last_ms[3] = {0, 0, 0};
+    int sm_count = 148;
+    // track
+    int n = 0, ncols = 0;
+    DevBuf xy, v, psi, kappa, segA, segB, blk;
+    // grid
+    DevBuf grid;
+    int gh = 0, gw = 0;
+    double gox = 0, goy = 0, gres = 1;
+    // lut
+    DevBuf lut;
+    int ldims[3] = {20, 21, 9};
+    double lranges[6] = {0.2, 4.0, -2.0, 2.0, -1.5707963267948966, 1.5707963267948966};
+    // goal grid
+    DevBuf lookaheads, widths;
+    int nL = 0, nW = 0;
+    // previous path
+    DevBuf prev;
+    int has_prev = 0, prev_m = 0;
+    // single-query device buffers
+    DevBuf q_in, q_goals, q_ctx, q_centres, q_best, q_idx, q_cost, q_status, q_ss, q_traj, q_costs,
+        q_terms, q_flags, q_gout, q_params, q_states, q_headings;
+    // pinned staging for the single query
+    void* h_in = nullptr;   // pose + opponents
+    void* h_out = nullptr;  // header + best trajectory
+    size_t h_out_cap = 0;
+    // batch (device-pointer API) scratch
+    DevBuf b_ctx, b_centres, b_best;
+    // batch pipeline (host-pointer API)
+    PipeSlot pipe[N_PIPE];
+    // misc scratch for the pure-pursuit / intersect host APIs
+    DevBuf m_in, m_in2, m_o0, m_o1, m_o2, m_o3, m_o4, m_o5;
+};
+
+namespace {
+
+int fail(f1l_handle h, cudaError_t e, const char* what) {
+    if (h) snprintf(h->err, sizeof(h->err), "%s: %s", what, cudaGetErrorString(e));
+    return F1L_ERR_CUDA;
+}
+
+#define CK(call)                                            \
+    do {                                                    \
+        cudaError_t e__ = (call);                           \
+        if (e__ != cudaSuccess) return fail(h, e__, #call); \
+    } while (0)
+
+int ensure(f1l_handle h, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return F1L_OK;
+    if (b.p) {
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes < 256 ? 256 : bytes;
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return F1L_OK;
+}
+
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+#define ENS(buf, bytes)                          \
+    do {                                         \
+        int r__ = ensure(h, (buf), (bytes));     \
+        if (r__ != F1L_OK) return r__;           \
+    } while (0)
+
+TrackView track_view(f1l_handle h) {
+    TrackView t;
+    t.n = h->n;
+    t.ncols = h->ncols;
+    t.xy = (const double2*)h->xy.p;
+    t.v = (const double*)h->v.p;
+    t.psi = (const double*)h->psi.p;
+    t.kappa = (const double*)h->kappa.p;
+    t.segA = (const float4*)h->segA.p;
+    t.segB = (const float2*)h->segB.p;
+    t.blk_origin = (const double2*)h->blk.p;
+    return t;
+}
+
+GridView grid_view(f1l_handle h) {
+    GridView g;
+    g.occ = (const uint8_t*)h->grid.p;
+    g.h = h->gh;
+    g.w = h->gw;
+    g.ox = h->gox;
+    g.oy = h->goy;
+    g.inv_res = 1.0 / h->gres;
+    return g;
+}
+
+LutView lut_view(f1l_handle h) {
+    LutView l;
+    l.cells = (const float4*)h->lut.p;
+    l.nx = h->ldims[0];
+    l.ny = h->ldims[1];
+    l.nt = h->ldims[2];
+    l.x0 = (float)h->lranges[0];
+    l.y0 = (float)h->lranges[2];
+    l.t0 = (float)h->lranges[4];
+    l.sx = l.nx > 1 ? (float)((l.nx - 1) / (h->lranges[1] - h->lranges[0])) : 0.0f;
+    l.sy = l.ny > 1 ? (float)((l.ny - 1) / (h->lranges[3] - h->lranges[2])) : 0.0f;
+    l.st = l.nt > 1 ? (float)((l.nt - 1) / (h->lranges[5] - h->lranges[4])) : 0.0f;
+    return l;
+}
+
+EvalParams eval_params(f1l_handle h) {
+    const f1l_config& c = h->cfg;
+    EvalParams e;
+    e.M = c.n_samples;
+    e.n_newton = c.n_newton;
+    e.window = c.window;
+    e.n_shift = c.n_shift;
+    e.n_cull = c.n_cull;
+    e.literal_tracker = c.literal_tracker;
+    e.use_goal_kappa = c.use_goal_kappa;
+    for (int i = 0; i < F1L_N_TERMS; ++i) e.w[i] = (float)c.weights[i];
+    e.kappa_max = (float)c.kappa_max;
+    e.half_l = (float)(0.5 * c.car_length);
+    e.half_w = (float)(0.5 * c.car_width);
+    const double hl = 0.5 * c.car_length, hw = 0.5 * c.car_width;
+    e.rc2 = (float)(4.0 * (hl * hl + hw * hw));
+    e.tol = (float)c.converge_tol;
+    e.tracker_lookahead = c.tracker_lookahead;
+    e.wheelbase = c.wheelbase;
+    e.max_reacquire = c.max_reacquire;
+    return e;
+}
+
+int check_config(const f1l_config* c) {
+    if (!c) return F1L_ERR_INVALID_ARG;
+    if (c->n_samples < 2 || c->n_samples > F1L_MAX_M) return F1L_ERR_INVALID_ARG;
+    if (c->n_newton < 0 || c->n_newton > 64) return F1L_ERR_INVALID_ARG;
+    if (c->n_shift < 0 || c->n_cull < 0) return F1L_ERR_INVALID_ARG;
+    if (!(c->car_length > 0) || !(c->car_width > 0)) return F1L_ERR_INVALID_ARG;
+    return F1L_OK;
+}
+
+// ---- kernel dispatch on the sample count -------------------------------------------------
+struct EvalShape {
+    int ipl, s, sg;
+};
+
+EvalShape eval_shape(int M) {
+    if (M <= 32) return {1, 4, 8};
+    if (M <= 64) return {2, 8, 8};
+    if (M <= 104) return {4, 13, 8};
+    if (M <= 128) return {4, 16, 8};
+    if (M <= 208) return {7, 13, 16};
+    return {8, 16, 16};
+}
+
+typedef void (*eval_fn)(EvalArgs);
+typedef void (*select_fn)(SelectArgs);
+typedef void (*generate_fn)(LutView, EvalParams, const float4*, int, float4*, float4*, uint8_t*);
+
+eval_fn eval_entry(int M) {
+    if (M <= 32) return eval_kernel<1, 4, 8>;
+    if (M <= 64) return eval_kernel<2, 8, 8>;
+    if (M <= 104) return eval_kernel<4, 13, 8>;
+    if (M <= 128) return eval_kernel<4, 16, 8>;
+    if (M <= 208) return eval_kernel<7, 13, 16>;
+    return eval_kernel<8, 16, 16>;
+}
+select_fn select_entry(int M) {
+    if (M <= 32) return select_kernel<1>;
+    if (M <= 64) return select_kernel<2>;
+    if (M <= 128) return select_kernel<4>;
+    if (M <= 208) return select_kernel<7>;
+    return select_kernel<8>;
+}
+generate_fn generate_entry(int M) {
+    if (M <= 32) return generate_kernel<1>;
+    if (M <= 64) return generate_kernel<2>;
+    if (M <= 128) return generate_kernel<4>;
+    if (M <= 208) return generate_kernel<7>;
+    return generate_kernel<8>;
+}
+
+int pick_warps_per_cta(int n_cand) {
+    if (n_cand >= 64) return 8;
+    for (int w = 8; w >= 4; --w)
+        if (n_cand % w == 0) return w;
+    return n_cand < 8 ? (n_cand > 0 ? n_cand : 1) : 8;
+}
+
+size_t eval_smem_bytes(int nseg_pad, int warps, int M) {
+    size_t b = (size_t)nseg_pad * (sizeof(float4) + sizeof(float2));
+    b += (size_t)warps * M * sizeof(float2);
+    b += (size_t)((M + 3) & ~3) * sizeof(float);
+    b += F1L_MAX_OPP * sizeof(float4);
+    return b;
+}
+
+struct BatchOut {
+    int32_t* best_idx = nullptr;
+    float* best_cost = nullptr;
+    int32_t* status = nullptr;
+    double* steer_speed = nullptr;
+    float4* best_traj = nullptr;
+    float* costs = nullptr;
+    float* terms = nullptr;
+    uint8_t* flags = nullptr;
+    float* goals_out = nullptr;
+    float4* params = nullptr;
+    float4* states = nullptr;
+    float2* headings = nullptr;
+    float* prev_out = nullptr;
+};
+
+// sampler -> eval -> select for S scenarios on `stream`; all pointers are device pointers
+int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, const double* opp,
+                    const int32_t* n_opp, int S, int max_opp, const float4* goals, int n_goals,
+                    int c_begin, int c_end, QueryCtx* ctx, Centre* centres,
+                    unsigned long long* best, const float* prev_theta, const BatchOut& o,
+                    bool time_it) {
+    if (h->n < 2) return F1L_ERR_NO_TRACK;
+    const int C = goals ? n_goals : h->nL * h->nW;
+    if (C <= 0) return F1L_ERR_NO_GOALS;
+    if (c_begin < 0) c_begin = 0;
+    if (c_end <= 0 || c_end > C) c_end = C;
+    if (c_begin >= c_end) return F1L_ERR_INVALID_ARG;
+    if (max_opp > F1L_MAX_OPP || max_opp < 0) return F1L_ERR_INVALID_ARG;
+    const int M = h->cfg.n_samples;
+    const EvalParams ep = eval_params(h);
+    const int nsegs = h->n - 1;
+    int nseg = h->cfg.window;
+    if (nseg <= 0 || nseg > nsegs) nseg = nsegs;
+    const int nseg_pad = (nseg + 31) & ~31;
+    const int n_cand = c_end - c_begin;
+    const int wpc = pick_warps_per_cta(n_cand);
+    const size_t smem = eval_smem_bytes(nseg_pad, wpc, M);
+    if (smem > 227 * 1024) return F1L_ERR_TOO_LARGE;
+
+    SampleArgs sa;
+    sa.tr = track_view(h);
+    sa.grid = grid_view(h);
+    sa.ep = ep;
+    sa.poses = poses;
+    sa.opp = opp;
+    sa.n_opp = n_opp;
+    sa.max_opp = max_opp;
+    sa.lookaheads = (const double*)h->lookaheads.p;
+    sa.nL = goals ? 0 : h->nL;
+    sa.ctx = ctx;
+    sa.centres = centres;
+    sa.best = best;
+    if (time_it) cudaEventRecord(h->ev[0], stream);
+    sample_kernel<<<S, SAMPLE_THREADS, 0, stream>>>(sa);
+    if (time_it) cudaEventRecord(h->ev[1], stream);
+
+    EvalArgs ea;
+    ea.tr = sa.tr;
+    ea.grid = sa.grid;
+    ea.lut = lut_view(h);
+    ea.ep = ep;
+    ea.ctx = ctx;
+    ea.centres = centres;
+    ea.widths = (const float*)h->widths.p;
+    ea.nL = h->nL;
+    ea.nW = h->nW;
+    ea.goals = goals;
+    ea.prev_theta = prev_theta;
+    ea.C = C;
+    ea.c_begin = c_begin;
+    ea.c_end = c_end;
+    ea.ctas_per_scn = (n_cand + wpc - 1) / wpc;
+    ea.nseg_pad = nseg_pad;
+    ea.costs = o.costs;
+    ea.terms = o.terms;
+    ea.flags = o.flags;
+    ea.goals_out = o.goals_out;
+    ea.params = o.params;
+    ea.states = o.states;
+    ea.headings = o.headings;
+    ea.best = best;
+    const long long n_ctas = (long long)S * ea.ctas_per_scn;
+    if (n_ctas > 0x7fffffffLL) return F1L_ERR_TOO_LARGE;
+    eval_entry(M)<<<(unsigned)n_ctas, wpc * 32, smem, stream>>>(ea);
+    if (time_it) cudaEventRecord(h->ev[2], stream);
+
+    SelectArgs se;
+    se.tr = sa.tr;
+    se.lut = ea.lut;
+    se.ep = ep;
+    se.ctx = ctx;
+    se.centres = centres;
+    se.widths = ea.widths;
+    se.nL = h->nL;
+    se.nW = h->nW;
+    se.goals = goals;
+    se.C = C;
+    se.c_begin = c_begin;
+    se.best = best;
+    se.best_idx = o.best_idx;
+    se.best_cost = o.best_cost;
+    se.status = o.status;
+    se.steer_speed = o.steer_speed;
+    se.best_traj = o.best_traj;
+    se.prev_theta_out = o.prev_out;
+    select_entry(M)<<<S, 32, 0, stream>>>(se);
+    if (time_it) cudaEventRecord(h->ev[3], stream);
+    h->launches += 3;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, e, "pipeline launch");
+    return F1L_OK;
+}
+
+struct QHeader {
+    double steer, speed;
+    int32_t best_idx, no_feasible, tracker_found, pad;
+    float best_cost, pad2;
+};
+
+}  // namespace
+
+extern "C" {
+
+int f1l_default_config(f1l_config* c) {
+    if (!c) return F1L_ERR_INVALID_ARG;
+    memset(c, 0, sizeof(*c));
+    c->n_samples = 100;
+    c->n_newton = 8;
+    c->window = 128;
+    c->n_shift = 5;
+    c->n_cull = 10;
+    c->literal_tracker = 0;
+    c->use_goal_kappa = 0;
+    c->weights[0] = 0.1;
+    c->weights[1] = 0.1;
+    c->weights[2] = 0.1;
+    c->weights[3] = 0.2;
+    c->weights[4] = 0.5;
+    c->kappa_max = std::tan(0.4189) / 0.33;
+    c->car_length = 0.58;
+    c->car_width = 0.31;
+    c->converge_tol = 1e-4;
+    c->tracker_lookahead = 0.8;
+    c->wheelbase = 0.33;
+    c->max_reacquire = 20.0;
+    return F1L_OK;
+}
+
+const char* f1l_strerror(int code) {
+    switch (code) {
+        case F1L_OK: return "ok";
+        case F1L_ERR_INVALID_ARG: return "invalid argument";
+        case F1L_ERR_NO_TRACK: return "no track uploaded (f1l_set_track)";
+        case F1L_ERR_CUDA: return "CUDA error (see f1l_last_cuda_error)";
+        case F1L_ERR_NO_DEVICE: return "no CUDA device / device index out of range";
+        case F1L_ERR_TOO_LARGE: return "problem too large for this build (window / grid limits)";
+        case F1L_ERR_NO_GOALS: return "no goal grid set (f1l_set_goal_grid) and no explicit goals";
+        case F1L_ERR_ALLOC: return "host allocation failed";
+        default: return "unknown f1l status";
+    }
+}
+
+const char* f1l_last_cuda_error(f1l_handle h) { return h ? h->err : ""; }
+int f1l_device(f1l_handle h) { return h ? h->device : -1; }
+int64_t f1l_launch_count(f1l_handle h) { return h ? h->launches : 0; }
+
+int f1l_set_timing(f1l_handle h, int on) {
+    if (!h) return F1L_ERR_INVALID_ARG;
+    h->timing = on;
+    return F1L_OK;
+}
+
+int f1l_last_kernel_ms(f1l_handle h, float* sample_ms, float* eval_ms, float* select_ms) {
+    if (!h) return F1L_ERR_INVALID_ARG;
+    if (sample_ms) *sample_ms = h->last_ms[0];
+    if (eval_ms) *eval_ms = h->last_ms[1];
+    if (select_ms) *select_ms = h->last_ms[2];
+    return F1L_OK;
+}
+
+int f1l_set_config(f1l_handle h, const f1l_config* cfg) {
+    if (!h) return F1L_ERR_INVALID_ARG;
+    int r = check_config(cfg);
+    if (r != F1L_OK) return r;
+    if (cfg->n_samples != h->cfg.n_samples) h->has_prev = 0;
+    h->cfg = *cfg;
+    return F1L_OK;
+}
+
+int f1l_get_config(f1l_handle h, f1l_config* cfg) {
+    if (!h || !cfg) return F1L_ERR_INVALID_ARG;
+    *cfg = h->cfg;
+    return F1L_OK;
+}
+
+static int build_lut(f1l_handle h) {
+    const int cells = h->ldims[0] * h->ldims[1] * h->ldims[2];
+    ENS(h->lut, (size_t)cells * sizeof(float4));
+    lut_build_kernel<<<(cells + 127) / 128, 128, 0, h->stream>>>(
+        (float4*)h->lut.p, h->ldims[0], h->ldims[1], h->ldims[2], h->lranges[0], h->lranges[1],
+        h->lranges[2], h->lranges[3], h->lranges[4], h->lranges[5]);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    return F1L_OK;
+}
+
+int f1l_create(f1l_handle* out, int device, const f1l_config* cfg) {
+    if (!out) return F1L_ERR_INVALID_ARG;
+    *out = nullptr;
+    f1l_config c;
+    if (cfg) c = *cfg;
+    else f1l_default_config(&c);
+    int r = check_config(&c);
+    if (r != F1L_OK) return r;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+        return F1L_ERR_NO_DEVICE;
+    f1l_handle h = new (std::nothrow) f1l_ctx();
+    if (!h) return F1L_ERR_ALLOC;
+    h->device = device;
+    h->cfg = c;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+    for (int i = 0; i < N_PIPE && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&h->pipe[i].stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->pipe[i].done, cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaHostAlloc(&h->h_in, 1024, cudaHostAllocDefault);
+    if (e == cudaSuccess) {
+        h->h_out_cap = sizeof(QHeader) + F1L_MAX_M * sizeof(float4);
+        e = cudaHostAlloc(&h->h_out, h->h_out_cap, cudaHostAllocDefault);
+    }
+    if (e == cudaSuccess) {
+        int sm = 0;
+        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+        if (sm > 0) h->sm_count = sm;
+        // opt in to large dynamic shared memory for every eval instantiation + the scan kernel
+        const int big = 227 * 1024;
+        cudaFuncSetAttribute(eval_kernel<1, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(eval_kernel<2, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(eval_kernel<4, 13, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(eval_kernel<4, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(eval_kernel<7, 13, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(eval_kernel<8, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        e = cudaFuncSetAttribute(pp_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)PP_SMEM_BYTES);
+    }
+    if (e != cudaSuccess) {
+        fail(h, e, "f1l_create");
+        f1l_destroy(h);
+        return F1L_ERR_CUDA;
+    }
+    r = build_lut(h);
+    if (r != F1L_OK) {
+        f1l_destroy(h);
+        return r;
+    }
+    *out = h;
+    return F1L_OK;
+}
+
+int f1l_destroy(f1l_handle h) {
+    if (!h) return F1L_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    DevBuf* bufs[] = {&h->xy, &h->v, &h->psi, &h->kappa, &h->segA, &h->segB, &h->blk, &h->grid,
+                      &h->lut, &h->lookaheads, &h->widths, &h->prev, &h->q_in, &h->q_goals,
+                      &h->q_ctx, &h->q_centres, &h->q_best, &h->q_idx, &h->q_cost, &h->q_status,
+                      &h->q_ss, &h->q_traj, &h->q_costs, &h->q_terms, &h->q_flags, &h->q_gout,
+                      &h->q_params, &h->q_states, &h->q_headings, &h->b_ctx, &h->b_centres,
+                      &h->b_best, &h->m_in, &h->m_in2, &h->m_o0, &h->m_o1, &h->m_o2, &h->m_o3,
+                      &h->m_o4, &h->m_o5};
+    for (DevBuf* b : bufs) release(*b);
+    for (int i = 0; i < N_PIPE; ++i) {
+        PipeSlot& p = h->pipe[i];
+        DevBuf* pb[] = {&p.poses, &p.opp, &p.nopp, &p.ctx, &p.centres, &p.best, &p.idx, &p.cost,
+                        &p.traj, &p.costs, &p.flags, &p.ss};
+        for (DevBuf* b : pb) release(*b);
+        if (p.done) cudaEventDestroy(p.done);
+        if (p.stream) cudaStreamDestroy(p.stream);
+    }
+    for (int i = 0; i < 4; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return F1L_OK;
+}
+
+int f1l_set_track(f1l_handle h, const double* wpts, int n, int ncols) {
+    if (!h || !wpts || n < 2 || ncols < 2) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    const int nseg = n - 1;
+    const int nblk = (nseg + 31) / 32;
+    std::vector<double> xy(2 * (size_t)n), v(n, 0.0), psi(n, 0.0), kap(n, 0.0);
+    for (int i = 0; i < n; ++i) {
+        xy[2 * i] = wpts[(size_t)i * ncols];
+        xy[2 * i + 1] = wpts[(size_t)i * ncols + 1];
+        if (ncols > 2) v[i] = wpts[(size_t)i * ncols + 2];
+        if (ncols > 3) psi[i] = wpts[(size_t)i * ncols + 3];
+        if (ncols > 4) kap[i] = wpts[(size_t)i * ncols + 4];
+    }
+    std::vector<float> segA(4 * (size_t)nseg), segB(2 * (size_t)nseg);
+    std::vector<double> blk(2 * (size_t)nblk);
+    for (int b = 0; b < nblk; ++b) {
+        blk[2 * b] = xy[2 * (size_t)(32 * b)];
+        blk[2 * b + 1] = xy[2 * (size_t)(32 * b) + 1];
+    }
+    for (int k = 0; k < nseg; ++k) {
+        const double ox = blk[2 * (k / 32)], oy = blk[2 * (k / 32) + 1];
+        const double ax = xy[2 * k] - ox, ay = xy[2 * k + 1] - oy;
+        const double dx = xy[2 * k + 2] - xy[2 * k], dy = xy[2 * k + 3] - xy[2 * k + 1];
+        const double len = std::sqrt(dx * dx + dy * dy);
+        const double ux = dx / len, uy = dy / len;
+        segA[4 * k] = (float)ux;
+        segA[4 * k + 1] = (float)uy;
+        segA[4 * k + 2] = (float)(ax * ux + ay * uy);
+        segA[4 * k + 3] = (float)(-ax * uy + ay * ux);
+        segB[2 * k] = (float)len;
+        segB[2 * k + 1] = (float)(1.0 / len);
+    }
+    ENS(h->xy, xy.size() * 8);
+    ENS(h->v, v.size() * 8);
+    ENS(h->psi, psi.size() * 8);
+    ENS(h->kappa, kap.size() * 8);
+    ENS(h->segA, segA.size() * 4);
+    ENS(h->segB, segB.size() * 4);
+    ENS(h->blk, blk.size() * 8);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->xy.p, xy.data(), xy.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->v.p, v.data(), v.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->psi.p, psi.data(), psi.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->kappa.p, kap.data(), kap.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->segA.p, segA.data(), segA.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->segB.p, segB.data(), segB.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->blk.p, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice));
+    h->n = n;
+    h->ncols = ncols;
+    return F1L_OK;
+}
+
+int f1l_set_grid(f1l_handle h, const uint8_t* occ, int height, int width, double ox, double oy,
+                 double res) {
+    if (!h || !occ || height <= 0 || width <= 0 || !(res > 0)) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    ENS(h->grid, (size_t)height * width);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->grid.p, occ, (size_t)height * width, cudaMemcpyHostToDevice));
+    h->gh = height;
+    h->gw = width;
+    h->gox = ox;
+    h->goy = oy;
+    h->gres = res;
+    return F1L_OK;
+}
+
+int f1l_clear_grid(f1l_handle h) {
+    if (!h) return F1L_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    release(h->grid);
+    h->gh = h->gw = 0;
+    return F1L_OK;
+}
+
+int f1l_set_goal_grid(f1l_handle h, const double* lookaheads, int nL, const double* widths,
+                      int nW) {
+    if (!h || !lookaheads || !widths || nL <= 0 || nW <= 0 || nL > F1L_MAX_LOOKAHEADS)
+        return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    std::vector<float> wf(nW);
+    for (int i = 0; i < nW; ++i) wf[i] = (float)widths[i];
+    ENS(h->lookaheads, (size_t)nL * 8);
+    ENS(h->widths, (size_t)nW * 4);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->lookaheads.p, lookaheads, (size_t)nL * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->widths.p, wf.data(), (size_t)nW * 4, cudaMemcpyHostToDevice));
+    h->nL = nL;
+    h->nW = nW;
+    return F1L_OK;
+}
+
+int f1l_get_lut_shape(f1l_handle h, int32_t dims[3], double ranges[6]) {
+    if (!h) return F1L_ERR_INVALID_ARG;
+    for (int i = 0; i < 3; ++i) dims[i] = h->ldims[i];
+    for (int i = 0; i < 6; ++i) ranges[i] = h->lranges[i];
+    return F1L_OK;
+}
+
+int f1l_get_lut(f1l_handle h, float* out) {
+    if (!h || !out) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, h->lut.p, (size_t)h->ldims[0] * h->ldims[1] * h->ldims[2] * sizeof(float4),
+                  cudaMemcpyDeviceToHost));
+    return F1L_OK;
+}
+
+int f1l_set_lut(f1l_handle h, const float* lut, const int32_t dims[3], const double ranges[6]) {
+    if (!h || !lut || !dims || !ranges) return F1L_ERR_INVALID_ARG;
+    if (dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    const size_t bytes = (size_t)dims[0] * dims[1] * dims[2] * sizeof(float4);
+    ENS(h->lut, bytes);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->lut.p, lut, bytes, cudaMemcpyHostToDevice));
+    for (int i = 0; i < 3; ++i) h->ldims[i] = dims[i];
+    for (int i = 0; i < 6; ++i) h->lranges[i] = ranges[i];
+    return F1L_OK;
+}
+
+int f1l_set_prev_path(f1l_handle h, const float* theta_prev, int m) {
+    if (!h || !theta_prev || m != h->cfg.n_samples) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    ENS(h->prev, F1L_MAX_M * sizeof(float));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(h->prev.p, theta_prev, (size_t)m * sizeof(float), cudaMemcpyHostToDevice));
+    h->has_prev = 1;
+    h->prev_m = m;
+    return F1L_OK;
+}
+
+int f1l_clear_prev_path(f1l_handle h) {
+    if (!h) return F1L_ERR_INVALID_ARG;
+    h->has_prev = 0;
+    return F1L_OK;
+}
+
+// ---- single query -------------------------------------------------------------------------
+static int plan_internal(f1l_handle h, const double pose[4], const double* opp, int n_opp,
+                         const double* goals, int n_goals, int c_begin, int c_end,
+                         int update_prev, f1l_plan_result* out) {
+    if (!h || !pose || !out) return F1L_ERR_INVALID_ARG;
+    if (n_opp < 0 || n_opp > F1L_MAX_OPP || (n_opp > 0 && !opp)) return F1L_ERR_INVALID_ARG;
+    if (h->n < 2) return F1L_ERR_NO_TRACK;
+    CK(cudaSetDevice(h->device));
+    const int C = goals ? n_goals : h->nL * h->nW;
+    if (C <= 0) return F1L_ERR_NO_GOALS;
+    const int M = h->cfg.n_samples;
+    cudaStream_t st = h->stream;
+
+    // stage inputs (pinned) -> device
+    double* hin = (double*)h->h_in;
+    memcpy(hin, pose, 4 * sizeof(double));
+    if (n_opp) memcpy(hin + 4, opp, (size_t)n_opp * 3 * sizeof(double));
+    ENS(h->q_in, (4 + 3 * F1L_MAX_OPP) * sizeof(double));
+    ENS(h->q_ctx, sizeof(QueryCtx));
+    ENS(h->q_centres, sizeof(Centre) * (size_t)(h->nL > 0 ? h->nL : 1));
+    ENS(h->q_best, 8);
+    ENS(h->q_idx, 4);
+    ENS(h->q_cost, 4);
+    ENS(h->q_status, 8);
+    ENS(h->q_ss, 16);
+    ENS(h->q_traj, F1L_MAX_M * sizeof(float4));
+    ENS(h->q_costs, (size_t)C * 4);
+    ENS(h->prev, F1L_MAX_M * sizeof(float));
+    if (out->terms) ENS(h->q_terms, (size_t)C * F1L_N_TERMS * 4);
+    if (out->flags) ENS(h->q_flags, (size_t)C);
+    if (out->goals) ENS(h->q_gout, (size_t)C * 3 * 4);
+    if (out->params) ENS(h->q_params, (size_t)C * 16);
+    if (out->states) ENS(h->q_states, (size_t)C * M * 16);
+    CK(cudaMemcpyAsync(h->q_in.p, hin, (4 + 3 * (size_t)n_opp) * sizeof(double),
+                       cudaMemcpyHostToDevice, st));
+    const float4* d_goals = nullptr;
+    if (goals) {
+        std::vector<float> g4(4 * (size_t)C);
+        for (int c = 0; c < C; ++c) {
+            g4[4 * c] = (float)goals[3 * c];
+            g4[4 * c + 1] = (float)goals[3 * c + 1];
+            g4[4 * c + 2] = (float)goals[3 * c + 2];
+            g4[4 * c + 3] = 0.0f;
+        }
+        ENS(h->q_goals, (size_t)C * 16);
+        CK(cudaMemcpyAsync(h->q_goals.p, g4.data(), (size_t)C * 16, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));  // g4 is a stack-lifetime staging buffer
+        d_goals = (const float4*)h->q_goals.p;
+    }
+
+    BatchOut o;
+    o.best_idx = (int32_t*)h->q_idx.p;
+    o.best_cost = (float*)h->q_cost.p;
+    o.status = (int32_t*)h->q_status.p;
+    o.steer_speed = (double*)h->q_ss.p;
+    o.best_traj = (float4*)h->q_traj.p;
+    o.costs = (float*)h->q_costs.p;
+    o.terms = out->terms ? (float*)h->q_terms.p : nullptr;
+    o.flags = out->flags ? (uint8_t*)h->q_flags.p : nullptr;
+    o.goals_out = out->goals ? (float*)h->q_gout.p : nullptr;
+    o.params = out->params ? (float4*)h->q_params.p : nullptr;
+    o.states = out->states ? (float4*)h->q_states.p : nullptr;
+    o.prev_out = update_prev ? (float*)h->prev.p : nullptr;
+    if (c_begin != 0 || (c_end > 0 && c_end < C)) {
+        // sharded evaluation: untouched candidates keep +inf / zero flags
+        fill_f32_kernel<<<(C + 255) / 256, 256, 0, st>>>((float*)h->q_costs.p, (size_t)C, INFINITY);
+        h->launches += 1;
+        if (o.flags) CK(cudaMemsetAsync(h->q_flags.p, 0, (size_t)C, st));
+    }
+    // the similarity term must read the previous path while select overwrites it: eval reads
+    // prev before select runs (stream order), so one buffer suffices.
+    int r = launch_pipeline(h, st, (const double*)h->q_in.p,
+                            n_opp ? (const double*)h->q_in.p + 4 : nullptr, nullptr, 1, n_opp,
+                            d_goals, C, c_begin, c_end, (QueryCtx*)h->q_ctx.p,
+                            (Centre*)h->q_centres.p, (unsigned long long*)h->q_best.p,
+                            h->has_prev ? (const float*)h->prev.p : nullptr, o, h->timing != 0);
+    if (r != F1L_OK) return r;
+
+    // results -> pinned staging -> caller
+    QHeader* hd = (QHeader*)h->h_out;
+    float* htraj = (float*)((char*)h->h_out + sizeof(QHeader));
+    CK(cudaMemcpyAsync(&hd->steer, h->q_ss.p, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hd->best_idx, h->q_idx.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hd->no_feasible, h->q_status.p, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&hd->best_cost, h->q_cost.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(htraj, h->q_traj.p, (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+    if (out->costs) CK(cudaMemcpyAsync(out->costs, h->q_costs.p, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
+    if (out->terms) CK(cudaMemcpyAsync(out->terms, h->q_terms.p, (size_t)C * F1L_N_TERMS * 4, cudaMemcpyDeviceToHost, st));
+    if (out->flags) CK(cudaMemcpyAsync(out->flags, h->q_flags.p, (size_t)C, cudaMemcpyDeviceToHost, st));
+    if (out->goals) CK(cudaMemcpyAsync(out->goals, h->q_gout.p, (size_t)C * 12, cudaMemcpyDeviceToHost, st));
+    if (out->params) CK(cudaMemcpyAsync(out->params, h->q_params.p, (size_t)C * 16, cudaMemcpyDeviceToHost, st));
+    if (out->states) CK(cudaMemcpyAsync(out->states, h->q_states.p, (size_t)C * M * 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h->timing) {
+        cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[1]);
+        cudaEventElapsedTime(&h->last_ms[1], h->ev[1], h->ev[2]);
+        cudaEventElapsedTime(&h->last_ms[2], h->ev[2], h->ev[3]);
+    }
+    if (update_prev) {
+        h->has_prev = 1;
+        h->prev_m = M;
+    }
+    out->steer = hd->steer;
+    out->speed = hd->speed;
+    out->best_idx = hd->best_idx;
+    out->no_feasible = hd->no_feasible;
+    out->tracker_found = hd->tracker_found;
+    out->n_candidates = C;
+    out->best_cost = hd->best_cost;
+    if (out->best_traj) memcpy(out->best_traj, htraj, (size_t)M * 16);
+    return F1L_OK;
+}
+
+int f1l_plan(f1l_handle h, const double pose[4], const double* opp, int n_opp, int update_prev,
+             f1l_plan_result* out) {
+    return plan_internal(h, pose, opp, n_opp, nullptr, 0, 0, 0, update_prev, out);
+}
+
+int f1l_plan_shard(f1l_handle h, const double pose[4], const double* opp, int n_opp, int c_begin,
+                   int c_end, f1l_plan_result* out) {
+    return plan_internal(h, pose, opp, n_opp, nullptr, 0, c_begin, c_end, 0, out);
+}
+
+int f1l_plan_goals(f1l_handle h, const double pose[4], const double* goals, int n_goals,
+                   const double* opp, int n_opp, int update_prev, f1l_plan_result* out) {
+    if (!goals || n_goals <= 0) return F1L_ERR_INVALID_ARG;
+    return plan_internal(h, pose, opp, n_opp, goals, n_goals, 0, 0, update_prev, out);
+}
+
+int f1l_generate(f1l_handle h, const double* goals, int n_goals, float* states, float* params,
+                 uint8_t* flags) {
+    if (!h || !goals || n_goals <= 0 || !states) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    const int C = n_goals, M = h->cfg.n_samples;
+    std::vector<float> g4(4 * (size_t)C);
+    for (int c = 0; c < C; ++c) {
+        g4[4 * c] = (float)goals[3 * c];
+        g4[4 * c + 1] = (float)goals[3 * c + 1];
+        g4[4 * c + 2] = (float)goals[3 * c + 2];
+        g4[4 * c + 3] = 0.0f;
+    }
+    ENS(h->q_goals, (size_t)C * 16);
+    ENS(h->q_states, (size_t)C * M * 16);
+    ENS(h->q_params, (size_t)C * 16);
+    ENS(h->q_flags, (size_t)C);
+    cudaStream_t st = h->stream;
+    CK(cudaMemcpyAsync(h->q_goals.p, g4.data(), (size_t)C * 16, cudaMemcpyHostToDevice, st));
+    const int wpc = 8;
+    generate_entry(M)<<<(C + wpc - 1) / wpc, wpc * 32, 0, st>>>(
+        lut_view(h), eval_params(h), (const float4*)h->q_goals.p, C, (float4*)h->q_states.p,
+        (float4*)h->q_params.p, (uint8_t*)h->q_flags.p);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(states, h->q_states.p, (size_t)C * M * 16, cudaMemcpyDeviceToHost, st));
+    if (params) CK(cudaMemcpyAsync(params, h->q_params.p, (size_t)C * 16, cudaMemcpyDeviceToHost, st));
+    if (flags) CK(cudaMemcpyAsync(flags, h->q_flags.p, (size_t)C, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return F1L_OK;
+}
+
+// ---- batch --------------------------------------------------------------------------------
+int f1l_plan_batch_dev(f1l_handle h, const double* poses_dev, const double* opp_dev,
+                       const int32_t* n_opp_dev, int S, int max_opp, int32_t* best_idx_dev,
+                       float* best_cost_dev, float* best_traj_dev, float* costs_dev,
+                       uint8_t* flags_dev, double* steer_speed_dev, void* stream) {
+    if (!h || !poses_dev || S <= 0) return F1L_ERR_INVALID_ARG;
+    if (max_opp > 0 && !opp_dev) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (h->nL * h->nW <= 0) return F1L_ERR_NO_GOALS;
+    ENS(h->b_ctx, sizeof(QueryCtx) * (size_t)S);
+    ENS(h->b_centres, sizeof(Centre) * (size_t)S * h->nL);
+    ENS(h->b_best, 8 * (size_t)S);
+    BatchOut o;
+    o.best_idx = best_idx_dev;
+    o.best_cost = best_cost_dev;
+    o.best_traj = (float4*)best_traj_dev;
+    o.costs = costs_dev;
+    o.flags = flags_dev;
+    o.steer_speed = steer_speed_dev;
+    return launch_pipeline(h, (cudaStream_t)stream, poses_dev, max_opp > 0 ? opp_dev : nullptr,
+                           n_opp_dev, S, max_opp, nullptr, 0, 0, 0, (QueryCtx*)h->b_ctx.p,
+                           (Centre*)h->b_centres.p, (unsigned long long*)h->b_best.p, nullptr, o,
+                           false);
+}
+
+int f1l_plan_batch(f1l_handle h, const double* poses, const double* opp, const int32_t* n_opp,
+                   int S, int max_opp, int32_t* best_idx, float* best_cost, float* best_traj,
+                   float* costs, uint8_t* flags, double* steer_speed) {
+    if (!h || !poses || S <= 0) return F1L_ERR_INVALID_ARG;
+    if (max_opp > 0 && !opp) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    const int C = h->nL * h->nW;
+    if (C <= 0) return F1L_ERR_NO_GOALS;
+    const int M = h->cfg.n_samples;
+    // chunked 3-stream pipeline: H2D(i+1) | kernels(i) | D2H(i-1)
+    int chunk = 8192;
+    if (S < chunk * N_PIPE) chunk = (S + N_PIPE - 1) / N_PIPE;
+    if (chunk < 1) chunk = 1;
+    int slot = 0;
+    for (int s0 = 0; s0 < S; s0 += chunk, slot = (slot + 1) % N_PIPE) {
+        const int n = (S - s0 < chunk) ? (S - s0) : chunk;
+        PipeSlot& p = h->pipe[slot];
+        cudaStream_t st = p.stream;
+        CK(cudaStreamSynchronize(st));  // slot buffers free again (grow-only ensure below)
+        ENS(p.poses, (size_t)n * 32);
+        if (max_opp > 0) ENS(p.opp, (size_t)n * max_opp * 24);
+        if (n_opp) ENS(p.nopp, (size_t)n * 4);
+        ENS(p.ctx, sizeof(QueryCtx) * (size_t)n);
+        ENS(p.centres, sizeof(Centre) * (size_t)n * h->nL);
+        ENS(p.best, 8 * (size_t)n);
+        if (best_idx) ENS(p.idx, (size_t)n * 4);
+        if (best_cost) ENS(p.cost, (size_t)n * 4);
+        if (best_traj) ENS(p.traj, (size_t)n * M * 16);
+        if (costs) ENS(p.costs, (size_t)n * C * 4);
+        if (flags) ENS(p.flags, (size_t)n * C);
+        if (steer_speed) ENS(p.ss, (size_t)n * 16);
+        CK(cudaMemcpyAsync(p.poses.p, poses + 4 * (size_t)s0, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+        if (max_opp > 0)
+            CK(cudaMemcpyAsync(p.opp.p, opp + 3 * (size_t)max_opp * s0, (size_t)n * max_opp * 24,
+                               cudaMemcpyHostToDevice, st));
+        if (n_opp) CK(cudaMemcpyAsync(p.nopp.p, n_opp + s0, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        BatchOut o;
+        o.best_idx = best_idx ? (int32_t*)p.idx.p : nullptr;
+        o.best_cost = best_cost ? (float*)p.cost.p : nullptr;
+        o.best_traj = best_traj ? (float4*)p.traj.p : nullptr;
+        o.costs = costs ? (float*)p.costs.p : nullptr;
+        o.flags = flags ? (uint8_t*)p.flags.p : nullptr;
+        o.steer_speed = steer_speed ? (double*)p.ss.p : nullptr;
+        int r = launch_pipeline(h, st, (const double*)p.poses.p,
+                                max_opp > 0 ? (const double*)p.opp.p : nullptr,
+                                n_opp ? (const int32_t*)p.nopp.p : nullptr, n, max_opp, nullptr, 0,
+                                0, 0, (QueryCtx*)p.ctx.p, (Centre*)p.centres.p,
+                                (unsigned long long*)p.best.p, nullptr, o, false);
+        if (r != F1L_OK) return r;
+        if (best_idx) CK(cudaMemcpyAsync(best_idx + s0, p.idx.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (best_cost) CK(cudaMemcpyAsync(best_cost + s0, p.cost.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (best_traj)
+            CK(cudaMemcpyAsync(best_traj + 4 * (size_t)M * s0, p.traj.p, (size_t)n * M * 16,
+                               cudaMemcpyDeviceToHost, st));
+        if (costs) CK(cudaMemcpyAsync(costs + (size_t)C * s0, p.costs.p, (size_t)n * C * 4, cudaMemcpyDeviceToHost, st));
+        if (flags) CK(cudaMemcpyAsync(flags + (size_t)C * s0, p.flags.p, (size_t)n * C, cudaMemcpyDeviceToHost, st));
+        if (steer_speed) CK(cudaMemcpyAsync(steer_speed + 2 * (size_t)s0, p.ss.p, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < N_PIPE; ++i) CK(cudaStreamSynchronize(h->pipe[i].stream));
+    return F1L_OK;
+}
+
+// ---- pure pursuit -------------------------------------------------------------------------
+int f1l_pure_pursuit_batch_dev(f1l_handle h, const double* poses_dev, int n_poses, double L,
+                               double* nearest_dev, int32_t* nearest_i_dev, double* lookahead_dev,
+                               int32_t* lookahead_i_dev, double* actuation_dev,
+                               int32_t* status_dev, void* stream) {
+    if (!h || !poses_dev || n_poses <= 0) return F1L_ERR_INVALID_ARG;
+    if (h->n < 2) return F1L_ERR_NO_TRACK;
+    CK(cudaSetDevice(h->device));
+    PPOut o;
+    o.nearest = nearest_dev;
+    o.nearest_i = nearest_i_dev;
+    o.lookahead = lookahead_dev;
+    o.lookahead_i = lookahead_i_dev;
+    o.actuation = actuation_dev;
+    o.status = status_dev;
+    const int blocks = (n_poses + PP_THREADS - 1) / PP_THREADS;
+    pp_batch_kernel<<<blocks, PP_THREADS, PP_SMEM_BYTES, (cudaStream_t)stream>>>(
+        track_view(h), poses_dev, n_poses, L, h->cfg.wheelbase, h->cfg.max_reacquire, o);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return F1L_OK;
+}
+
+int f1l_pure_pursuit_batch(f1l_handle h, const double* poses, int n, double L, double* nearest,
+                           int32_t* nearest_i, double* lookahead, int32_t* lookahead_i,
+                           double* actuation, int32_t* status) {
+    if (!h || !poses || n <= 0) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    ENS(h->m_in, (size_t)n * 24);
+    if (nearest) ENS(h->m_o0, (size_t)n * 32);
+    if (nearest_i) ENS(h->m_o1, (size_t)n * 4);
+    if (lookahead) ENS(h->m_o2, (size_t)n * 32);
+    if (lookahead_i) ENS(h->m_o3, (size_t)n * 4);
+    if (actuation) ENS(h->m_o4, (size_t)n * 16);
+    if (status) ENS(h->m_o5, (size_t)n * 4);
+    CK(cudaMemcpyAsync(h->m_in.p, poses, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    int r = f1l_pure_pursuit_batch_dev(
+        h, (const double*)h->m_in.p, n, L, nearest ? (double*)h->m_o0.p : nullptr,
+        nearest_i ? (int32_t*)h->m_o1.p : nullptr, lookahead ? (double*)h->m_o2.p : nullptr,
+        lookahead_i ? (int32_t*)h->m_o3.p : nullptr, actuation ? (double*)h->m_o4.p : nullptr,
+        status ? (int32_t*)h->m_o5.p : nullptr, st);
+    if (r != F1L_OK) return r;
+    if (nearest) CK(cudaMemcpyAsync(nearest, h->m_o0.p, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    if (nearest_i) CK(cudaMemcpyAsync(nearest_i, h->m_o1.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (lookahead) CK(cudaMemcpyAsync(lookahead, h->m_o2.p, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    if (lookahead_i) CK(cudaMemcpyAsync(lookahead_i, h->m_o3.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if (actuation) CK(cudaMemcpyAsync(actuation, h->m_o4.p, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    if (status) CK(cudaMemcpyAsync(status, h->m_o5.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return F1L_OK;
+}
+
+int f1l_intersect_point_batch(f1l_handle h, const double* points, const double* t_start, int n,
+                              double radius, int wrap, double* out, int32_t* out_i) {
+    if (!h || !points || !t_start || n <= 0 || !out || !out_i) return F1L_ERR_INVALID_ARG;
+    if (h->n < 2) return F1L_ERR_NO_TRACK;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    ENS(h->m_in, (size_t)n * 16);
+    ENS(h->m_in2, (size_t)n * 8);
+    ENS(h->m_o0, (size_t)n * 32);
+    ENS(h->m_o1, (size_t)n * 4);
+    CK(cudaMemcpyAsync(h->m_in.p, points, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->m_in2.p, t_start, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    intersect_batch_kernel<<<(n + 63) / 64, 64, 0, st>>>(
+        track_view(h), (const double*)h->m_in.p, (const double*)h->m_in2.p, n, radius, wrap,
+        (double*)h->m_o0.p, (int32_t*)h->m_o1.p);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->m_o0.p, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_i, h->m_o1.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return F1L_OK;
+}
+
+int f1l_get_actuation_batch(f1l_handle h, const double* in, int n, double wheelbase, double* out) {
+    if (!h || !in || n <= 0 || !out) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    ENS(h->m_in, (size_t)n * 56);
+    ENS(h->m_o0, (size_t)n * 16);
+    CK(cudaMemcpyAsync(h->m_in.p, in, (size_t)n * 56, cudaMemcpyHostToDevice, st));
+    actuation_batch_kernel<<<(n + 63) / 64, 64, 0, st>>>((const double*)h->m_in.p, n, wheelbase,
+                                                         (double*)h->m_o0.p);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->m_o0.p, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return F1L_OK;
+}
+
+// debug: the last single query's context (teacher-forced collision tests):
+// out[0..1] cos/sin pose, [2..7] grid A00 A01 A10 A11 fx fy, [8..9] gix giy (as float bits via
+// int copy), [10..] opponents 16 x (x, y, cos, sin)
+int f1l_debug_query_ctx(f1l_handle h, float* out_f, int32_t* out_i) {
+    if (!h || !out_f || !out_i || !h->q_ctx.p) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    QueryCtx q;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(&q, h->q_ctx.p, sizeof(q), cudaMemcpyDeviceToHost));
+    out_f[0] = q.cth; out_f[1] = q.sth;
+    out_f[2] = q.gA00; out_f[3] = q.gA01; out_f[4] = q.gA10; out_f[5] = q.gA11;
+    out_f[6] = q.gfx; out_f[7] = q.gfy;
+    for (int k = 0; k < F1L_MAX_OPP; ++k) {
+        out_f[8 + 4 * k] = q.opp[k].x; out_f[9 + 4 * k] = q.opp[k].y;
+        out_f[10 + 4 * k] = q.opp[k].z; out_f[11 + 4 * k] = q.opp[k].w;
+    }
+    out_i[0] = q.gix; out_i[1] = q.giy; out_i[2] = q.i_ego; out_i[3] = q.seg0;
+    out_i[4] = q.nseg; out_i[5] = q.n_opp;
+    return F1L_OK;
+}
+
+int f1l_measure_peaks(f1l_handle h, double* fp32_tflops, double* mufu_gops) {
+    if (!h) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    ENS(h->m_o0, (size_t)h->sm_count * 8 * 256 * 4);
+    cudaStream_t st = h->stream;
+    const int blocks = h->sm_count * 8, threads = 256, iters = 4096;
+    float ms = 0.f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(h->ev[0], st));
+        ffma_peak_kernel<<<blocks, threads, 0, st>>>((float*)h->m_o0.p, iters, 1.0001f, 0.5f);
+        CK(cudaEventRecord(h->ev[1], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    }
+    h->launches += 3;
+    if (fp32_tflops)
+        *fp32_tflops = 2.0 * PEAK_CHAINS * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(h->ev[0], st));
+        mufu_peak_kernel<<<blocks, threads, 0, st>>>((float*)h->m_o0.p, iters);
+        CK(cudaEventRecord(h->ev[1], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    }
+    h->launches += 3;
+    if (mufu_gops)
+        *mufu_gops = (double)PEAK_CHAINS * iters * blocks * threads / (ms * 1e-3) / 1e9;
+    CK(cudaGetLastError());
+    return F1L_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,234 @@
+// f1l_common.cuh -- shared device structs and helpers for the sm_100a lattice-planner kernels.
+//
+// Reference citations are into f1tenth_planning/ of the upstream repo.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/f1l.h"
+
+#define F1L_WARP 32
+#define F1L_FULL 0xffffffffu
+#define F1L_MAX_LOOKAHEADS 1024
+
+// ---------------------------------------------------------------------------------------------
+// device-side views
+// ---------------------------------------------------------------------------------------------
+struct TrackView {
+    int n;                 // waypoints
+    int ncols;             // columns uploaded (2..5)
+    const double2* xy;     // [n] map frame, float64 (exact copy of the host array)
+    const double* v;       // [n] column 2 (speed) or zeros
+    const double* psi;     // [n] column 3 or zeros
+    const double* kappa;   // [n] column 4 or zeros
+    // float32 line form of the n-1 open segments in block-local frames (pure-pursuit scan):
+    //   segA[k] = (ux, uy, c, e): unit direction, c = a.u, e = a.n with a relative to the origin
+    //   of block k/32 and n = (-uy, ux);  segB[k] = (len, 1/len)
+    const float4* segA;
+    const float2* segB;
+    const double2* blk_origin;  // [ceil((n-1)/32)]
+};
+
+struct GridView {
+    const uint8_t* occ;  // [h, w] row-major, 0 free
+    int h, w;
+    double ox, oy, inv_res;
+};
+
+struct LutView {
+    const float4* cells;  // [nx, ny, nt] (p1, p2, s_f, converged)
+    int nx, ny, nt;
+    float x0, y0, t0;     // axis origins
+    float sx, sy, st;     // (n-1)/(hi-lo) per axis (0 when n == 1)
+};
+
+// planner constants in the types the kernels use
+struct EvalParams {
+    int M;            // arc samples
+    int n_newton;
+    int window;       // requested window (<=0: all)
+    int n_shift, n_cull;
+    int literal_tracker, use_goal_kappa;
+    float w[F1L_N_TERMS];
+    float kappa_max;  // <= 0: off
+    float half_l, half_w;
+    float rc2;        // (2 r_circ)^2 broad-phase radius
+    float tol;
+    double tracker_lookahead, wheelbase, max_reacquire;
+};
+
+// per-scenario context written by the sampler kernel, read by eval / select
+struct __align__(16) QueryCtx {
+    double px, py, th, vel;
+    float cth, sth;        // cos / sin of the pose heading
+    int i_ego;             // nearest open-polyline segment (utils.py:66)
+    int seg0, nseg;        // cyclic raceline window [seg0, seg0+nseg) over the n-1 segments
+    int n_opp;
+    int has_grid;
+    int pad0;
+    // vehicle frame -> grid cell coordinates: cell = i0 + floor(A * (x, y) + f)
+    float gA00, gA01, gA10, gA11, gfx, gfy;
+    int gix, giy;
+    float4 opp[F1L_MAX_OPP];  // vehicle frame (x, y, cos phi, sin phi)
+};
+
+// per lookahead row: goal centre in the vehicle frame
+struct __align__(16) Centre {
+    float cx, cy, psi_rel, kappa_g;  // centre xy, wrap(psi - theta), raceline curvature
+    float nx, ny, v, ok;             // unit normal (-sin psi_rel, cos psi_rel), raceline speed, found
+};
+
+// ---------------------------------------------------------------------------------------------
+// float64 helpers that follow the reference operation by operation (no FMA contraction)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dsub_rn(a, b); }
+
+struct Nearest64 {
+    double px, py, dist, t;
+    int i;
+};
+
+// one segment of nearest_point (utils/utils.py:53-65)
+__device__ __forceinline__ void nearest_segment64(double qx, double qy, double ax, double ay,
+                                                  double bx, double by, double& px, double& py,
+                                                  double& dist, double& t) {
+    const double dx = xsub(bx, ax), dy = xsub(by, ay);                       // :53
+    const double l2 = xadd(xmul(dx, dx), xmul(dy, dy));                       // :54
+    const double dot = xadd(xmul(xsub(qx, ax), dx), xmul(xsub(qy, ay), dy));  // :57
+    double tt = __ddiv_rn(dot, l2);                                           // :58
+    if (tt < 0.0) tt = 0.0;                                                   // :59
+    if (tt > 1.0) tt = 1.0;                                                   // :60
+    px = xadd(ax, xmul(tt, dx));                                              // :61
+    py = xadd(ay, xmul(tt, dy));
+    const double ex = xsub(qx, px), ey = xsub(qy, py);                        // :64
+    dist = __dsqrt_rn(xadd(xmul(ex, ex), xmul(ey, ey)));                      // :65
+    t = tt;
+}
+
+// lexicographic (dist, index) minimum == np.argmin first-minimum rule (utils.py:66)
+__device__ __forceinline__ bool nearest_better(double d, int i, double bd, int bi) {
+    return d < bd || (d == bd && i < bi);
+}
+
+// python-style modulo
+__device__ __forceinline__ int pymod(int a, int n) {
+    int r = a % n;
+    return r < 0 ? r + n : r;
+}
+
+// accessor concept: P(i) returns double2 waypoint i
+struct XYTrack {
+    const double2* xy;
+    __device__ __forceinline__ double2 operator()(int i) const { return xy[i]; }
+};
+struct XYTraj4 {  // float4 trajectory rows (x, y, theta, kappa) widened to float64
+    const float4* st;
+    __device__ __forceinline__ double2 operator()(int i) const {
+        const float4 s = st[i];
+        return make_double2((double)s.x, (double)s.y);
+    }
+};
+
+// one segment test of intersect_point (utils/utils.py:85-101); returns false if disc < 0
+__device__ __forceinline__ bool intersect_segment64(double qx, double qy, double r, double2 s,
+                                                    double2 e0, double& t1, double& t2,
+                                                    double& vx, double& vy) {
+    const double ex = xadd(e0.x, 1e-6), ey = xadd(e0.y, 1e-6);  // :86
+    vx = xsub(ex, s.x);
+    vy = xsub(ey, s.y);
+    const double a = xadd(xmul(vx, vx), xmul(vy, vy));                                  // :89
+    const double b = xmul(2.0, xadd(xmul(vx, xsub(s.x, qx)), xmul(vy, xsub(s.y, qy))));  // :90
+    const double c = xsub(xsub(xadd(xadd(xmul(s.x, s.x), xmul(s.y, s.y)),
+                                    xadd(xmul(qx, qx), xmul(qy, qy))),
+                               xmul(2.0, xadd(xmul(s.x, qx), xmul(s.y, qy)))),
+                          xmul(r, r));                                                   // :91
+    double disc = xsub(xmul(b, b), xmul(xmul(4.0, a), c));                               // :92
+    if (disc < 0.0) return false;                                                        // :94
+    disc = __dsqrt_rn(disc);
+    t1 = __ddiv_rn(xsub(-b, disc), xmul(2.0, a));                                        // :100
+    t2 = __ddiv_rn(xadd(-b, disc), xmul(2.0, a));
+    return true;
+}
+
+struct Intersect64 {
+    double px, py, t;
+    int i;      // un-modded segment index (may be -1, utils.py:125)
+    int found;
+};
+
+// intersect_point (utils/utils.py:69-151), sequential early-exit scan by one thread
+template <class P>
+__device__ inline Intersect64 intersect_point64(const P& pts, int n, double qx, double qy,
+                                                double r, double t, bool wrap) {
+    Intersect64 o;
+    o.px = 0.0; o.py = 0.0; o.t = 0.0; o.i = 0; o.found = 0;
+    const int start_i = (int)t;                 // :78
+    const double start_t = fmod(t, 1.0);        // :79
+    double t1, t2, vx, vy;
+    for (int i = start_i; i < n - 1; ++i) {     // :84
+        const double2 s = pts(i);
+        if (!intersect_segment64(qx, qy, r, s, pts(i + 1), t1, t2, vx, vy)) continue;
+        double tt = -1.0;
+        if (i == start_i) {                     // :102-112
+            if (t1 >= 0.0 && t1 <= 1.0 && t1 >= start_t) tt = t1;
+            else if (t2 >= 0.0 && t2 <= 1.0 && t2 >= start_t) tt = t2;
+        } else if (t1 >= 0.0 && t1 <= 1.0) tt = t1;   // :113
+        else if (t2 >= 0.0 && t2 <= 1.0) tt = t2;     // :118
+        if (tt >= 0.0) {
+            o.t = tt; o.i = i; o.found = 1;
+            o.px = xadd(s.x, xmul(tt, vx)); o.py = xadd(s.y, xmul(tt, vy));
+            return o;
+        }
+    }
+    if (wrap) {                                 // :124
+        for (int i = -1; i < start_i; ++i) {    // :125
+            const double2 s = pts(pymod(i, n));
+            if (!intersect_segment64(qx, qy, r, s, pts(pymod(i + 1, n)), t1, t2, vx, vy)) continue;
+            double tt = -1.0;
+            if (t1 >= 0.0 && t1 <= 1.0) tt = t1;        // :140
+            else if (t2 >= 0.0 && t2 <= 1.0) tt = t2;   // :145
+            if (tt >= 0.0) {
+                o.t = tt; o.i = i; o.found = 1;
+                o.px = xadd(s.x, xmul(tt, vx)); o.py = xadd(s.y, xmul(tt, vy));
+                return o;
+            }
+        }
+    }
+    return o;
+}
+
+// get_actuation (utils/utils.py:153-161): returns steer, passes speed through
+__device__ __forceinline__ double actuation_steer64(double pose_theta, double lx, double ly,
+                                                    double qx, double qy, double L, double wb) {
+    const double wy = xadd(xmul(sin(-pose_theta), xsub(lx, qx)), xmul(cos(-pose_theta), xsub(ly, qy)));
+    if (fabs(wy) < 1e-6) return 0.0;                                   // :157
+    const double radius = __ddiv_rn(1.0, __ddiv_rn(xmul(2.0, wy), xmul(L, L)));  // :159
+    return atan(__ddiv_rn(wb, radius));                                // :160
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(F1L_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(F1L_FULL, v, o));
+    return v;
+}
+
+// order-preserving float -> uint32 map (for the packed 64-bit atomicMin argmin)
+__device__ __forceinline__ uint32_t float_orderable(float f) {
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float orderable_float(uint32_t u) {
+    const uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(b);
+}

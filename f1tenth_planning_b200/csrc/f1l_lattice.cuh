@@ -1,0 +1,886 @@
+// f1l_lattice.cuh -- K2 sampler, K3+K4 fused spiral generation / cost / collision, K5 select.
+//
+// One warp per candidate.  FP32 FMA + MUFU math; float64 only where the reference's own float64
+// functions are being reproduced (sampler nearest/intersect, tracker).
+//
+//   sample_kernel  : per scenario -- nearest_point on the raceline, one intersect_point per
+//                    lookahead row, goal centres, ego-frame opponents, grid transform, window.
+//                    (intent of lattice_planner.py:223-260)
+//   eval_kernel    : per candidate -- LUT seed, I Newton steps on (p1, p2, s_f) with a 32-node
+//                    Simpson rule (one node per lane), M arc samples by per-interval Simpson and
+//                    a warp scan, cost terms (lattice_planner.py:268-296 + raceline deviation
+//                    with nearest_point semantics, utils.py:37-67), rectangle-vs-opponent SAT and
+//                    occupancy-grid probes, packed 64-bit atomicMin argmin
+//                    (lattice_planner.py:159-172).
+//   select_kernel  : per scenario -- decode the argmin, regenerate the winning trajectory, run
+//                    the pure-pursuit tracker on it (lattice_planner.py:204-214).
+#pragma once
+#include "f1l_common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// cubic spiral, FP32
+// ---------------------------------------------------------------------------------------------
+struct SpiralF {
+    float p0, p3;
+    float p1, p2, sf;
+    float h1, h2, h3;  // b1/2, b2/3, b3/4   (theta polynomial)
+    float b1, b2, b3;  // curvature polynomial
+};
+
+__device__ __forceinline__ void spiral_set(SpiralF& s) {
+    s.b1 = 0.5f * (-11.0f * s.p0 + 18.0f * s.p1 - 9.0f * s.p2 + 2.0f * s.p3);
+    s.b2 = 0.5f * (18.0f * s.p0 - 45.0f * s.p1 + 36.0f * s.p2 - 9.0f * s.p3);
+    s.b3 = 0.5f * (-9.0f * s.p0 + 27.0f * s.p1 - 27.0f * s.p2 + 9.0f * s.p3);
+    s.h1 = 0.5f * s.b1;
+    s.h2 = (1.0f / 3.0f) * s.b2;
+    s.h3 = 0.25f * s.b3;
+}
+__device__ __forceinline__ float spiral_g(const SpiralF& s, float u) {
+    return u * fmaf(u, fmaf(u, fmaf(u, s.h3, s.h2), s.h1), s.p0);
+}
+__device__ __forceinline__ float spiral_kappa(const SpiralF& s, float u) {
+    return fmaf(u, fmaf(u, fmaf(u, s.b3, s.b2), s.b1), s.p0);
+}
+
+// all-reduce (sum) of 8 values per lane with 9 + 8 shuffles instead of 40: three halving steps
+// leave each lane with one partial column, two full steps finish it, then 8 broadcasts.
+__device__ __forceinline__ void warp_allreduce8(float (&v)[8], int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+    float a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float keep = h16 ? v[j + 4] : v[j];
+        const float send = h16 ? v[j] : v[j + 4];
+        a[j] = keep + __shfl_xor_sync(F1L_FULL, send, 16);
+    }
+    float b[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const float keep = h8 ? a[j + 2] : a[j];
+        const float send = h8 ? a[j] : a[j + 2];
+        b[j] = keep + __shfl_xor_sync(F1L_FULL, send, 8);
+    }
+    float c;
+    {
+        const float keep = h4 ? b[1] : b[0];
+        const float send = h4 ? b[0] : b[1];
+        c = keep + __shfl_xor_sync(F1L_FULL, send, 4);
+    }
+    c += __shfl_xor_sync(F1L_FULL, c, 2);
+    c += __shfl_xor_sync(F1L_FULL, c, 1);
+    // lane l now holds the total of column ((l>>4)&1)*4 + ((l>>3)&1)*2 + ((l>>2)&1)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int src = ((j & 4) ? 16 : 0) + ((j & 2) ? 8 : 0) + ((j & 1) ? 4 : 0);
+        v[j] = __shfl_sync(F1L_FULL, c, src);
+    }
+}
+
+// I fixed Newton steps q <- q - J^-1 r, whole warp, lane = Simpson node (lane+1)/32 (node 0 is
+// analytic: cos 0 = 1 and every other integrand vanishes there).
+__device__ __forceinline__ void spiral_newton(SpiralF& sp, float gx, float gy, float gth,
+                                              int iters, int lane) {
+    const float u = (float)(lane + 1) * (1.0f / 32.0f);
+    const float w = (lane == 31) ? (1.0f / 96.0f) : (((lane + 1) & 1) ? (4.0f / 96.0f) : (2.0f / 96.0f));
+    const float u2 = u * u;
+    const float d1 = u2 * fmaf(u, fmaf(u, 3.375f, -7.5f), 4.5f);
+    const float d2 = u2 * fmaf(u, fmaf(u, -3.375f, 6.0f), -2.25f);
+    for (int it = 0; it < iters; ++it) {
+        spiral_set(sp);
+        const float g = spiral_g(sp, u);
+        float s, c;
+        __sincosf(sp.sf * g, &s, &c);
+        const float wc = w * c, ws = w * s;
+        float v[8] = {wc, ws, wc * g, ws * g, wc * d1, ws * d1, wc * d2, ws * d2};
+        warp_allreduce8(v, lane);
+        const float C0 = v[0] + (1.0f / 96.0f), S0 = v[1], Cg = v[2], Sg = v[3];
+        const float C1 = v[4], S1 = v[5], C2 = v[6], S2 = v[7];
+        const float sf = sp.sf, sf2 = sf * sf;
+        const float g1 = 0.125f * (sp.p0 + 3.0f * sp.p1 + 3.0f * sp.p2 + sp.p3);
+        const float r0 = fmaf(sf, C0, -gx), r1 = fmaf(sf, S0, -gy), r2 = fmaf(sf, g1, -gth);
+        const float J00 = -sf2 * S1, J01 = -sf2 * S2, J02 = fmaf(-sf, Sg, C0);
+        const float J10 = sf2 * C1, J11 = sf2 * C2, J12 = fmaf(sf, Cg, S0);
+        const float J20 = 0.375f * sf, J21 = J20, J22 = g1;
+        const float m0 = J11 * J22 - J12 * J21, m1 = J10 * J22 - J12 * J20, m2 = J10 * J21 - J11 * J20;
+        const float det = J00 * m0 - J01 * m1 + J02 * m2;
+        const float inv = __fdividef(1.0f, det);
+        const float n0 = r1 * J22 - J12 * r2, n1 = r1 * J21 - J11 * r2, n2 = J10 * r2 - r1 * J20;
+        const float dq0 = (r0 * m0 - J01 * n0 + J02 * n1) * inv;
+        const float dq1 = (J00 * n0 - r0 * m1 + J02 * n2) * inv;
+        const float dq2 = (-J00 * n1 - J01 * n2 + r0 * m2) * inv;
+        sp.p1 -= dq0;
+        sp.p2 -= dq1;
+        sp.sf -= dq2;
+    }
+    spiral_set(sp);
+}
+
+// nearest-cell LUT seed
+__device__ __forceinline__ float4 lut_lookup(const LutView& lut, float gx, float gy, float gth) {
+    int ix = __float2int_rd(fmaf(gx - lut.x0, lut.sx, 0.5f));
+    int iy = __float2int_rd(fmaf(gy - lut.y0, lut.sy, 0.5f));
+    int it = __float2int_rd(fmaf(gth - lut.t0, lut.st, 0.5f));
+    ix = min(max(ix, 0), lut.nx - 1);
+    iy = min(max(iy, 0), lut.ny - 1);
+    it = min(max(it, 0), lut.nt - 1);
+    return __ldg(lut.cells + ((size_t)ix * lut.ny + iy) * lut.nt + it);
+}
+
+// M arc samples, lane l owns samples [l*IPL, (l+1)*IPL).  Per-interval Simpson
+// dx_i = h/6 (cos th_{i-1} + 4 cos th_{i-1/2} + cos th_i), inclusive prefix by a warp scan.
+template <int IPL>
+__device__ __forceinline__ void spiral_sample(const SpiralF& sp, int M, int lane, float (&x)[IPL],
+                                              float (&y)[IPL], float (&th)[IPL], float (&kp)[IPL],
+                                              float (&cs)[IPL], float (&sn)[IPL]) {
+    const float inv = 1.0f / (float)(M - 1);
+    const float h6 = sp.sf * inv * (1.0f / 6.0f);
+    const int i0 = lane * IPL;
+#pragma unroll
+    for (int j = 0; j < IPL; ++j) {
+        const float u = (float)(i0 + j) * inv;
+        th[j] = sp.sf * spiral_g(sp, u);
+        kp[j] = spiral_kappa(sp, u);
+        __sincosf(th[j], &sn[j], &cs[j]);
+    }
+    // cos/sin at the node before this lane's first sample
+    float cprev = __shfl_up_sync(F1L_FULL, cs[IPL - 1], 1);
+    float sprev = __shfl_up_sync(F1L_FULL, sn[IPL - 1], 1);
+    float accx = 0.0f, accy = 0.0f;
+#pragma unroll
+    for (int j = 0; j < IPL; ++j) {
+        const int i = i0 + j;
+        const float um = ((float)i - 0.5f) * inv;
+        float sm, cm;
+        __sincosf(sp.sf * spiral_g(sp, um), &sm, &cm);
+        float dx = h6 * (cprev + 4.0f * cm + cs[j]);
+        float dy = h6 * (sprev + 4.0f * sm + sn[j]);
+        if (i == 0 || i >= M) { dx = 0.0f; dy = 0.0f; }
+        accx += dx;
+        accy += dy;
+        x[j] = accx;
+        y[j] = accy;
+        cprev = cs[j];
+        sprev = sn[j];
+    }
+    // exclusive scan of the lane totals
+    float ix = accx, iy = accy;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float nx = __shfl_up_sync(F1L_FULL, ix, o);
+        const float ny = __shfl_up_sync(F1L_FULL, iy, o);
+        if (lane >= o) { ix += nx; iy += ny; }
+    }
+    const float ox = ix - accx, oy = iy - accy;
+#pragma unroll
+    for (int j = 0; j < IPL; ++j) { x[j] += ox; y[j] += oy; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernel arguments
+// ---------------------------------------------------------------------------------------------
+struct SampleArgs {
+    TrackView tr;
+    GridView grid;
+    EvalParams ep;
+    const double* poses;     // [S,4]
+    const double* opp;       // [S,max_opp,3] or null
+    const int32_t* n_opp;    // [S] or null (-> max_opp)
+    int max_opp;
+    const double* lookaheads;  // [nL] device
+    int nL;                    // 0 in explicit-goal mode
+    QueryCtx* ctx;             // [S]
+    Centre* centres;           // [S,nL]
+    unsigned long long* best;  // [S]
+};
+
+struct EvalArgs {
+    TrackView tr;
+    GridView grid;
+    LutView lut;
+    EvalParams ep;
+    const QueryCtx* ctx;
+    const Centre* centres;
+    const float* widths;     // [nW] device
+    int nL, nW;
+    const float4* goals;     // explicit goals [S,C] (gx, gy, gth, p3) or null
+    const float* prev_theta; // [M] or null
+    int C;                   // candidates per scenario
+    int c_begin, c_end;      // evaluated range
+    int ctas_per_scn;
+    int nseg_pad;            // shared-memory window capacity (multiple of 32)
+    // outputs (nullable)
+    float* costs;            // [S,C]
+    float* terms;            // [S,C,5]
+    uint8_t* flags;          // [S,C]
+    float* goals_out;        // [S,C,3]
+    float4* params;          // [S,C]
+    float4* states;          // [S,C,M]
+    float2* headings;        // [S,C,M] (cos, sin) used by the footprint (teacher-forced tests)
+    unsigned long long* best;  // [S]
+};
+
+struct SelectArgs {
+    TrackView tr;
+    LutView lut;
+    EvalParams ep;
+    const QueryCtx* ctx;
+    const Centre* centres;
+    const float* widths;
+    int nL, nW;
+    const float4* goals;
+    int C, c_begin;
+    const unsigned long long* best;
+    // outputs (nullable)
+    int32_t* best_idx;      // [S]
+    float* best_cost;       // [S]
+    int32_t* status;        // [S,2] no_feasible, tracker_found
+    double* steer_speed;    // [S,2]
+    float4* best_traj;      // [S,M]
+    float* prev_theta_out;  // [M] (single query, update_prev)
+};
+
+// goal of candidate c of scenario s: centre + width * normal, or the explicit goal
+__device__ __forceinline__ void candidate_goal(const Centre* __restrict__ centres,
+                                               const float* __restrict__ widths,
+                                               const float4* __restrict__ goals, int nL, int nW,
+                                               int C, int s, int c, bool use_goal_kappa, float& gx,
+                                               float& gy, float& gth, float& p3, bool& have_centre,
+                                               float& v_ref) {
+    if (goals) {
+        const float4 g = __ldg(goals + (size_t)s * C + c);
+        gx = g.x; gy = g.y; gth = g.z; p3 = g.w;
+        have_centre = true;
+        v_ref = -1.0f;
+    } else {
+        const int row = c / nW, k = c - row * nW;
+        const Centre* ce = centres + (size_t)s * nL + row;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(ce));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ce) + 1);
+        const float wk = __ldg(widths + k);
+        gx = fmaf(wk, b.x, a.x);
+        gy = fmaf(wk, b.y, a.y);
+        gth = a.z;
+        p3 = use_goal_kappa ? a.w : 0.0f;
+        have_centre = b.w != 0.0f;
+        v_ref = b.z;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: sampler
+// ---------------------------------------------------------------------------------------------
+#define SAMPLE_THREADS 256
+
+__device__ __forceinline__ double wrap_to_pi64(double a) {
+    const double two_pi = 6.283185307179586476925286766559;
+    a = fmod(a + 3.14159265358979323846, two_pi);
+    if (a < 0.0) a += two_pi;
+    return a - 3.14159265358979323846;
+}
+
+__global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
+    __shared__ double s_d[SAMPLE_THREADS / 32];
+    __shared__ int s_i[SAMPLE_THREADS / 32];
+    __shared__ double s_t;
+    __shared__ int s_best;
+    const int s = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double px = a.poses[4 * (size_t)s], py = a.poses[4 * (size_t)s + 1];
+    const double pth = a.poses[4 * (size_t)s + 2], pv = a.poses[4 * (size_t)s + 3];
+    const int nseg = a.tr.n - 1;
+
+    // nearest_point (utils.py:37-67), float64, first minimum
+    double bd = CUDART_INF;
+    int bi = 0x7fffffff;
+    for (int k = tid; k < nseg; k += SAMPLE_THREADS) {
+        const double2 p0 = a.tr.xy[k], p1 = a.tr.xy[k + 1];
+        double qx, qy, d, t;
+        nearest_segment64(px, py, p0.x, p0.y, p1.x, p1.y, qx, qy, d, t);
+        if (nearest_better(d, k, bd, bi)) { bd = d; bi = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(F1L_FULL, bd, o);
+        const int oi = __shfl_xor_sync(F1L_FULL, bi, o);
+        if (nearest_better(od, oi, bd, bi)) { bd = od; bi = oi; }
+    }
+    if (lane == 0) { s_d[wid] = bd; s_i[wid] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < SAMPLE_THREADS / 32; ++w)
+            if (nearest_better(s_d[w], s_i[w], bd, bi)) { bd = s_d[w]; bi = s_i[w]; }
+        if (bi == 0x7fffffff) bi = 0;
+        const double2 p0 = a.tr.xy[bi], p1 = a.tr.xy[bi + 1];
+        double qx, qy, d, t;
+        nearest_segment64(px, py, p0.x, p0.y, p1.x, p1.y, qx, qy, d, t);
+        s_best = bi;
+        s_t = t;
+    }
+    __syncthreads();
+    const int i_ego = s_best;
+    const double t_ego = s_t;
+    const double cth = cos(pth), sth = sin(pth);
+
+    // one intersect_point per lookahead row (lattice_planner.py:249-251)
+    XYTrack acc{a.tr.xy};
+    for (int j = tid; j < a.nL; j += SAMPLE_THREADS) {
+        const Intersect64 ip =
+            intersect_point64(acc, a.tr.n, px, py, a.lookaheads[j], (double)i_ego + t_ego, true);
+        Centre ce;
+        const int r = ip.found ? pymod(ip.i, a.tr.n) : 0;
+        const double2 c = a.tr.xy[r];
+        const double psi = a.tr.psi[r];
+        const double dx = c.x - px, dy = c.y - py;
+        const double prel = wrap_to_pi64(psi - pth);
+        ce.cx = ip.found ? (float)(cth * dx + sth * dy) : 0.0f;
+        ce.cy = ip.found ? (float)(-sth * dx + cth * dy) : 0.0f;
+        ce.psi_rel = ip.found ? (float)prel : 0.0f;
+        ce.kappa_g = (float)a.tr.kappa[r];
+        ce.nx = ip.found ? (float)(-sin(prel)) : 0.0f;
+        ce.ny = ip.found ? (float)cos(prel) : 0.0f;
+        ce.v = (float)a.tr.v[r];
+        ce.ok = ip.found ? 1.0f : 0.0f;
+        a.centres[(size_t)s * a.nL + j] = ce;
+    }
+
+    QueryCtx* q = a.ctx + s;
+    const int n_opp = a.opp ? (a.n_opp ? min(a.n_opp[s], a.max_opp) : a.max_opp) : 0;
+    if (tid < F1L_MAX_OPP) {
+        float4 o = make_float4(1e9f, 1e9f, 1.0f, 0.0f);
+        if (tid < n_opp) {
+            const double* op = a.opp + 3 * ((size_t)s * a.max_opp + tid);
+            const double dx = op[0] - px, dy = op[1] - py, ph = op[2] - pth;
+            o = make_float4((float)(cth * dx + sth * dy), (float)(-sth * dx + cth * dy),
+                            (float)cos(ph), (float)sin(ph));
+        }
+        q->opp[tid] = o;
+    }
+    if (tid == 32) {
+        q->px = px; q->py = py; q->th = pth; q->vel = pv;
+        q->cth = (float)cth; q->sth = (float)sth;
+        q->i_ego = i_ego;
+        int ns = a.ep.window;
+        if (ns <= 0 || ns > nseg) ns = nseg;
+        q->nseg = ns;
+        q->seg0 = pymod(i_ego - ns / 4, nseg);
+        q->n_opp = n_opp;
+        q->has_grid = a.grid.occ != nullptr;
+        q->pad0 = 0;
+        if (a.grid.occ) {
+            const double bx = (px - a.grid.ox) * a.grid.inv_res, by = (py - a.grid.oy) * a.grid.inv_res;
+            const double fx = floor(bx), fy = floor(by);
+            q->gix = (int)fx; q->giy = (int)fy;
+            q->gfx = (float)(bx - fx); q->gfy = (float)(by - fy);
+            q->gA00 = (float)(cth * a.grid.inv_res); q->gA01 = (float)(-sth * a.grid.inv_res);
+            q->gA10 = (float)(sth * a.grid.inv_res); q->gA11 = (float)(cth * a.grid.inv_res);
+        } else {
+            q->gix = 0; q->giy = 0; q->gfx = 0.f; q->gfy = 0.f;
+            q->gA00 = 0.f; q->gA01 = 0.f; q->gA10 = 0.f; q->gA11 = 0.f;
+        }
+        a.best[s] = ~0ull;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 + K4: fused generate / cost / collision, one warp per candidate
+// ---------------------------------------------------------------------------------------------
+#define EVAL_MAX_WARPS 8
+
+// collision predicate pieces use explicitly rounded FP32 ops (no FMA contraction) so that the
+// float32 mirror in the oracle reproduces the flags bit for bit on identical inputs.
+__device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
+
+// SAT of two equal rectangles; ego axes (c, s), opponent axes (oc, os), T = opp - ego.
+// collide iff every axis overlaps strictly (touching = no collision).
+__device__ __forceinline__ bool sat_collide(float tx, float ty, float c, float s, float oc,
+                                            float os, float hl, float hw) {
+    const float cc = fabsf(fa(fm(c, oc), fm(s, os)));
+    const float ss = fabsf(fs(fm(s, oc), fm(c, os)));
+    const float rl = fa(hl, fa(fm(hl, cc), fm(hw, ss)));
+    const float rw = fa(hw, fa(fm(hl, ss), fm(hw, cc)));
+    const float e0 = fabsf(fa(fm(tx, c), fm(ty, s)));
+    const float e1 = fabsf(fs(fm(ty, c), fm(tx, s)));
+    const float e2 = fabsf(fa(fm(tx, oc), fm(ty, os)));
+    const float e3 = fabsf(fs(fm(ty, oc), fm(tx, os)));
+    return e0 < rl && e1 < rw && e2 < rl && e3 < rw;
+}
+
+__device__ __forceinline__ bool grid_hit(const uint8_t* __restrict__ occ, int gw, int gh, int ix0,
+                                         int iy0, float cx, float cy) {
+    const int col = ix0 + __float2int_rd(cx), row = iy0 + __float2int_rd(cy);
+    if ((unsigned)col >= (unsigned)gw || (unsigned)row >= (unsigned)gh) return true;
+    return __ldg(occ + (size_t)row * gw + col) != 0;
+}
+
+template <int IPL, int S, int SG>
+__global__ void __launch_bounds__(EVAL_MAX_WARPS * 32) eval_kernel(EvalArgs a) {
+    constexpr int GG = 32 / SG;
+    extern __shared__ __align__(16) unsigned char ev_smem[];
+    const int M = a.ep.M;
+    const int nwarps = blockDim.x >> 5;
+    float4* sA = reinterpret_cast<float4*>(ev_smem);
+    float2* sB = reinterpret_cast<float2*>(sA + a.nseg_pad);
+    float4* sopp = reinterpret_cast<float4*>(sB + a.nseg_pad);               // [F1L_MAX_OPP]
+    float* sprev = reinterpret_cast<float*>(sopp + F1L_MAX_OPP);             // [M] (padded to 4)
+    float2* slab_all = reinterpret_cast<float2*>(sprev + ((M + 3) & ~3));    // [nwarps][M]
+
+    const int s = blockIdx.x / a.ctas_per_scn;
+    const int cta = blockIdx.x - s * a.ctas_per_scn;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const QueryCtx* __restrict__ q = a.ctx + s;
+
+    // ---- prologue: raceline window -> vehicle frame -> line form in shared memory ----
+    {
+        const double px = q->px, py = q->py;
+        const double cth = cos(q->th), sth = sin(q->th);
+        const int seg0 = q->seg0, nseg = q->nseg, ns = a.tr.n - 1;
+        for (int k = tid; k < a.nseg_pad; k += blockDim.x) {
+            float4 A = make_float4(1.0f, 0.0f, 1e15f, 1e15f);  // padding: far away, finite
+            float2 Bv = make_float2(1.0f, 1.0f);
+            if (k < nseg) {
+                int sg = seg0 + k;
+                if (sg >= ns) sg -= ns;
+                const double2 p0 = a.tr.xy[sg], p1 = a.tr.xy[sg + 1];
+                const double ax = p0.x - px, ay = p0.y - py, bx = p1.x - px, by = p1.y - py;
+                const double avx = cth * ax + sth * ay, avy = -sth * ax + cth * ay;
+                const double bvx = cth * bx + sth * by, bvy = -sth * bx + cth * by;
+                const double dx = bvx - avx, dy = bvy - avy;
+                const double len = sqrt(dx * dx + dy * dy);
+                const double ux = dx / len, uy = dy / len;
+                A = make_float4((float)ux, (float)uy, (float)(avx * ux + avy * uy),
+                                (float)(-avx * uy + avy * ux));
+                Bv = make_float2((float)len, (float)(1.0 / len));
+            }
+            sA[k] = A;
+            sB[k] = Bv;
+        }
+        if (a.prev_theta)
+            for (int i = tid; i < M; i += blockDim.x) sprev[i] = a.prev_theta[i];
+        if (tid < F1L_MAX_OPP) sopp[tid] = q->opp[tid];
+    }
+    __syncthreads();
+
+    const int c = a.c_begin + cta * nwarps + wid;
+    if (c >= a.c_end) return;
+    float2* slab = slab_all + (size_t)wid * M;
+
+    // ---- goal, seed, Newton ----
+    float gx, gy, gth, p3, v_ref;
+    bool have_centre;
+    candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.C, s, c, a.ep.use_goal_kappa != 0,
+                   gx, gy, gth, p3, have_centre, v_ref);
+    SpiralF sp;
+    sp.p0 = 0.0f;
+    sp.p3 = p3;
+    {
+        const float4 seed = lut_lookup(a.lut, gx, gy, gth);
+        sp.p1 = seed.x; sp.p2 = seed.y; sp.sf = seed.z;
+    }
+    spiral_newton(sp, gx, gy, gth, a.ep.n_newton, lane);
+
+    // ---- arc samples ----
+    float x[IPL], y[IPL], th[IPL], kp[IPL], cs[IPL], sn[IPL];
+    spiral_sample<IPL>(sp, M, lane, x, y, th, kp, cs, sn);
+
+    const size_t cand = (size_t)s * a.C + c;
+    if (a.states) {
+#pragma unroll
+        for (int j = 0; j < IPL; ++j) {
+            const int i = lane * IPL + j;
+            if (i < M) a.states[cand * M + i] = make_float4(x[j], y[j], th[j], kp[j]);
+        }
+    }
+    if (a.headings) {
+#pragma unroll
+        for (int j = 0; j < IPL; ++j) {
+            const int i = lane * IPL + j;
+            if (i < M) a.headings[cand * M + i] = make_float2(cs[j], sn[j]);
+        }
+    }
+
+    // ---- curvature terms, endpoint, validity ----
+    float maxk = 0.0f, sumk = 0.0f, ex = 0.0f, ey = 0.0f, eth = 0.0f;
+#pragma unroll
+    for (int j = 0; j < IPL; ++j) {
+        const int i = lane * IPL + j;
+        if (i < M) {
+            const float ak = fabsf(kp[j]);
+            maxk = fmaxf(maxk, ak);
+            sumk += ak;
+            slab[i] = make_float2(x[j], y[j]);
+            if (i == M - 1) { ex = x[j]; ey = y[j]; eth = th[j]; }
+        }
+    }
+    const int last_lane = (M - 1) / IPL;
+    ex = __shfl_sync(F1L_FULL, ex, last_lane);
+    ey = __shfl_sync(F1L_FULL, ey, last_lane);
+    eth = __shfl_sync(F1L_FULL, eth, last_lane);
+    maxk = warp_max(maxk);
+    sumk = warp_sum(sumk);
+    const float gn = sqrtf(fmaf(gx, gx, fmaf(gy, gy, gth * gth)));
+    const float tol = a.ep.tol * fmaxf(gn, 1.0f);
+    bool valid = have_centre && isfinite(sp.p1) && isfinite(sp.p2) && isfinite(sp.sf) &&
+                 sp.sf > 0.0f && fabsf(ex - gx) < tol && fabsf(ey - gy) < tol &&
+                 fabsf(eth - gth) < tol;
+    if (valid && a.ep.kappa_max > 0.0f && !(maxk <= a.ep.kappa_max)) valid = false;
+
+    unsigned flags = valid ? F1L_FLAG_VALID : 0u;
+    if (!have_centre) flags |= F1L_FLAG_NO_CENTRE;
+    float t_len = 0.0f, t_maxk = 0.0f, t_meank = 0.0f, t_sim = 0.0f, t_dev = 0.0f;
+    float cost = CUDART_INF_F;
+
+    if (valid) {  // warp-uniform
+        t_len = __fdividef(1.0f, sp.sf);       // lattice_planner.py:271
+        t_maxk = maxk;                         // :277
+        t_meank = sumk / (float)M;             // :284
+
+        // ---- similarity (lattice_planner.py:287-296), collision ----
+        float sim = 0.0f;
+        bool hit_opp = false, hit_map = false;
+        const int lim = M - a.ep.n_shift - a.ep.n_cull;
+        const int n_opp = q->n_opp;
+        const bool has_grid = q->has_grid != 0;
+        const float hl = a.ep.half_l, hw = a.ep.half_w;
+        const float A00 = q->gA00, A01 = q->gA01, A10 = q->gA10, A11 = q->gA11;
+        const float gfx = q->gfx, gfy = q->gfy;
+        const int gix = q->gix, giy = q->giy;
+#pragma unroll
+        for (int j = 0; j < IPL; ++j) {
+            const int i = lane * IPL + j;
+            if (i < M) {
+                if (a.prev_theta && i < lim) {
+                    const float d = th[j] - sprev[i + a.ep.n_shift];
+                    sim = fmaf(d, d, sim);
+                }
+                for (int k = 0; k < n_opp; ++k) {
+                    const float4 o = sopp[k];
+                    const float tx = fs(o.x, x[j]), ty = fs(o.y, y[j]);
+                    const float d2 = fa(fm(tx, tx), fm(ty, ty));
+                    if (d2 <= a.ep.rc2 && sat_collide(tx, ty, cs[j], sn[j], o.z, o.w, hl, hw))
+                        hit_opp = true;
+                }
+                if (has_grid) {
+                    // footprint centre and half-axes in grid-cell coordinates
+                    const float ccx = fa(fa(fm(A00, x[j]), fm(A01, y[j])), gfx);
+                    const float ccy = fa(fa(fm(A10, x[j]), fm(A11, y[j])), gfy);
+                    const float lx = fm(cs[j], hl), ly = fm(sn[j], hl);    // body x axis * hl
+                    const float wx = fm(-sn[j], hw), wy = fm(cs[j], hw);   // body y axis * hw
+                    const float elx = fa(fm(A00, lx), fm(A01, ly)), ely = fa(fm(A10, lx), fm(A11, ly));
+                    const float ewx = fa(fm(A00, wx), fm(A01, wy)), ewy = fa(fm(A10, wx), fm(A11, wy));
+                    const uint8_t* occ = a.grid.occ;
+                    const int gw = a.grid.w, gh = a.grid.h;
+                    bool h = false;
+                    // 4 corners, 4 edge mid-points, centre (SURVEY B.6, P = 9)
+                    h |= grid_hit(occ, gw, gh, gix, giy, fa(fa(ccx, elx), ewx), fa(fa(ccy, ely), ewy));
+                    h |= grid_hit(occ, gw, gh, gix, giy, fs(fa(ccx, elx), ewx), fs(fa(ccy, ely), ewy));
+                    h |= grid_hit(occ, gw, gh, gix, giy, fa(fs(ccx, elx), ewx), fa(fs(ccy, ely), ewy));
+                    h |= grid_hit(occ, gw, gh, gix, giy, fs(fs(ccx, elx), ewx), fs(fs(ccy, ely), ewy));
+                    h |= grid_hit(occ, gw, gh, gix, giy, fa(ccx, elx), fa(ccy, ely));
+                    h |= grid_hit(occ, gw, gh, gix, giy, fs(ccx, elx), fs(ccy, ely));
+                    h |= grid_hit(occ, gw, gh, gix, giy, fa(ccx, ewx), fa(ccy, ewy));
+                    h |= grid_hit(occ, gw, gh, gix, giy, fs(ccx, ewx), fs(ccy, ewy));
+                    h |= grid_hit(occ, gw, gh, gix, giy, ccx, ccy);
+                    hit_map |= h;
+                }
+            }
+        }
+        t_sim = warp_sum(sim);
+        hit_opp = __any_sync(F1L_FULL, hit_opp);
+        hit_map = __any_sync(F1L_FULL, hit_map);
+        if (hit_opp) flags |= F1L_FLAG_COLLIDE_OPP;
+        if (hit_map) flags |= F1L_FLAG_COLLIDE_MAP;
+
+        // ---- raceline deviation: mean over samples of the nearest distance to the window
+        //      (nearest_point semantics, utils.py:53-66).  Lane = (sample group sg, segment
+        //      group gg); each lane keeps S samples in registers and walks every GG-th segment.
+        __syncwarp();
+        {
+            const int sgi = lane / GG, ggi = lane - sgi * GG;
+            float sx[S], sy[S], bd[S];
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const int i = j * SG + sgi;
+                const float2 p = slab[i < M ? i : M - 1];
+                sx[j] = p.x; sy[j] = p.y; bd[j] = CUDART_INF_F;
+            }
+            const int nq = a.nseg_pad;
+#pragma unroll 2
+            for (int k = ggi; k < nq; k += GG) {
+                const float4 A = sA[k];
+                const float2 Bv = sB[k];
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const float qq = fmaf(sx[j], A.x, fmaf(sy[j], A.y, -A.z));
+                    const float nn = fmaf(sy[j], A.x, fmaf(-sx[j], A.y, -A.w));
+                    const float t = __saturatef(qq * Bv.y);
+                    const float e = fmaf(-t, Bv.x, qq);
+                    bd[j] = fminf(bd[j], fmaf(e, e, nn * nn));
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < GG; o <<= 1) {
+#pragma unroll
+                for (int j = 0; j < S; ++j) bd[j] = fminf(bd[j], __shfl_xor_sync(F1L_FULL, bd[j], o));
+            }
+            float dsum = 0.0f;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const int i = j * SG + sgi;
+                if ((j % GG) == ggi && i < M) dsum += sqrtf(bd[j]);
+            }
+            t_dev = warp_sum(dsum) / (float)M;
+        }
+
+        if (!(flags & (F1L_FLAG_COLLIDE_OPP | F1L_FLAG_COLLIDE_MAP))) {
+            cost = a.ep.w[0] * t_len + a.ep.w[1] * t_maxk + a.ep.w[2] * t_meank +
+                   a.ep.w[3] * t_sim + a.ep.w[4] * t_dev;
+            if (!isfinite(cost)) cost = CUDART_INF_F;
+        }
+    }
+
+    if (lane == 0) {
+        if (a.costs) a.costs[cand] = cost;
+        if (a.flags) a.flags[cand] = (uint8_t)flags;
+        if (a.terms) {
+            float* t = a.terms + cand * F1L_N_TERMS;
+            t[0] = t_len; t[1] = t_maxk; t[2] = t_meank; t[3] = t_sim; t[4] = t_dev;
+        }
+        if (a.goals_out) {
+            float* g = a.goals_out + cand * 3;
+            g[0] = gx; g[1] = gy; g[2] = gth;
+        }
+        if (a.params) a.params[cand] = make_float4(sp.p1, sp.p2, sp.sf, sp.p3);
+        const unsigned long long key =
+            ((unsigned long long)float_orderable(cost) << 32) | (unsigned)c;
+        atomicMin(a.best + s, key);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: select + regenerate + tracker, one warp per scenario
+// ---------------------------------------------------------------------------------------------
+template <int IPL>
+__global__ void __launch_bounds__(32) select_kernel(SelectArgs a) {
+    __shared__ float4 s_traj[F1L_MAX_M];
+    const int s = blockIdx.x, lane = threadIdx.x;
+    const int M = a.ep.M;
+    const QueryCtx* __restrict__ q = a.ctx + s;
+    const unsigned long long key = a.best[s];
+    int idx = (int)(key & 0xffffffffu);
+    float cost = orderable_float((uint32_t)(key >> 32));
+    const bool none = (key == ~0ull) || !(cost < CUDART_INF_F);
+    if (key == ~0ull) { idx = a.c_begin; cost = CUDART_INF_F; }
+
+    float gx, gy, gth, p3, v_ref;
+    bool have_centre;
+    candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.C, s, idx,
+                   a.ep.use_goal_kappa != 0, gx, gy, gth, p3, have_centre, v_ref);
+    SpiralF sp;
+    sp.p0 = 0.0f;
+    sp.p3 = p3;
+    {
+        const float4 seed = lut_lookup(a.lut, gx, gy, gth);
+        sp.p1 = seed.x; sp.p2 = seed.y; sp.sf = seed.z;
+    }
+    spiral_newton(sp, gx, gy, gth, a.ep.n_newton, lane);
+    float x[IPL], y[IPL], th[IPL], kp[IPL], cs[IPL], sn[IPL];
+    spiral_sample<IPL>(sp, M, lane, x, y, th, kp, cs, sn);
+#pragma unroll
+    for (int j = 0; j < IPL; ++j) {
+        const int i = lane * IPL + j;
+        if (i < M) {
+            const float4 st = make_float4(x[j], y[j], th[j], kp[j]);
+            s_traj[i] = st;
+            if (a.best_traj) a.best_traj[(size_t)s * M + i] = st;
+            if (a.prev_theta_out) a.prev_theta_out[i] = th[j];
+        }
+    }
+    __syncwarp();
+
+    // tracker: pure pursuit on the best trajectory (lattice_planner.py:208-212)
+    const bool literal = a.ep.literal_tracker != 0;
+    const double qx = literal ? q->px : 0.0, qy = literal ? q->py : 0.0;
+    const double qth = literal ? q->th : 0.0;
+    const double L = a.ep.tracker_lookahead;
+    const double wb = literal ? 0.33 : a.ep.wheelbase;  // :55 tracker built with the default
+    XYTraj4 acc{s_traj};
+    double bd = CUDART_INF;
+    int bi = 0x7fffffff;
+    for (int k = lane; k < M - 1; k += 32) {
+        const double2 p0 = acc(k), p1 = acc(k + 1);
+        double ux, uy, d, t;
+        nearest_segment64(qx, qy, p0.x, p0.y, p1.x, p1.y, ux, uy, d, t);
+        // NaN distances (degenerate trajectory) never win; the reference would return them
+        if (nearest_better(d, k, bd, bi)) { bd = d; bi = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(F1L_FULL, bd, o);
+        const int oi = __shfl_xor_sync(F1L_FULL, bi, o);
+        if (nearest_better(od, oi, bd, bi)) { bd = od; bi = oi; }
+    }
+    if (lane == 0) {
+        int found = 0;
+        double steer = 0.0, speed = 0.0;
+        if (bi != 0x7fffffff) {
+            const double2 p0 = acc(bi), p1 = acc(bi + 1);
+            double ux, uy, d, t;
+            nearest_segment64(qx, qy, p0.x, p0.y, p1.x, p1.y, ux, uy, d, t);
+            const double v_track = literal ? (double)s_traj[bi].z
+                                           : (v_ref >= 0.0f ? (double)v_ref : q->vel);
+            double lx = 0.0, ly = 0.0;
+            if (d < L) {                                        // pure_pursuit.py:70
+                const Intersect64 ip = intersect_point64(acc, M, qx, qy, L, (double)bi + t, true);
+                if (ip.found) {
+                    const int r = pymod(ip.i, M);
+                    lx = acc(r).x; ly = acc(r).y;
+                    found = 1;
+                }
+            } else if (d < a.ep.max_reacquire) {                 // :80
+                lx = p0.x; ly = p0.y;
+                found = 1;
+            }
+            if (found) {
+                steer = actuation_steer64(qth, lx, ly, qx, qy, L, wb);
+                speed = v_track;
+            }
+        }
+        if (a.best_idx) a.best_idx[s] = idx;
+        if (a.best_cost) a.best_cost[s] = cost;
+        if (a.status) { a.status[2 * s] = none ? 1 : 0; a.status[2 * s + 1] = found; }
+        if (a.steer_speed) { a.steer_speed[2 * (size_t)s] = steer; a.steer_speed[2 * (size_t)s + 1] = speed; }
+    }
+}
+
+__global__ void fill_f32_kernel(float* __restrict__ p, size_t n, float v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generate-only kernel (user cost functions on the host): goals -> states / params / flags
+// ---------------------------------------------------------------------------------------------
+template <int IPL>
+__global__ void __launch_bounds__(EVAL_MAX_WARPS * 32)
+generate_kernel(LutView lut, EvalParams ep, const float4* __restrict__ goals, int C,
+                float4* __restrict__ states, float4* __restrict__ params,
+                uint8_t* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= C) return;
+    const int M = ep.M;
+    const float4 g = __ldg(goals + c);
+    SpiralF sp;
+    sp.p0 = 0.0f;
+    sp.p3 = g.w;
+    const float4 seed = lut_lookup(lut, g.x, g.y, g.z);
+    sp.p1 = seed.x; sp.p2 = seed.y; sp.sf = seed.z;
+    spiral_newton(sp, g.x, g.y, g.z, ep.n_newton, lane);
+    float x[IPL], y[IPL], th[IPL], kp[IPL], cs[IPL], sn[IPL];
+    spiral_sample<IPL>(sp, M, lane, x, y, th, kp, cs, sn);
+    float maxk = 0.0f, ex = 0.0f, ey = 0.0f, eth = 0.0f;
+#pragma unroll
+    for (int j = 0; j < IPL; ++j) {
+        const int i = lane * IPL + j;
+        if (i < M) {
+            states[(size_t)c * M + i] = make_float4(x[j], y[j], th[j], kp[j]);
+            maxk = fmaxf(maxk, fabsf(kp[j]));
+            if (i == M - 1) { ex = x[j]; ey = y[j]; eth = th[j]; }
+        }
+    }
+    const int last_lane = (M - 1) / IPL;
+    ex = __shfl_sync(F1L_FULL, ex, last_lane);
+    ey = __shfl_sync(F1L_FULL, ey, last_lane);
+    eth = __shfl_sync(F1L_FULL, eth, last_lane);
+    maxk = warp_max(maxk);
+    const float gn = sqrtf(fmaf(g.x, g.x, fmaf(g.y, g.y, g.z * g.z)));
+    const float tol = ep.tol * fmaxf(gn, 1.0f);
+    bool valid = isfinite(sp.p1) && isfinite(sp.p2) && isfinite(sp.sf) && sp.sf > 0.0f &&
+                 fabsf(ex - g.x) < tol && fabsf(ey - g.y) < tol && fabsf(eth - g.z) < tol;
+    if (valid && ep.kappa_max > 0.0f && !(maxk <= ep.kappa_max)) valid = false;
+    if (lane == 0) {
+        if (params) params[c] = make_float4(sp.p1, sp.p2, sp.sf, sp.p3);
+        if (flags) flags[c] = valid ? F1L_FLAG_VALID : 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// spiral seed LUT build, float64, one thread per cell (continuation from the
+// straight line to the cell's goal, then polishing; non-converged cells get the heuristic seed)
+// ---------------------------------------------------------------------------------------------
+__device__ inline bool newton_step64(double gx, double gy, double gth, double& p1, double& p2,
+                                     double& sf) {
+    const double b1 = (18.0 * p1 - 9.0 * p2) / 2.0;
+    const double b2 = (-45.0 * p1 + 36.0 * p2) / 2.0;
+    const double b3 = (27.0 * p1 - 27.0 * p2) / 2.0;
+    double C0 = 0, S0 = 0, Cg = 0, Sg = 0, C1 = 0, S1 = 0, C2 = 0, S2 = 0;
+    for (int j = 0; j <= 32; ++j) {
+        const double u = (double)j / 32.0;
+        const double w = ((j == 0 || j == 32) ? 1.0 : ((j & 1) ? 4.0 : 2.0)) / 96.0;
+        const double g = u * (u * (b1 / 2.0 + u * (b2 / 3.0 + u * (b3 / 4.0))));
+        const double th = sf * g;
+        const double c = cos(th), s = sin(th);
+        const double u2 = u * u;
+        const double d1 = u2 * (4.5 + u * (-7.5 + 3.375 * u));
+        const double d2 = u2 * (-2.25 + u * (6.0 - 3.375 * u));
+        C0 += w * c; S0 += w * s; Cg += w * c * g; Sg += w * s * g;
+        C1 += w * c * d1; S1 += w * s * d1; C2 += w * c * d2; S2 += w * s * d2;
+    }
+    const double g1 = (3.0 * p1 + 3.0 * p2) / 8.0;
+    const double r0 = sf * C0 - gx, r1 = sf * S0 - gy, r2 = sf * g1 - gth;
+    const double sf2 = sf * sf;
+    const double J00 = -sf2 * S1, J01 = -sf2 * S2, J02 = C0 - sf * Sg;
+    const double J10 = sf2 * C1, J11 = sf2 * C2, J12 = S0 + sf * Cg;
+    const double J20 = 0.375 * sf, J21 = 0.375 * sf, J22 = g1;
+    const double m0 = J11 * J22 - J12 * J21, m1 = J10 * J22 - J12 * J20, m2 = J10 * J21 - J11 * J20;
+    const double det = J00 * m0 - J01 * m1 + J02 * m2;
+    const double inv = 1.0 / det;
+    const double n0 = r1 * J22 - J12 * r2, n1 = r1 * J21 - J11 * r2, n2 = J10 * r2 - r1 * J20;
+    p1 -= (r0 * m0 - J01 * n0 + J02 * n1) * inv;
+    p2 -= (J00 * n0 - r0 * m1 + J02 * n2) * inv;
+    sf -= (-J00 * n1 - J01 * n2 + r0 * m2) * inv;
+    return isfinite(p1) && isfinite(p2) && isfinite(sf);
+}
+
+__device__ inline double residual64(double gx, double gy, double gth, double p1, double p2,
+                                    double sf) {
+    const double b1 = (18.0 * p1 - 9.0 * p2) / 2.0;
+    const double b2 = (-45.0 * p1 + 36.0 * p2) / 2.0;
+    const double b3 = (27.0 * p1 - 27.0 * p2) / 2.0;
+    double C0 = 0, S0 = 0;
+    for (int j = 0; j <= 32; ++j) {
+        const double u = (double)j / 32.0;
+        const double w = ((j == 0 || j == 32) ? 1.0 : ((j & 1) ? 4.0 : 2.0)) / 96.0;
+        const double th = sf * (u * (u * (b1 / 2.0 + u * (b2 / 3.0 + u * (b3 / 4.0)))));
+        C0 += w * cos(th); S0 += w * sin(th);
+    }
+    const double g1 = (3.0 * p1 + 3.0 * p2) / 8.0;
+    return fmax(fabs(sf * C0 - gx), fmax(fabs(sf * S0 - gy), fabs(sf * g1 - gth)));
+}
+
+__global__ void lut_build_kernel(float4* __restrict__ cells, int nx, int ny, int nt, double x0,
+                                 double x1, double y0, double y1, double t0, double t1) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= nx * ny * nt) return;
+    const int it = cell % nt, iy = (cell / nt) % ny, ix = cell / (nt * ny);
+    const double gx = nx > 1 ? x0 + (x1 - x0) * (double)ix / (double)(nx - 1) : x0;
+    const double gy = ny > 1 ? y0 + (y1 - y0) * (double)iy / (double)(ny - 1) : y0;
+    const double gt = nt > 1 ? t0 + (t1 - t0) * (double)it / (double)(nt - 1) : t0;
+    double p1 = 0.0, p2 = 0.0, sf = gx;
+    bool ok = gx > 0.0;
+    for (int s = 1; s <= 16 && ok; ++s) {
+        const double lam = (double)s / 16.0;
+        for (int k = 0; k < 4 && ok; ++k) ok = newton_step64(gx, lam * gy, lam * gt, p1, p2, sf);
+        if (!(sf > 0.0)) ok = false;
+    }
+    for (int k = 0; k < 8 && ok; ++k) ok = newton_step64(gx, gy, gt, p1, p2, sf);
+    if (ok && sf > 0.0 && residual64(gx, gy, gt, p1, p2, sf) < 1e-8) {
+        cells[cell] = make_float4((float)p1, (float)p2, (float)sf, 1.0f);
+    } else {
+        const double d = sqrt(gx * gx + gy * gy);
+        cells[cell] = make_float4(0.0f, 0.0f, (float)(d * (gt * gt / 5.0 + 1.0) + 2.0 * fabs(gt) / 5.0),
+                                  0.0f);
+    }
+}

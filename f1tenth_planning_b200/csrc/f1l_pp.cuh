@@ -1,0 +1,168 @@
+// f1l_pp.cuh -- K1: batched nearest_point + pure-pursuit lookahead on the uploaded track.
+//
+// Replaces, for B poses at once, utils/utils.py:37-67 (nearest_point), :69-151
+// (intersect_point), :153-161 (get_actuation) and pure_pursuit.py:56-122.
+//
+// Design: one THREAD per pose.  The segment table streams through shared memory in chunks and
+// every lane of a warp reads the same segment (a broadcast: one wavefront per LDS), so the
+// inner loop is 8 FMA-pipe + 3 ALU instructions per (pose, segment) with no cross-lane traffic.
+// The scan runs in FP32 on a line-form of each segment expressed in the frame of its 32-segment
+// block (origin kept in float64), which keeps |coordinates| small where it matters; the winner
+// and its +-2 neighbours are then re-evaluated in float64 operation by operation like the
+// reference, so index / t / dist / projection agree with the numba path to rounding.
+#pragma once
+#include "f1l_common.cuh"
+
+#define PP_CHUNK 2048          // segments staged per shared-memory chunk
+#define PP_THREADS 128
+#define PP_SMEM_BYTES (PP_CHUNK * (sizeof(float4) + sizeof(float2)) + (PP_CHUNK / 32) * sizeof(double2))
+
+struct PPOut {
+    double* nearest;      // [B,4] proj_x, proj_y, dist, t
+    int32_t* nearest_i;   // [B]
+    double* lookahead;    // [B,4] p_x, p_y, t2, found
+    int32_t* lookahead_i; // [B]
+    double* actuation;    // [B,2] steer, speed
+    int32_t* status;      // [B]
+};
+
+// float64 refinement of the FP32 argmin: segments [k-2, k+2], first minimum (utils.py:66)
+__device__ __forceinline__ Nearest64 refine_nearest64(const double2* __restrict__ xy, int nseg,
+                                                      double qx, double qy, int k) {
+    Nearest64 b;
+    b.dist = CUDART_INF; b.i = 0; b.px = 0.0; b.py = 0.0; b.t = 0.0;
+    const int lo = max(k - 2, 0), hi = min(k + 2, nseg - 1);
+    for (int s = lo; s <= hi; ++s) {
+        const double2 a = xy[s], c = xy[s + 1];
+        double px, py, d, t;
+        nearest_segment64(qx, qy, a.x, a.y, c.x, c.y, px, py, d, t);
+        if (d < b.dist) { b.dist = d; b.i = s; b.px = px; b.py = py; b.t = t; }
+    }
+    return b;
+}
+
+__global__ void __launch_bounds__(PP_THREADS)
+pp_batch_kernel(TrackView tr, const double* __restrict__ poses, int n_poses, double L, double wb,
+                double max_reacquire, PPOut out) {
+    extern __shared__ __align__(16) unsigned char pp_smem[];
+    float4* sA = reinterpret_cast<float4*>(pp_smem);
+    float2* sB = reinterpret_cast<float2*>(sA + PP_CHUNK);
+    double2* sO = reinterpret_cast<double2*>(sB + PP_CHUNK);
+
+    const int nseg = tr.n - 1;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = gid < n_poses;
+    const int pid = active ? gid : n_poses - 1;
+    const double qx = poses[3 * (size_t)pid], qy = poses[3 * (size_t)pid + 1];
+    const double qth = poses[3 * (size_t)pid + 2];
+
+    float best = CUDART_INF_F;
+    int bk = 0;
+    for (int c0 = 0; c0 < nseg; c0 += PP_CHUNK) {
+        const int cn = min(PP_CHUNK, nseg - c0);
+        for (int q = threadIdx.x; q < cn; q += blockDim.x) {
+            sA[q] = __ldg(tr.segA + c0 + q);
+            sB[q] = __ldg(tr.segB + c0 + q);
+        }
+        const int nblk = (cn + 31) >> 5;
+        for (int b = threadIdx.x; b < nblk; b += blockDim.x) sO[b] = tr.blk_origin[(c0 >> 5) + b];
+        __syncthreads();
+        for (int blk = 0; blk < nblk; ++blk) {
+            const double2 o = sO[blk];
+            const float prx = (float)(qx - o.x), pry = (float)(qy - o.y);
+            const int j0 = blk << 5;
+            const int jn = min(32, cn - j0);
+            if (jn == 32) {
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) {
+                    const float4 A = sA[j0 + j];
+                    const float2 Bv = sB[j0 + j];
+                    const float q = fmaf(prx, A.x, fmaf(pry, A.y, -A.z));
+                    const float nn = fmaf(pry, A.x, fmaf(-prx, A.y, -A.w));
+                    const float t = __saturatef(q * Bv.y);
+                    const float ex = fmaf(-t, Bv.x, q);
+                    const float d2 = fmaf(ex, ex, nn * nn);
+                    if (d2 < best) { best = d2; bk = c0 + j0 + j; }
+                }
+            } else {
+                for (int j = 0; j < jn; ++j) {
+                    const float4 A = sA[j0 + j];
+                    const float2 Bv = sB[j0 + j];
+                    const float q = fmaf(prx, A.x, fmaf(pry, A.y, -A.z));
+                    const float nn = fmaf(pry, A.x, fmaf(-prx, A.y, -A.w));
+                    const float t = __saturatef(q * Bv.y);
+                    const float ex = fmaf(-t, Bv.x, q);
+                    const float d2 = fmaf(ex, ex, nn * nn);
+                    if (d2 < best) { best = d2; bk = c0 + j0 + j; }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (!active) return;
+
+    // float64 epilogue: exact nearest among the neighbours, then pure_pursuit.py:69-83
+    const Nearest64 nr = refine_nearest64(tr.xy, nseg, qx, qy, bk);
+    Intersect64 ip;
+    ip.px = 0.0; ip.py = 0.0; ip.t = 0.0; ip.i = 0; ip.found = 0;
+    int status = 0;
+    double lx = 0.0, ly = 0.0, speed = 0.0;
+    if (nr.dist < L) {                                            // :70
+        XYTrack acc{tr.xy};
+        ip = intersect_point64(acc, tr.n, qx, qy, L, (double)nr.i + nr.t, true);  // :71-75
+        if (ip.found) {                                           // :78
+            const int r = pymod(ip.i, tr.n);
+            lx = tr.xy[r].x; ly = tr.xy[r].y; speed = tr.v[nr.i];
+            status = 1;
+        }
+    } else if (nr.dist < max_reacquire) {                         // :80-81
+        lx = tr.xy[nr.i].x; ly = tr.xy[nr.i].y; speed = tr.v[nr.i];
+        status = 2;
+    }
+    double steer = 0.0;
+    if (status) steer = actuation_steer64(qth, lx, ly, qx, qy, L, wb);  // :116-120
+    else speed = 0.0;                                                   // :112-114
+
+    if (out.nearest) {
+        double2* o = reinterpret_cast<double2*>(out.nearest + 4 * (size_t)gid);
+        o[0] = make_double2(nr.px, nr.py);
+        o[1] = make_double2(nr.dist, nr.t);
+    }
+    if (out.nearest_i) out.nearest_i[gid] = nr.i;
+    if (out.lookahead) {
+        double2* o = reinterpret_cast<double2*>(out.lookahead + 4 * (size_t)gid);
+        o[0] = make_double2(ip.px, ip.py);
+        o[1] = make_double2(ip.t, ip.found ? 1.0 : 0.0);
+    }
+    if (out.lookahead_i) out.lookahead_i[gid] = ip.found ? ip.i : 0;
+    if (out.actuation)
+        *reinterpret_cast<double2*>(out.actuation + 2 * (size_t)gid) = make_double2(steer, speed);
+    if (out.status) out.status[gid] = status;
+}
+
+// intersect_point for independent queries (API parity for the free function)
+__global__ void intersect_batch_kernel(TrackView tr, const double* __restrict__ pts,
+                                       const double* __restrict__ t0, int n, double radius,
+                                       int wrap, double* __restrict__ out,
+                                       int32_t* __restrict__ out_i) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n) return;
+    XYTrack acc{tr.xy};
+    const Intersect64 ip = intersect_point64(acc, tr.n, pts[2 * (size_t)gid],
+                                             pts[2 * (size_t)gid + 1], radius, t0[gid], wrap != 0);
+    out[4 * (size_t)gid] = ip.px;
+    out[4 * (size_t)gid + 1] = ip.py;
+    out[4 * (size_t)gid + 2] = ip.t;
+    out[4 * (size_t)gid + 3] = ip.found ? 1.0 : 0.0;
+    out_i[gid] = ip.found ? ip.i : 0;
+}
+
+// get_actuation for independent queries; in [n,7], out [n,2] = (speed, steer)
+__global__ void actuation_batch_kernel(const double* __restrict__ in, int n, double wb,
+                                       double* __restrict__ out) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n) return;
+    const double* r = in + 7 * (size_t)gid;
+    out[2 * (size_t)gid] = r[3];
+    out[2 * (size_t)gid + 1] = actuation_steer64(r[0], r[1], r[2], r[4], r[5], r[6], wb);
+}

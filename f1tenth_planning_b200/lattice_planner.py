@@ -1,0 +1,257 @@
+"""Drop-in for f1tenth_planning/planning/lattice_planner/lattice_planner.py:40-296.
+
+Same class, constructor, plug-in hooks and ``plan`` 3-tuple as the reference; underneath, the
+goal-grid sampler, cubic-spiral generation, fused cost + collision stage and argmin run as
+sm_100a CUDA kernels through the C-ABI library (include/f1l.h).
+
+Reference-compatible surface
+    LatticePlanner(wheelbase=0.33, waypoints=None)                      :44
+    .add_cost_function(func | [funcs])                                  :57-75
+    .add_sample_function(func)                                          :77-98
+    .add_selection_function(func)                                       :100-111
+    .sample(pose_x, pose_y, pose_theta, velocity, waypoints)            :113-128
+    .eval(all_traj, cost_weights)                                       :130-156
+    .select(all_costs)                                                  :159-172
+    .plan(pose_x, pose_y, pose_theta, velocity, waypoints=None)         :174-214
+        -> (steering_angle, speed, selected_traj [M,4])
+    sample_lookahead_square(...), get_length_cost(...) ...              :223-296
+
+Additive (north-star) surface
+    .plan(..., opponent_poses=[K,3])      opponents in the map frame
+    .plan_detailed(...) / .last           PlanDetail: best_idx, costs[C], terms[C,5], flags[C] ...
+    .plan_batch(poses[S,4], opponents[S,K,3], n_opp[S])
+    .set_map(occupancy, origin, resolution), .set_goal_grid(lookaheads, widths)
+
+With no plug-ins registered every stage runs on the GPU.  A registered ``sample_func`` replaces
+only the sampler (its goals are uploaded); registered ``cost_funcs`` are user Python code and are
+evaluated on the host over GPU-generated trajectories, as the reference's ``eval`` does.
+"""
+import zlib
+
+import numpy as np
+
+from .engine import Engine, PlanDetail, FLAG_VALID  # noqa: F401
+from .pure_pursuit import PurePursuitPlanner
+from . import synth
+
+# constants the reference's cost helpers reference but never define (lattice_planner.py:277-294)
+NUM_STEPS = 100
+N_SHIFT = 5
+N_CULL = 10
+
+
+class LatticePlanner():
+    """Sampling lattice planner (reference lattice_planner.py:40)."""
+
+    def __init__(self, wheelbase=0.33, waypoints=None, device=None, **config):
+        self.wheelbase = wheelbase
+        self.waypoints = waypoints
+
+        self.sample_func = None
+        self.cost_funcs = []
+        self.selection_func = None
+        self.cost_weights = None   # weights for registered python cost functions (eval)
+
+        self.tracker = PurePursuitPlanner(device=device)   # :55 (default wheelbase, as upstream)
+
+        self._device = device
+        config.setdefault("wheelbase", float(wheelbase))
+        self._config = config
+        self._engine = None
+        self._key = None
+        self._lookaheads = synth.DEFAULT_LOOKAHEADS.copy()   # :228
+        self._widths = synth.DEFAULT_WIDTHS.copy()           # :229
+        self._grid_dirty = True
+        self._map = None
+        self.last = None
+
+    # -- reference plug-in API ------------------------------------------------------------------
+    def add_cost_function(self, func):
+        """lattice_planner.py:57-75"""
+        if type(func) is list:
+            self.cost_funcs.extend(func)
+        else:
+            self.cost_funcs.append(func)
+
+    def add_sample_function(self, func):
+        """lattice_planner.py:77-98; func(pose_x, pose_y, pose_theta, velocity, waypoints) ->
+        goal_grid [N,3] in the vehicle frame."""
+        self.sample_func = func
+
+    def add_selection_function(self, func):
+        """lattice_planner.py:100-111; func(costs) -> index."""
+        self.selection_func = func
+
+    def sample(self, pose_x, pose_y, pose_theta, velocity, waypoints):
+        """lattice_planner.py:113-128"""
+        if self.sample_func is None:
+            raise NotImplementedError('Please set a sample function before sampling.')
+        goal_grid = self.sample_func(pose_x, pose_y, pose_theta, velocity, waypoints)
+        return goal_grid
+
+    def eval(self, all_traj, cost_weights):
+        """lattice_planner.py:130-156 (user cost functions, host)."""
+        if len(self.cost_funcs) == 0:
+            raise NotImplementedError('Please set cost functions before evaluating.')
+        if len(self.cost_funcs) != len(cost_weights):
+            raise ValueError('Length of cost weights must be the same as number of cost functions.')
+        if np.sum(cost_weights) != 1:
+            raise ValueError('Cost weights must add up to 1.')
+        all_costs = []
+        for traj in all_traj:
+            cost = 0.
+            for i, func in enumerate(self.cost_funcs):
+                cost += cost_weights[i] * func(traj)
+            all_costs.append(cost)
+        return all_costs
+
+    def select(self, all_costs):
+        """lattice_planner.py:159-172"""
+        if self.selection_func is None:
+            self.selection_func = np.argmin
+        best_idx = self.selection_func(all_costs)
+        return best_idx
+
+    # -- additive configuration -----------------------------------------------------------------
+    def set_goal_grid(self, lookahead_distances, widths):
+        self._lookaheads = np.asarray(lookahead_distances, dtype=np.float64).ravel()
+        self._widths = np.asarray(widths, dtype=np.float64).ravel()
+        self._grid_dirty = True
+
+    def set_map(self, occupancy, origin, resolution):
+        """uint8 occupancy [H,W] (0 free), origin (x, y) of cell (0,0), metres per cell."""
+        self._map = (np.ascontiguousarray(occupancy, dtype=np.uint8), tuple(origin), float(resolution))
+        if self._engine is not None:
+            self._engine.set_grid(*self._map)
+
+    def configure(self, **config):
+        self._config.update(config)
+        if self._engine is not None:
+            self._engine.configure(**config)
+
+    @property
+    def engine(self):
+        return self._sync()
+
+    def _sync(self):
+        if self.waypoints is None:
+            raise ValueError('Please set waypoints during planner instantiation or when calling plan()')
+        if self._engine is None:
+            self._engine = Engine(device=self._device, **self._config)
+            if self._map is not None:
+                self._engine.set_grid(*self._map)
+        w = np.ascontiguousarray(self.waypoints, dtype=np.float64)
+        key = (w.shape, zlib.crc32(w.tobytes()))
+        if key != self._key:
+            if w.ndim != 2 or w.shape[1] < 4:
+                raise ValueError('Waypoints needs to be a (Nxm), m >= 4 (x, y, v, psi[, kappa]), numpy array!')
+            self._engine.set_track(w)
+            self._key = key
+        if self._grid_dirty:
+            self._engine.set_goal_grid(self._lookaheads, self._widths)
+            self._grid_dirty = False
+        return self._engine
+
+    # -- planning -------------------------------------------------------------------------------
+    def plan_detailed(self, pose_x, pose_y, pose_theta, velocity, waypoints=None,
+                      opponent_poses=None, want_states=False):
+        """Full result of one query as a PlanDetail (see engine.PlanDetail)."""
+        if waypoints is not None:
+            self.waypoints = waypoints
+        eng = self._sync()
+        pose = np.array([pose_x, pose_y, pose_theta, velocity], dtype=np.float64)
+        custom_cost = len(self.cost_funcs) > 0
+        custom_select = self.selection_func is not None and self.selection_func is not np.argmin
+        need_states = want_states or custom_cost or custom_select
+        if self.sample_func is not None:
+            goal_grid = np.asarray(self.sample(pose_x, pose_y, pose_theta, velocity, self.waypoints),
+                                   dtype=np.float64).reshape(-1, 3)
+            d = eng.plan_goals(pose, goal_grid, opponent_poses, want_states=need_states)
+        else:
+            d = eng.plan(pose, opponent_poses, want_states=need_states)
+        if custom_cost or custom_select:
+            # user python plug-ins: evaluate on the host over the GPU-generated trajectories
+            all_traj = d.states.astype(np.float64)
+            all_traj[:, :, 3] = np.abs(all_traj[:, :, 3])   # utils.py:293 column = |kappa|
+            if custom_cost:
+                weights = self.cost_weights
+                if weights is None:
+                    weights = [1.0 / len(self.cost_funcs)] * len(self.cost_funcs)
+                costs = np.asarray(self.eval(all_traj, weights), dtype=np.float64)
+            else:
+                costs = d.costs.astype(np.float64)
+            idx = int(self.select(costs))
+            best = d.states[idx].copy()
+            steer, speed = self.tracker.plan(pose_x, pose_y, pose_theta,
+                                             eng.config.tracker_lookahead,
+                                             all_traj[idx])                  # :208-212
+            d = d._replace(steer=steer, speed=speed, best_traj=best, best_idx=idx,
+                           best_cost=float(costs[idx]), costs=costs.astype(np.float32))
+        self.last = d
+        return d
+
+    def plan(self, pose_x, pose_y, pose_theta, velocity, waypoints=None, opponent_poses=None):
+        """lattice_planner.py:174-214 -> (steering_angle, speed, selected_traj [M,4]).
+
+        selected_traj columns are (x, y, theta, |kappa|) in the vehicle frame like
+        utils.sample_traj (utils/utils.py:285-295); the signed-curvature float32 trajectory,
+        index, cost vector and flags are in ``self.last``."""
+        d = self.plan_detailed(pose_x, pose_y, pose_theta, velocity, waypoints, opponent_poses)
+        traj = d.best_traj.astype(np.float64)
+        traj[:, 3] = np.abs(traj[:, 3])
+        return d.steer, d.speed, traj
+
+    def plan_batch(self, poses, opponents=None, n_opp=None, **kw):
+        """S independent scenarios: poses [S,4], opponents [S,K,3], n_opp [S] -> BatchPlan
+        (best_idx [S], best_cost [S], best_traj [S,M,4], costs [S,C], flags, steer_speed [S,2])."""
+        return self._sync().plan_batch(poses, opponents, n_opp, **kw)
+
+
+# ---------------------------------------------------------------------------------------------
+# example sampler / cost helpers with the reference's names
+# ---------------------------------------------------------------------------------------------
+_sampler_planners = {}
+
+
+def sample_lookahead_square(pose_x, pose_y, pose_theta, velocity, waypoints,
+                            lookahead_distances=[0.4, 0.6, 0.8, 1.0],
+                            widths=np.linspace(-1.0, 1.0, num=7)):
+    """Goal grid around look-ahead points on the raceline (lattice_planner.py:223-260, with the
+    repairs listed in DESIGN.md: every centre gets every width, offsets along the raceline
+    normal, goals in the vehicle frame).  Runs the GPU sampler; returns [n_L*n_W, 3]."""
+    w = np.ascontiguousarray(waypoints, dtype=np.float64)
+    key = (w.shape, zlib.crc32(w.tobytes()))
+    pl = _sampler_planners.get("p")
+    if pl is None:
+        pl = LatticePlanner()
+        _sampler_planners["p"] = pl
+    if _sampler_planners.get("key") != key:
+        pl.waypoints = w
+        _sampler_planners["key"] = key
+    pl.set_goal_grid(lookahead_distances, widths)
+    eng = pl._sync()
+    d = eng.plan(np.array([pose_x, pose_y, pose_theta, velocity], dtype=np.float64),
+                 update_prev=False)
+    return d.goals.astype(np.float64)
+
+
+def get_length_cost(param_list):
+    """lattice_planner.py:268-271"""
+    return 1. / param_list[:, 0]
+
+
+def get_max_curvature(traj_list, num_traj):
+    """lattice_planner.py:273-278 (NUM_STEPS defined here)"""
+    return np.max(np.abs(traj_list[:num_traj * NUM_STEPS, 3].reshape(num_traj, NUM_STEPS)), axis=1)
+
+
+def get_mean_curvature(traj_list, num_traj):
+    """lattice_planner.py:280-285"""
+    return np.mean(np.abs(traj_list[:num_traj * NUM_STEPS, 3].reshape(num_traj, NUM_STEPS)), axis=1)
+
+
+def get_similarity_cost(traj_list, prev_path, num_traj):
+    """lattice_planner.py:287-296"""
+    prev_shifted = prev_path[N_SHIFT:-N_CULL, 2]
+    th = traj_list[:num_traj * NUM_STEPS, 2].reshape(num_traj, NUM_STEPS)
+    return np.sum(np.square(th[:, :-N_SHIFT - N_CULL] - prev_shifted[None, :]), axis=1)

@@ -1,0 +1,249 @@
+/*
+ * f1l.h -- C-ABI of the B200-native lattice-planner hot path.
+ *
+ * The reference (f1tenth/f1tenth_planning) has no FFI: its boundary is the
+ * Python API.  Every entry point below names the reference interface it
+ * replaces (paths relative to the reference checkout).  The Python package
+ * f1tenth_planning_b200 binds these with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 (F1L_OK) or a negative f1l_status; nothing
+ *     throws across the ABI; f1l_strerror() names the code.
+ *   - the caller owns every buffer it passes; the handle owns the device
+ *     copies of track / grid / LUT / previous path and all scratch.
+ *   - "*_dev" entry points take DEVICE pointers and enqueue on the caller's
+ *     stream without synchronising; the others take HOST pointers, do their
+ *     own H2D/D2H on the handle's stream and synchronise it before returning.
+ *   - one handle per device; a handle is not thread-safe; handles are
+ *     independent of each other.
+ *   - all angles in radians, lengths in metres, arrays row-major.
+ */
+#ifndef F1L_H
+#define F1L_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct f1l_ctx* f1l_handle;
+
+typedef enum {
+    F1L_OK = 0,
+    F1L_ERR_INVALID_ARG = -1,
+    F1L_ERR_NO_TRACK = -2,
+    F1L_ERR_CUDA = -3,
+    F1L_ERR_NO_DEVICE = -4,
+    F1L_ERR_TOO_LARGE = -5,
+    F1L_ERR_NO_GOALS = -6,
+    F1L_ERR_ALLOC = -7
+} f1l_status;
+
+#define F1L_N_TERMS 5       /* length, max|kappa|, mean|kappa|, similarity, raceline deviation */
+#define F1L_MAX_OPP 16      /* opponents per scenario */
+#define F1L_MAX_M 256       /* arc samples per candidate */
+
+/* per-candidate flag bits (flags output) */
+#define F1L_FLAG_VALID 1u        /* Newton converged, s_f > 0, finite, max|kappa| <= kappa_max */
+#define F1L_FLAG_COLLIDE_OPP 2u  /* footprint overlaps an opponent rectangle */
+#define F1L_FLAG_COLLIDE_MAP 4u  /* a footprint probe hits an occupied / out-of-bounds cell */
+#define F1L_FLAG_NO_CENTRE 8u    /* lookahead circle found no raceline intersection for this row */
+
+/*
+ * Planner configuration.  Replaces the constructor kwargs / hard-coded numbers
+ * of the reference: LatticePlanner.__init__ (planning/lattice_planner/
+ * lattice_planner.py:44-55), samples per trajectory =100 (:197), tracker
+ * lookahead =0.8 (:211), the undefined N_SHIFT/N_CULL/NUM_STEPS globals of the
+ * cost helpers (:273-296), vehicle footprint LENGTH/WIDTH
+ * (control/kinematic_mpc/kinematic_mpc.py:60-61).
+ */
+typedef struct {
+    int32_t n_samples;       /* M, arc samples per candidate (2..F1L_MAX_M); ref 100 */
+    int32_t n_newton;        /* fixed Newton iterations per candidate; default 8 */
+    int32_t window;          /* W raceline-deviation window in segments; <=0 or >=N-1 -> all N-1 */
+    int32_t n_shift;         /* similarity cost: shift of the previous path; default 5 */
+    int32_t n_cull;          /* similarity cost: samples culled from the tail; default 10 */
+    int32_t literal_tracker; /* 1: reproduce lattice_planner.py:208-212 literally (map pose vs
+                                vehicle-frame trajectory, "speed" = theta column) */
+    int32_t use_goal_kappa;  /* 1: end curvature p3 = raceline kappa at the goal centre; 0: p3 = 0 */
+    int32_t reserved0;
+    double weights[F1L_N_TERMS]; /* cost weights (lattice_planner.py:130-156) */
+    double kappa_max;        /* candidates with max|kappa| above it are invalid; <=0 disables */
+    double car_length;       /* 0.58 */
+    double car_width;        /* 0.31 */
+    double converge_tol;     /* endpoint tolerance: |end - goal| < tol*max(1,|goal|); default 1e-4 */
+    double tracker_lookahead;/* 0.8 (lattice_planner.py:211) */
+    double wheelbase;        /* 0.33 */
+    double max_reacquire;    /* 20.0 (pure_pursuit.py:52) */
+} f1l_config;
+
+/* Fills *cfg with the defaults named above. */
+int f1l_default_config(f1l_config* cfg);
+
+/* Create / destroy the per-device planner state.  Replaces LatticePlanner.__init__
+ * (lattice_planner.py:44-55) and PurePursuitPlanner.__init__ (pure_pursuit.py:51-54).
+ * Builds the cubic-spiral seed LUT on the device (see f1l_get_lut). */
+int f1l_create(f1l_handle* out, int device, const f1l_config* cfg);
+int f1l_destroy(f1l_handle h);
+const char* f1l_strerror(int code);
+int f1l_set_config(f1l_handle h, const f1l_config* cfg);
+int f1l_get_config(f1l_handle h, f1l_config* cfg);
+int f1l_device(f1l_handle h);
+/* Last CUDA error string seen by this handle ("" if none). */
+const char* f1l_last_cuda_error(f1l_handle h);
+
+/* Track upload.  wpts is [N, ncols] float64 row-major, columns x, y[, v, psi, kappa]
+ * (examples/control/Spielberg_raceline.csv:1; pure_pursuit.py:101 uses col 2 as speed).
+ * Replaces `self.waypoints = waypoints` (lattice_planner.py:49, pure_pursuit.py:54,103). */
+int f1l_set_track(f1l_handle h, const double* wpts, int n, int ncols);
+
+/* Occupancy grid upload: occ is [H, W] uint8 row-major, 0 = free, non-zero = occupied,
+ * cell (row, col) covers [ox+col*res, ox+(col+1)*res) x [oy+row*res, ...).
+ * Replaces the map_collision stub (utils/utils.py:297-301). */
+int f1l_set_grid(f1l_handle h, const uint8_t* occ, int height, int width,
+                 double origin_x, double origin_y, double resolution);
+int f1l_clear_grid(f1l_handle h);
+
+/* Goal grid of the built-in sampler: lookahead distances x lateral widths.
+ * Replaces the kwargs of sample_lookahead_square (lattice_planner.py:228-229).
+ * Candidate index c = j*n_widths + k (lookahead-major). */
+int f1l_set_goal_grid(f1l_handle h, const double* lookaheads, int n_lookaheads,
+                      const double* widths, int n_widths);
+
+/* Spiral seed LUT [nx, ny, nt, 4] float32 = (p1, p2, s_f, converged) over local goals
+ * x in [x0,x1], y in [y0,y1], theta in [t0,t1].  The handle builds it on the device at
+ * f1l_create; these read it back / replace it.  dims/ranges: int[3], double[6]. */
+int f1l_get_lut_shape(f1l_handle h, int32_t dims[3], double ranges[6]);
+int f1l_get_lut(f1l_handle h, float* lut_out);
+int f1l_set_lut(f1l_handle h, const float* lut, const int32_t dims[3], const double ranges[6]);
+
+/* Previous plan for the similarity cost (lattice_planner.py:287-296 `prev_path`):
+ * theta column of the previous best trajectory, vehicle frame of the previous call.
+ * f1l_plan stores it automatically; these override / clear it. */
+int f1l_set_prev_path(f1l_handle h, const float* theta_prev, int m);
+int f1l_clear_prev_path(f1l_handle h);
+
+/*
+ * Result of one planning query (host memory, filled by f1l_plan*).
+ * The optional arrays may be NULL to skip that download.
+ */
+typedef struct {
+    /* scalars */
+    double steer;            /* tracker output (pure_pursuit.py:122 order: steer, speed) */
+    double speed;
+    int32_t best_idx;        /* argmin candidate, ties -> lowest index (lattice_planner.py:169-171) */
+    int32_t no_feasible;     /* 1 if every candidate cost is +inf (best_idx = 0) */
+    int32_t tracker_found;   /* 0 -> "Cannot find lookahead point" (pure_pursuit.py:112-114) */
+    int32_t n_candidates;    /* C */
+    float best_cost;
+    int32_t reserved;
+    /* arrays, caller-allocated */
+    float* best_traj;        /* [M,4] x, y, theta, kappa(signed) in the vehicle frame */
+    float* costs;            /* [C] total cost, +inf for invalid / collided */
+    float* terms;            /* [C,5] per-term costs (unweighted) */
+    uint8_t* flags;          /* [C] F1L_FLAG_* */
+    float* goals;            /* [C,3] local goals (x, y, theta) fed to the generator */
+    float* params;           /* [C,4] solved spiral (p1, p2, s_f, p3) */
+    float* states;           /* [C,M,4] every trajectory (debug / custom cost functions) */
+} f1l_plan_result;
+
+/*
+ * One planning query: sampler -> spiral generation -> fused cost + collision -> argmin ->
+ * tracker.  Replaces LatticePlanner.plan (lattice_planner.py:174-214).
+ * pose = (x, y, theta, velocity) map frame; opp = [K,3] map-frame (x, y, theta) or NULL.
+ * update_prev != 0 stores the best trajectory's theta column as the next call's prev_path.
+ */
+int f1l_plan(f1l_handle h, const double pose[4], const double* opp, int n_opp,
+             int update_prev, f1l_plan_result* out);
+
+/* Same, but only candidates [c_begin, c_end) are evaluated (candidate sharding of one dense
+ * query across GPUs; best_idx is still the global index). */
+int f1l_plan_shard(f1l_handle h, const double pose[4], const double* opp, int n_opp,
+                   int c_begin, int c_end, f1l_plan_result* out);
+
+/* Same pipeline with caller-supplied local goals [C,3] (vehicle frame) instead of the built-in
+ * sampler.  Replaces the user `sample_func` plug-in (lattice_planner.py:77-98,113-128). */
+int f1l_plan_goals(f1l_handle h, const double pose[4], const double* goals, int n_goals,
+                   const double* opp, int n_opp, int update_prev, f1l_plan_result* out);
+
+/* Trajectory generation only: goals [C,3] -> states [C,M,4], params [C,4], flags [C] (host).
+ * Replaces the Clothoid.G1Hermite + sample_traj loop (lattice_planner.py:195-198,
+ * utils/utils.py:285-295) for user cost functions evaluated on the host. */
+int f1l_generate(f1l_handle h, const double* goals, int n_goals,
+                 float* states, float* params, uint8_t* flags);
+
+/*
+ * Batch of S independent scenarios, device buffers, caller's stream, no sync.
+ *   poses_dev [S,4] f64, opp_dev [S,max_opp,3] f64, n_opp_dev [S] i32 (NULL -> all max_opp)
+ * outputs (any may be NULL):
+ *   best_idx [S] i32, best_cost [S] f32, best_traj [S,M,4] f32, costs [S,C] f32,
+ *   flags [S,C] u8, steer_speed [S,2] f64
+ */
+int f1l_plan_batch_dev(f1l_handle h, const double* poses_dev, const double* opp_dev,
+                       const int32_t* n_opp_dev, int n_scenarios, int max_opp,
+                       int32_t* best_idx_dev, float* best_cost_dev, float* best_traj_dev,
+                       float* costs_dev, uint8_t* flags_dev, double* steer_speed_dev,
+                       void* stream);
+
+/* Same with HOST buffers: chunked H2D -> kernels -> D2H pipeline on the handle's streams,
+ * synchronised before returning. */
+int f1l_plan_batch(f1l_handle h, const double* poses, const double* opp,
+                   const int32_t* n_opp, int n_scenarios, int max_opp,
+                   int32_t* best_idx, float* best_cost, float* best_traj,
+                   float* costs, uint8_t* flags, double* steer_speed);
+
+/*
+ * Batched nearest_point + pure-pursuit lookahead over B poses on the uploaded track.
+ * Replaces nearest_point (utils/utils.py:37-67), intersect_point (:69-151), get_actuation
+ * (:153-161) and PurePursuitPlanner._get_current_waypoint / plan (pure_pursuit.py:56-122).
+ *   poses [B,3] f64 (x, y, theta)
+ * outputs (any may be NULL):
+ *   nearest [B,4] f64 = (proj_x, proj_y, dist, t);  nearest_i [B] i32
+ *   lookahead [B,4] f64 = (p_x, p_y, t2, found);    lookahead_i [B] i32 (un-modded, may be -1)
+ *   actuation [B,2] f64 = (steer, speed);           status [B] i32 (1 intersect branch,
+ *                                                   2 reacquire branch, 0 no lookahead point)
+ */
+int f1l_pure_pursuit_batch_dev(f1l_handle h, const double* poses_dev, int n_poses,
+                               double lookahead_distance, double* nearest_dev,
+                               int32_t* nearest_i_dev, double* lookahead_dev,
+                               int32_t* lookahead_i_dev, double* actuation_dev,
+                               int32_t* status_dev, void* stream);
+int f1l_pure_pursuit_batch(f1l_handle h, const double* poses, int n_poses,
+                           double lookahead_distance, double* nearest, int32_t* nearest_i,
+                           double* lookahead, int32_t* lookahead_i, double* actuation,
+                           int32_t* status);
+
+/* intersect_point (utils/utils.py:69-151) for B independent queries on the uploaded track:
+ * points [B,2], radius, start parameter t [B]; out [B,4] = (p_x, p_y, t, found), out_i [B]. */
+int f1l_intersect_point_batch(f1l_handle h, const double* points, const double* t_start,
+                              int n, double radius, int wrap, double* out, int32_t* out_i);
+
+/* get_actuation (utils/utils.py:153-161) for B queries: in [B,7] = (pose_theta, lp_x, lp_y,
+ * lp_speed, pos_x, pos_y, lookahead_distance); out [B,2] = (speed, steer) in the reference's
+ * return order. */
+int f1l_get_actuation_batch(f1l_handle h, const double* in, int n, double wheelbase,
+                            double* out);
+
+/* Timing / evidence helpers: number of kernels launched by this handle so far, and the device
+ * time (ms, CUDA events on the handle's stream) of the kernels of the last host-pointer call. */
+int64_t f1l_launch_count(f1l_handle h);
+/* on != 0: f1l_plan* record CUDA events around their three kernels (read with
+ * f1l_last_kernel_ms); off by default to keep the single-query latency minimal. */
+int f1l_set_timing(f1l_handle h, int on);
+int f1l_last_kernel_ms(f1l_handle h, float* sample_ms, float* eval_ms, float* select_ms);
+
+/* FP32 FMA / MUFU pipe peak microbenchmarks (roofline denominators):
+ * returns achieved TFLOP/s (FMA = 2 FLOP) and MUFU Gop/s on the handle's device. */
+int f1l_measure_peaks(f1l_handle h, double* fp32_tflops, double* mufu_gops);
+
+/* Debug / test hook: the float32 per-query constants of the last f1l_plan* call, for
+ * teacher-forced collision checks.  out_f[72]: cos, sin of the pose heading; grid transform A00
+ * A01 A10 A11 fx fy; then 16 opponents x (x, y, cos, sin) in the vehicle frame.  out_i[6]: grid
+ * ix0, iy0, nearest segment, window start, window length, opponent count. */
+int f1l_debug_query_ctx(f1l_handle h, float* out_f, int32_t* out_i);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F1L_H */

@@ -1,0 +1,184 @@
+"""Lattice pipeline parity (through the C-ABI) vs the float64 oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from f1tenth_planning_b200 import synth
+from oracle import c_oracle as co
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(eng, cfg, world, pose, opp, verbose=False):
+    d = eng.plan(pose, opp, update_prev=False, want_states=True)
+    o = co.plan(cfg, world, pose, opp, want_states=True)
+    return d, o, H.compare_plan(d, o, cfg, verbose=verbose)
+
+
+def test_lut_matches_oracle():
+    from f1tenth_planning_b200.engine import Engine
+    eng = Engine()
+    lut, ranges = eng.get_lut()
+    ref = co.lut_build()
+    assert lut.shape == ref.shape
+    assert (lut[..., 3] == ref[..., 3]).mean() > 0.999
+    ok = (lut[..., 3] == 1) & (ref[..., 3] == 1)
+    assert ok.mean() > 0.5
+    np.testing.assert_allclose(lut[ok], ref[ok], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("seed", [1001, 7, 8, 9])
+def test_config1_default_grid(ellipse, seed):
+    """C1: 4x7 goals, M=100, 1 opponent, exact raceline window (W = N-1), kappa limit off so that
+    most of the 28 candidates are feasible."""
+    la, wd = synth.goal_grid(1)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, window=0, kappa_max=0.0)
+    pose, opp = H.scenario(ellipse, seed, 1)
+    d, o, st = _run(eng, cfg, world, pose, opp)
+    assert st["n_both_valid"] >= 10
+
+
+def test_config1_kappa_limit_and_grid(ellipse, corridor):
+    la, wd = synth.goal_grid(1)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, grid=corridor, window=0)
+    for seed in (11, 12, 13):
+        pose, opp = H.scenario(ellipse, seed, 1)
+        _run(eng, cfg, world, pose, opp)
+
+
+def test_config3_4096_candidates(ellipse, corridor):
+    """C3: 64x64 goals, M=100, 8 opponents + occupancy grid, W=128."""
+    la, wd = synth.goal_grid(3)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, grid=corridor)
+    pose, opp = H.scenario(ellipse, 1003, 8)
+    d, o, st = _run(eng, cfg, world, pose, opp, verbose=True)
+    assert st["n_both_valid"] > 1000
+    assert st["collide_map_count"] > 0 and st["collide_opp_count"] > 0
+    assert st["valid_mismatch"] <= 4 and st["collide_map_mismatch"] + st["collide_opp_mismatch"] <= 8
+
+
+def test_oracle_lut_seed_gives_same_answers(ellipse):
+    """Seeding Newton from the oracle's own float64 LUT instead of the device LUT must not move
+    the converged spirals beyond the tolerance."""
+    la, wd = synth.goal_grid(3)
+    eng, cfg, world = H.make_pair(ellipse, la[::4], wd[::4], use_device_lut=False)
+    pose, opp = H.scenario(ellipse, 5, 4)
+    _run(eng, cfg, world, pose, opp)
+
+
+def test_similarity_term_and_prev_path(ellipse):
+    la, wd = synth.goal_grid(1)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, window=0, kappa_max=0.0)
+    pose, opp = H.scenario(ellipse, 21, 1)
+    d0 = eng.plan(pose, opp, update_prev=True, want_states=True)
+    assert (d0.terms[:, 3] == 0).all()
+    world.set_prev(d0.best_traj[:, 2])
+    pose2 = pose + np.array([0.05, 0.02, 0.01, 0.0])
+    d1 = eng.plan(pose2, opp, update_prev=False, want_states=True)
+    o1 = co.plan(cfg, world, pose2, opp, want_states=True)
+    H.compare_plan(d1, o1, cfg)
+    assert (d1.terms[(d1.flags & 1) != 0, 3] > 0).any()
+
+
+def test_m200_and_other_sample_counts(ellipse, corridor):
+    la, wd = np.linspace(0.6, 3.5, 12), np.linspace(-1.0, 1.0, 9)
+    for m in (200, 64, 33, 128, 256):
+        eng, cfg, world = H.make_pair(ellipse, la, wd, grid=corridor, n_samples=m,
+                                      n_shift=2, n_cull=3)
+        pose, opp = H.scenario(ellipse, 30 + m, 3)
+        _run(eng, cfg, world, pose, opp)
+
+
+def test_spielberg_track(golden_spielberg):
+    wp = golden_spielberg["waypoints"]
+    la, wd = np.linspace(0.8, 3.0, 8), np.linspace(-0.8, 0.8, 9)
+    eng, cfg, world = H.make_pair(wp, la, wd)
+    for pose in ([0.0, -0.84, 3.40, 4.0], [-20.0, -6.0, 3.4, 5.0]):
+        d, o, st = _run(eng, cfg, world, np.array(pose), None)
+        assert st["n_both_valid"] > 20
+
+
+def test_no_feasible_and_off_track(ellipse):
+    la, wd = synth.goal_grid(1)
+    eng, cfg, world = H.make_pair(ellipse, la, wd)
+    pose = np.array([0.0, 0.0, 0.3, 3.0])   # centre of the oval: no lookahead intersection
+    d, o, st = _run(eng, cfg, world, pose, None)
+    assert d.no_feasible and d.best_idx == 0 and not np.isfinite(d.costs).any()
+    assert ((d.flags & 8) != 0).all()
+
+
+def test_explicit_goals_and_generate(ellipse):
+    la, wd = synth.goal_grid(1)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, kappa_max=0.0)
+    pose, opp = H.scenario(ellipse, 41, 2)
+    gx, gy = np.meshgrid(np.linspace(0.8, 3.5, 10), np.linspace(-1.0, 1.0, 11), indexing="ij")
+    goals = np.stack([gx.ravel(), gy.ravel(), 0.2 * gy.ravel()], axis=1)
+    d = eng.plan_goals(pose, goals, opp, update_prev=False, want_states=True)
+    o = co.plan(cfg, world, pose, opp, goals=goals, want_states=True)
+    H.compare_plan(d, o, cfg)
+    states, params, valid = eng.generate(goals)
+    both = valid & ((o["flags"] & 1) != 0)
+    assert both.sum() > 80
+    assert H.close(states[both], o["states"][both]).all()
+
+
+def test_candidate_sharding_matches_unsharded(ellipse, corridor):
+    la, wd = synth.goal_grid(3)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, grid=corridor)
+    pose, opp = H.scenario(ellipse, 77, 8)
+    full = eng.plan(pose, opp, update_prev=False)
+    C = eng.n_candidates
+    best = (np.inf, -1)
+    for g in range(4):
+        lo, hi = g * C // 4, (g + 1) * C // 4
+        part = eng.plan(pose, opp, update_prev=False, shard=(lo, hi))
+        assert np.array_equal(part.costs[lo:hi], full.costs[lo:hi])
+        assert not np.isfinite(part.costs[:lo]).any() and not np.isfinite(part.costs[hi:]).any()
+        if (part.best_cost, part.best_idx) < best:
+            best = (float(part.best_cost), int(part.best_idx))
+    assert best[1] == full.best_idx
+
+
+def test_batch_matches_single_and_oracle(ellipse, corridor):
+    la, wd = synth.goal_grid(4)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, grid=corridor, kappa_max=3.0)
+    S, K = 96, 8
+    poses, opp, n_opp = synth.scenario_batch(ellipse, S, K, 1004)
+    b = eng.plan_batch(poses, opp, n_opp, want_flags=True)
+    o = co.plan_batch(cfg, world, poses, opp, n_opp, n_threads=co.max_threads())
+    fin = np.isfinite(o["costs"]) & np.isfinite(b.costs)
+    assert fin.sum() > 200
+    assert H.close(b.costs[fin], o["costs"][fin]).all()
+    assert (np.isfinite(o["costs"]) != np.isfinite(b.costs)).mean() < 0.01
+    agree = b.best_idx == o["best_idx"]
+    for s in np.nonzero(~agree)[0]:
+        gap = abs(float(o["costs"][s, b.best_idx[s]]) - float(o["best_cost"][s]))
+        assert gap < 1e-5, (s, gap)
+    ok = agree & np.isfinite(o["best_cost"])
+    assert ok.sum() > 50
+    assert H.close(b.best_traj[ok], o["best_traj"][ok]).all()
+    assert H.close(b.steer_speed[ok], o["steer_speed"][ok], 1e-4, 1e-4).all()
+    for s in (0, 17, 95):
+        d = eng.plan(poses[s], opp[s, :n_opp[s]], update_prev=False)
+        assert d.best_idx == b.best_idx[s]
+        assert np.array_equal(d.costs, b.costs[s])
+        assert np.array_equal(d.best_traj, b.best_traj[s])
+
+
+def test_batch_device_pointer_api(ellipse):
+    import torch
+    la, wd = synth.goal_grid(4)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, kappa_max=3.0)
+    S, K = 64, 4
+    poses, opp, n_opp = synth.scenario_batch(ellipse, S, K, 5)
+    dev = torch.device("cuda", eng.device)
+    tp, to = torch.from_numpy(poses).to(dev), torch.from_numpy(opp).to(dev)
+    tn = torch.from_numpy(n_opp).to(dev)
+    idx = torch.empty(S, dtype=torch.int32, device=dev)
+    cost = torch.empty(S, dtype=torch.float32, device=dev)
+    costs = torch.empty(S, eng.n_candidates, dtype=torch.float32, device=dev)
+    eng.plan_batch_dev(tp, to, tn, best_idx=idx, best_cost=cost, costs=costs)
+    torch.cuda.synchronize(dev)
+    b = eng.plan_batch(poses, opp, n_opp)
+    assert np.array_equal(idx.cpu().numpy(), b.best_idx)
+    assert np.array_equal(costs.cpu().numpy(), b.costs)

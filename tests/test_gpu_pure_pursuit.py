@@ -1,0 +1,123 @@
+"""K1 parity (through the C-ABI): batched nearest_point + pure pursuit vs the golden vectors minted
+from the reference and vs the oracle at BASELINE config 2 sizes."""
+import numpy as np
+import pytest
+
+from f1tenth_planning_b200 import synth
+from oracle import c_oracle as co
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(track):
+    from f1tenth_planning_b200.engine import Engine
+    eng = Engine()
+    eng.set_track(track)
+    return eng
+
+
+def _check(r, g, n_wp):
+    """r: PurePursuitBatch (GPU), g: dict of reference outputs."""
+    gi = g["nearest_i"]
+    same = r.nearest_i == gi
+    # (k, t=1) == (k+1, t=0): a vertex tie may resolve to the neighbouring segment
+    for k in np.nonzero(~same)[0]:
+        assert abs(int(r.nearest_i[k]) - int(gi[k])) == 1, (k, r.nearest_i[k], gi[k])
+        assert abs(r.nearest[k, 2] - g["nearest"][k, 2]) < 1e-9
+    assert (~same).mean() < 0.02
+    np.testing.assert_allclose(r.nearest[same], g["nearest"][same], rtol=1e-9, atol=1e-9)
+    m = (g["nearest"][:, 2] < 0.8) & same
+    found = g["lookahead"][:, 3] > 0
+    assert (r.lookahead[m, 3] > 0).tolist() == found[m].tolist()
+    mf = m & found
+    assert (r.lookahead_i[mf] == g["lookahead_i"][mf]).all()
+    np.testing.assert_allclose(r.lookahead[mf, :3], g["lookahead"][mf, :3], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(r.actuation[same], g["actuation"][same], rtol=1e-9, atol=1e-9)
+
+
+def test_golden_spielberg(golden_spielberg):
+    g = golden_spielberg
+    eng = _engine(g["waypoints"])
+    r = eng.pure_pursuit_batch(g["poses"], float(g["lookahead_distance"]))
+    _check(r, g, g["waypoints"].shape[0])
+    # the three known-answer poses of SURVEY appendix C
+    assert r.nearest_i[:3].tolist() == [1690, 103, 1659]
+    assert r.lookahead_i[0] == 3 and r.lookahead_i[1] == 106
+    np.testing.assert_allclose(r.actuation[:3, 0], [-0.00035935558090650324, 0.22560092622792158,
+                                                    -1.3435444691165728], rtol=1e-9)
+    assert r.status[:3].tolist() == [1, 1, 2]
+
+
+def test_golden_ellipse(golden_ellipse, ellipse):
+    eng = _engine(ellipse)
+    r = eng.pure_pursuit_batch(golden_ellipse["poses"], 0.8)
+    _check(r, golden_ellipse, ellipse.shape[0])
+
+
+def test_config2_sample_vs_oracle(ellipse):
+    """10^5 poses on the 2k-waypoint track; a 4000-pose sample against the oracle, the rest by
+    properties (projection lies on its segment, distance consistent, t in [0,1])."""
+    rng = np.random.default_rng(1002)
+    poses, _ = synth.random_poses(ellipse, 100000, rng)
+    poses = poses[:, :3].copy()
+    eng = _engine(ellipse)
+    r = eng.pure_pursuit_batch(poses, 0.8)
+    sub = rng.choice(100000, 4000, replace=False)
+    o = co.pure_pursuit_batch(ellipse, poses[sub], 0.8, n_threads=co.max_threads())
+    same = r.nearest_i[sub] == o["nearest_i"]
+    assert (~same).mean() < 0.02
+    np.testing.assert_allclose(r.nearest[sub][same], o["nearest"][same], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(r.actuation[sub][same], o["actuation"][same], rtol=1e-9, atol=1e-9)
+    assert (r.status[sub][same] == o["status"][same]).all()
+    # properties at full size
+    i = r.nearest_i
+    a, b = ellipse[i, :2], ellipse[i + 1, :2]
+    t = r.nearest[:, 3]
+    assert ((t >= 0) & (t <= 1)).all()
+    proj = a + t[:, None] * (b - a)
+    np.testing.assert_allclose(proj, r.nearest[:, :2], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(np.hypot(*(poses[:, :2] - proj).T), r.nearest[:, 2], rtol=0, atol=1e-9)
+    # no vertex of the track is closer than the reported nearest distance
+    d_vert = np.min(np.hypot(poses[:2000, None, 0] - ellipse[None, :, 0],
+                             poses[:2000, None, 1] - ellipse[None, :, 1]), axis=1)
+    assert (r.nearest[:2000, 2] <= d_vert + 1e-9).all()
+
+
+def test_free_functions_match_reference(golden_spielberg, golden_misc):
+    from f1tenth_planning_b200 import utils
+    g, m = golden_spielberg, golden_misc
+    xy = g["waypoints"][:, :2]
+    for k in (0, 1, 2, 10, 50):
+        p, d, t, i = utils.nearest_point(g["poses"][k, :2], xy)
+        assert i == g["nearest_i"][k]
+        np.testing.assert_allclose([p[0], p[1], d, t], g["nearest"][k], rtol=1e-9, atol=1e-9)
+    for k in range(0, 300, 7):
+        p, i, t = utils.intersect_point(m["ip_points"][k], m["ip_radius"][k], xy, m["ip_t"][k],
+                                        bool(m["ip_wrap"][k]))
+        if m["ip_out"][k, 3] == 0:
+            assert p is None and i is None and t is None
+        else:
+            assert i == m["ip_i"][k]
+            np.testing.assert_allclose([p[0], p[1], t], m["ip_out"][k, :3], rtol=1e-9, atol=1e-9)
+    for k in range(m["act_in"].shape[0]):
+        r = m["act_in"][k]
+        sp, st = utils.get_actuation(r[0], r[1:4], r[4:6], r[6], 0.33)
+        np.testing.assert_allclose([sp, st], m["act_out"][k], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(utils.get_rotation_matrix(0.3), m["rot_03"])
+    assert [utils.pi_2_pi(a) for a in m["angles"]] == m["pi_2_pi"].tolist()
+
+
+def test_planner_class_api(golden_spielberg):
+    from f1tenth_planning_b200 import PurePursuitPlanner
+    g = golden_spielberg
+    pl = PurePursuitPlanner(waypoints=g["waypoints"])
+    for k in (0, 1, 2):
+        steer, speed = pl.plan(*g["poses"][k], 0.8)
+        np.testing.assert_allclose([steer, speed], g["actuation"][k], rtol=1e-9, atol=1e-12)
+    with pytest.raises(ValueError):
+        PurePursuitPlanner().plan(0.0, 0.0, 0.0, 0.8)
+    with pytest.raises(ValueError):
+        pl.plan(0.0, 0.0, 0.0, 0.8, waypoints=np.zeros((5, 2)))
+    far = PurePursuitPlanner(waypoints=g["waypoints"])
+    with pytest.warns(UserWarning):
+        assert far.plan(500.0, 500.0, 0.0, 0.8) == (0.0, 0.0)
