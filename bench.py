@@ -1,0 +1,453 @@
+#!/usr/bin/env python
+"""bench.py -- lattice candidates evaluated / s (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c4]
+
+A step = one pass of the hot path (sampler -> spiral generation -> fused cost + collision ->
+argmin -> tracker) over one batch of synthetic planning scenarios:
+per GPU 10^5 independent scenarios x the default 4x7 goal grid = 2.8e6 candidates, M=100 arc
+samples, raceline window W=128, up to 8 opponents, occupancy grid on.  Scenarios are independent,
+so ranks shard them with no data-path collective (weak scaling; the only collectives are the
+barrier and the max-over-ranks of the step time).
+
+`value` is device-resident throughput (inputs in HBM, CUDA events); `e2e` is the same metric
+through the public Python API (LatticePlanner.plan_batch) with pinned HOST buffers, H2D and D2H
+inside the timed region.  `--impl reference` times the CPU oracle port (the reference's lattice
+path cannot execute: SURVEY.md section 0) on all host cores on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from f1tenth_planning_b200 import flops as F  # noqa: E402
+from f1tenth_planning_b200 import synth  # noqa: E402
+
+METRIC = "lattice candidates evaluated/sec"
+UNIT = "candidates/s"
+S_PER_GPU = 100000
+K_OPP = 8
+PLAN_CFG = dict(n_samples=100, n_newton=8, window=128, kappa_max=0.0)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c4"])
+    ap.add_argument("--scenarios", type=int, default=S_PER_GPU, help="scenarios per GPU per step")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C2/C3/C5 side measurements")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload(seed_rank, S):
+    track = synth.ellipse_track()
+    grid = synth.corridor_grid()
+    la, wd = synth.goal_grid(4)
+    poses, opp, n_opp = synth.scenario_batch(track, S, K_OPP, 1004 + 7919 * seed_rank)
+    return track, grid, la, wd, poses, opp, n_opp
+
+
+def work_flops(flags, M, W, n_opp_mean):
+    """algorithmic FLOPs of one step from the validity flags it produced (appendix D)"""
+    valid = (flags & 1) != 0
+    n_full = int(valid.sum())
+    n_short = int(valid.size - n_full)
+    return (n_full * F.candidate_flops(M=M, W=W, K=n_opp_mean, full=True) +
+            n_short * F.candidate_flops(M=M, W=W, K=n_opp_mean, full=False)), n_full / valid.size
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(track, grid, la, wd, poses, opp, n_opp, seconds, threads=None):
+    """oracle port on the host cores: (cand/s, sample size, threads)"""
+    from oracle import c_oracle as co
+    threads = threads or co.max_threads()
+    world = co.World_(track, la, wd, grid=grid[0], grid_origin=grid[1], grid_res=grid[2])
+    cfg = co.default_config(**PLAN_CFG)
+    C = world.n_candidates
+    n0 = min(poses.shape[0], 16 * threads)
+    t = time.perf_counter()
+    co.plan_batch(cfg, world, poses[:n0], opp[:n0], n_opp[:n0], n_threads=threads,
+                  want_traj=True, want_costs=True)
+    rate = n0 * C / (time.perf_counter() - t)
+    n = int(max(n0, min(poses.shape[0], rate * seconds / C)))
+    t = time.perf_counter()
+    co.plan_batch(cfg, world, poses[:n], opp[:n], n_opp[:n], n_threads=threads, want_traj=True,
+                  want_costs=True)
+    dt = time.perf_counter() - t
+    return n * C / dt, n, threads, dt
+
+
+def run_reference(args):
+    """--impl reference: the CPU path on the host cores, rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import c_oracle as co
+    threads = co.max_threads()
+    track, grid, la, wd, poses, opp, n_opp = workload(0, 20000)
+    world = co.World_(track, la, wd, grid=grid[0], grid_origin=grid[1], grid_res=grid[2])
+    cfg = co.default_config(**PLAN_CFG)
+    C = world.n_candidates
+    # size one step so that warmup + steps fit in ~2 minutes
+    n0 = 16 * threads
+    t = time.perf_counter()
+    co.plan_batch(cfg, world, poses[:n0], opp[:n0], n_opp[:n0], n_threads=threads)
+    rate = n0 * C / (time.perf_counter() - t)
+    budget = min(10.0, 120.0 / max(1, args.steps + args.warmup))
+    n = int(max(n0, min(poses.shape[0], rate * budget / C)))
+    for _ in range(args.warmup):
+        co.plan_batch(cfg, world, poses[:n], opp[:n], n_opp[:n], n_threads=threads)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        co.plan_batch(cfg, world, poses[:n], opp[:n], n_opp[:n], n_threads=threads)
+    dt = time.perf_counter() - t
+    value = n * C * args.steps / dt
+    sample = "%d scenarios x %d candidates per step (bounded sample of the 10^5-scenario workload)" % (n, C)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "c4: independent scenarios x 4x7 goal grid, M=100, W=128, <=8 opponents, grid on",
+                   "note": "reference lattice path cannot execute (SURVEY 0.1); this is the C oracle port "
+                           "(oracle/c/f1o.c), OpenMP over scenarios"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def extras(track, grid, device):
+    """side measurements (not the headline): C3 plan() latency, C2 poses/s, C5 dense sweep."""
+    import torch
+    from f1tenth_planning_b200.engine import Engine
+    out = {}
+    # C3: single query, 4096 candidates
+    la, wd = synth.goal_grid(3)
+    eng = Engine(device=device, n_samples=100, window=128)
+    eng.set_track(track)
+    eng.set_grid(*grid)
+    eng.set_goal_grid(la, wd)
+    poses, opp, n_opp = synth.scenario_batch(track, 64, 8, 1003)
+    for i in range(5):
+        eng.plan(poses[i], opp[i], update_prev=False, detail=False)
+    ts = []
+    for i in range(300):
+        s = i % 64
+        t = time.perf_counter()
+        eng.plan(poses[s], opp[s], update_prev=True, detail=False)
+        ts.append(time.perf_counter() - t)
+    out["c3_plan_p50_us"] = 1e6 * float(np.percentile(ts, 50))
+    out["c3_plan_p99_us"] = 1e6 * float(np.percentile(ts, 99))
+    eng.set_timing(True)
+    for i in range(20):
+        eng.plan(poses[i], opp[i], update_prev=False, detail=False)
+    sm, ev, se, n = eng.mean_kernel_ms()
+    out["c3_kernel_us"] = {"sample": 1e3 * sm, "eval": 1e3 * ev, "select": 1e3 * se}
+    out["c3_eval_candidates_per_s"] = 4096 / (ev * 1e-3) if ev > 0 else None
+    eng.close()
+    # C5: dense sweep 65536 x 200
+    la, wd = synth.goal_grid(5)
+    eng = Engine(device=device, n_samples=200, window=128)
+    eng.set_track(track)
+    eng.set_grid(*grid)
+    eng.set_goal_grid(la, wd)
+    eng.set_timing(True)
+    for i in range(3):
+        eng.plan(poses[i], opp[i], update_prev=False, detail=False)
+    eng.set_timing(True)
+    ts = []
+    for i in range(10):
+        t = time.perf_counter()
+        eng.plan(poses[i], opp[i], update_prev=False, detail=False)
+        ts.append(time.perf_counter() - t)
+    sm, ev, se, n = eng.mean_kernel_ms()
+    out["c5_plan_p50_us"] = 1e6 * float(np.percentile(ts, 50))
+    out["c5_eval_candidates_per_s"] = 65536 / (ev * 1e-3) if ev > 0 else None
+    eng.close()
+    # C2: 10^5 poses pure pursuit, device resident
+    eng = Engine(device=device)
+    eng.set_track(track)
+    rng = np.random.default_rng(1002)
+    pp, _ = synth.random_poses(track, 100000, rng)
+    dev = torch.device("cuda", device)
+    tp = torch.from_numpy(np.ascontiguousarray(pp[:, :3])).to(dev)
+    near = torch.empty(100000, 4, dtype=torch.float64, device=dev)
+    ni = torch.empty(100000, dtype=torch.int32, device=dev)
+    look = torch.empty(100000, 4, dtype=torch.float64, device=dev)
+    li = torch.empty(100000, dtype=torch.int32, device=dev)
+    act = torch.empty(100000, 2, dtype=torch.float64, device=dev)
+    stt = torch.empty(100000, dtype=torch.int32, device=dev)
+    for _ in range(3):
+        eng.pure_pursuit_batch_dev(tp, 0.8, near, ni, look, li, act, stt)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        eng.pure_pursuit_batch_dev(tp, 0.8, near, ni, look, li, act, stt)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / 10
+    out["c2_poses_per_s"] = 100000 / (ms * 1e-3)
+    out["c2_ms"] = ms
+    out["c2_fp32_tflops"] = 100000 * F.pose_flops(track.shape[0]) / (ms * 1e-3) / 1e12
+    eng.close()
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from f1tenth_planning_b200 import LatticePlanner
+    from f1tenth_planning_b200.engine import Engine, pinned_empty
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback "
+                           "(use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S = args.scenarios
+    track, grid, la, wd, poses, opp, n_opp = workload(rank, S)
+    eng = Engine(device=local, **PLAN_CFG)
+    eng.set_track(track)
+    eng.set_grid(*grid)
+    eng.set_goal_grid(la, wd)
+    C, M = eng.n_candidates, eng.n_samples
+    fp32_peak, mufu_peak = eng.measure_peaks()
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    tp = torch.from_numpy(poses).to(dev)
+    to = torch.from_numpy(opp).to(dev)
+    tn = torch.from_numpy(n_opp).to(dev)
+    o_idx = torch.empty(S, dtype=torch.int32, device=dev)
+    o_cost = torch.empty(S, dtype=torch.float32, device=dev)
+    o_traj = torch.empty(S, M, 4, dtype=torch.float32, device=dev)
+    o_costs = torch.empty(S, C, dtype=torch.float32, device=dev)
+    o_flags = torch.empty(S, C, dtype=torch.uint8, device=dev)
+    o_ss = torch.empty(S, 2, dtype=torch.float64, device=dev)
+
+    def step():
+        eng.plan_batch_dev(tp, to, tn, best_idx=o_idx, best_cost=o_cost, best_traj=o_traj,
+                           costs=o_costs, flags=o_flags, steer_speed=o_ss)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize(dev)
+    eng.set_timing(True)
+    sampler = ClockSampler(local)
+    if world_size > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler.start()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world_size > 1:
+        dist.barrier()
+    launches = eng.launch_count - l0
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    k_sample, k_eval, k_select, n_timed = eng.mean_kernel_ms()
+    eng.set_timing(False)
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_total = float(t_ms.item())
+    value = world_size * S * C * args.steps / (ms_total * 1e-3)
+
+    flags = o_flags.cpu().numpy()
+    step_flops, valid_frac = work_flops(flags, M, PLAN_CFG["window"], float(n_opp.mean()))
+    achieved_tflops = step_flops / (k_eval * 1e-3) / 1e12 if k_eval > 0 else None
+    hbm_bytes = S * C * F.candidate_hbm_bytes() + S * (M * 16 + 32 + 4 + 4 + 16) + S * (32 + K_OPP * 24 + 4)
+
+    # ---- end-to-end arm: public API, pinned host buffers, H2D + D2H inside the timed region ------
+    planner = LatticePlanner(waypoints=track, device=local, **PLAN_CFG)
+    planner.set_map(*grid)
+    planner.set_goal_grid(la, wd)
+    h_poses = pinned_empty(poses.shape, np.float64); h_poses[:] = poses
+    h_opp = pinned_empty(opp.shape, np.float64); h_opp[:] = opp
+    h_nopp = pinned_empty(n_opp.shape, np.int32); h_nopp[:] = n_opp
+    h_out = {"best_idx": pinned_empty((S,), np.int32), "best_cost": pinned_empty((S,), np.float32),
+             "best_traj": pinned_empty((S, M, 4), np.float32),
+             "costs": pinned_empty((S, C), np.float32),
+             "steer_speed": pinned_empty((S, 2), np.float64)}
+    for _ in range(2):
+        planner.plan_batch(h_poses, h_opp, h_nopp, out=h_out)
+    if world_size > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e2e_steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r = planner.plan_batch(h_poses, h_opp, h_nopp, out=h_out)
+    torch.cuda.synchronize(dev)
+    t_e2e = time.perf_counter() - t0
+    t_e = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_value = world_size * S * C * e2e_steps / float(t_e.item())
+    assert np.array_equal(r.best_idx, o_idx.cpu().numpy()), "e2e and device-resident arms disagree"
+    h2d = h_poses.nbytes + h_opp.nbytes + h_nopp.nbytes
+    d2h = sum(v.nbytes for v in h_out.values())
+
+    if rank != 0:
+        if world_size > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {
+            "workload": "c4: %d independent scenarios per GPU x 4x7 goal grid (%d candidates/step/GPU), "
+                        "M=%d arc samples, raceline window W=%d, 1..%d opponents, occupancy grid on, "
+                        "kappa_max off (every converged candidate does the full cost+collision work)"
+                        % (S, S * C, M, PLAN_CFG["window"], K_OPP),
+            "track": "ellipse N=2000 a=80 b=40", "grid": "3400x1800 @0.05 m",
+            "valid_frac": valid_frac, "feasible_frac": float(np.isfinite(o_costs.cpu().numpy()).mean()),
+            "l2": "per-step working set %.0f MB > 126 MB L2 (outputs rewritten every step); no explicit flush"
+                  % ((hbm_bytes + S * C * 4) / 1e6),
+        },
+        "roofline": {
+            "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+            "frac": achieved_tflops / fp32_peak if achieved_tflops else None,
+            "peak_source": "FFMA microbenchmark measured in this run (f1l_measure_peaks); "
+                           "MEASURED_PEAKS.json has no FP32 entry; nominal 74.4",
+            "kernel": "eval_kernel<4,13,8>", "kernel_ms": k_eval, "kernel_launches_timed": n_timed,
+            "kernel_share_of_step": k_eval / (ms_total / args.steps) if k_eval else None,
+            "flops_per_launch": step_flops,
+            "mufu_peak_gops": mufu_peak,
+            "traffic": None,
+            "hbm": {"algorithmic_bytes_per_step": hbm_bytes,
+                    "achieved_gbs": hbm_bytes / (ms_total / args.steps * 1e-3) / 1e9},
+        },
+        "kernels_ms": {"sample": k_sample, "eval": k_eval, "select": k_select},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "api": "LatticePlanner.plan_batch (pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            mp = json.load(f)
+        line["roofline"]["hbm"]["peak_gbs"] = mp.get("hbm_gbs")
+        line["roofline"]["hbm"]["frac"] = line["roofline"]["hbm"]["achieved_gbs"] / mp["hbm_gbs"]
+    except Exception:
+        line["roofline"]["hbm"]["peak_gbs"] = 6650.0
+        line["roofline"]["hbm"]["note"] = "fallback peak"
+    if world_size == 1 and not args.no_cpu_baseline:
+        v, n, th, dt = cpu_reference_rate(track, grid, la, wd, poses, opp, n_opp, seconds=12.0)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": th, "kind": "port",
+                                "sample": "%d of the %d scenarios (x%d candidates), %.1f s, C oracle "
+                                          "(oracle/c/f1o.c) with OpenMP over scenarios" % (n, S, C, dt)}
+    if world_size == 1 and not args.no_extras:
+        try:
+            line["extra"] = extras(track, grid, local)
+        except Exception as ex:  # side measurements must not lose the headline
+            line["extra"] = {"error": repr(ex)}
+    print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        # convenience: self-launch one rank per GPU the way the driver does
+        port = str(29500 + (os.getpid() % 2000))
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+                                   "--master-port", port, os.path.abspath(__file__)] + sys.argv[1:])
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,7 +36,10 @@ struct f1l_ctx {
     char err[512] = {0};
     int64_t launches = 0;
     int timing = 0;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int timed = 0;  // events of the last pipeline launch are valid
+#define F1L_EV_SLOTS 64
+    cudaEvent_t ev[4 * F1L_EV_SLOTS] = {nullptr};
+    int ev_next = 0, ev_count = 0;  // ring of (before sample, eval, select, after) event quads
     float last_ms[3] = {0, 0, 0};
     int sm_count = 148;
     // track
@@ -291,9 +294,10 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     sa.ctx = ctx;
     sa.centres = centres;
     sa.best = best;
-    if (time_it) cudaEventRecord(h->ev[0], stream);
+    cudaEvent_t* ev = h->ev + 4 * h->ev_next;
+    if (time_it) cudaEventRecord(ev[0], stream);
     sample_kernel<<<S, SAMPLE_THREADS, 0, stream>>>(sa);
-    if (time_it) cudaEventRecord(h->ev[1], stream);
+    if (time_it) cudaEventRecord(ev[1], stream);
 
     EvalArgs ea;
     ea.tr = sa.tr;
@@ -323,7 +327,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     const long long n_ctas = (long long)S * ea.ctas_per_scn;
     if (n_ctas > 0x7fffffffLL) return F1L_ERR_TOO_LARGE;
     eval_entry(M)<<<(unsigned)n_ctas, wpc * 32, smem, stream>>>(ea);
-    if (time_it) cudaEventRecord(h->ev[2], stream);
+    if (time_it) cudaEventRecord(ev[2], stream);
 
     SelectArgs se;
     se.tr = sa.tr;
@@ -345,7 +349,12 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     se.best_traj = o.best_traj;
     se.prev_theta_out = o.prev_out;
     select_entry(M)<<<S, 32, 0, stream>>>(se);
-    if (time_it) cudaEventRecord(h->ev[3], stream);
+    if (time_it) {
+        cudaEventRecord(ev[3], stream);
+        h->timed = 1;
+        h->ev_next = (h->ev_next + 1) % F1L_EV_SLOTS;
+        if (h->ev_count < F1L_EV_SLOTS) h->ev_count++;
+    }
     h->launches += 3;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, e, "pipeline launch");
@@ -408,14 +417,49 @@ int64_t f1l_launch_count(f1l_handle h) { return h ? h->launches : 0; }
 int f1l_set_timing(f1l_handle h, int on) {
     if (!h) return F1L_ERR_INVALID_ARG;
     h->timing = on;
+    h->ev_next = 0;
+    h->ev_count = 0;
+    h->timed = 0;
     return F1L_OK;
 }
 
 int f1l_last_kernel_ms(f1l_handle h, float* sample_ms, float* eval_ms, float* select_ms) {
     if (!h) return F1L_ERR_INVALID_ARG;
+    if (h->timing && h->timed) {
+        CK(cudaSetDevice(h->device));
+        cudaEvent_t* ev = h->ev + 4 * ((h->ev_next + F1L_EV_SLOTS - 1) % F1L_EV_SLOTS);
+        CK(cudaEventSynchronize(ev[3]));
+        cudaEventElapsedTime(&h->last_ms[0], ev[0], ev[1]);
+        cudaEventElapsedTime(&h->last_ms[1], ev[1], ev[2]);
+        cudaEventElapsedTime(&h->last_ms[2], ev[2], ev[3]);
+    }
     if (sample_ms) *sample_ms = h->last_ms[0];
     if (eval_ms) *eval_ms = h->last_ms[1];
     if (select_ms) *select_ms = h->last_ms[2];
+    return F1L_OK;
+}
+
+int f1l_mean_kernel_ms(f1l_handle h, float* sample_ms, float* eval_ms, float* select_ms,
+                       int* n_launches) {
+    if (!h) return F1L_ERR_INVALID_ARG;
+    double acc[3] = {0, 0, 0};
+    const int n = h->ev_count;
+    if (n > 0) {
+        CK(cudaSetDevice(h->device));
+        for (int k = 0; k < n; ++k) {
+            cudaEvent_t* ev = h->ev + 4 * ((h->ev_next + F1L_EV_SLOTS - 1 - k) % F1L_EV_SLOTS);
+            CK(cudaEventSynchronize(ev[3]));
+            for (int j = 0; j < 3; ++j) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[j], ev[j + 1]);
+                acc[j] += ms;
+            }
+        }
+    }
+    if (sample_ms) *sample_ms = n ? (float)(acc[0] / n) : 0.f;
+    if (eval_ms) *eval_ms = n ? (float)(acc[1] / n) : 0.f;
+    if (select_ms) *select_ms = n ? (float)(acc[2] / n) : 0.f;
+    if (n_launches) *n_launches = n;
     return F1L_OK;
 }
 
@@ -463,7 +507,7 @@ int f1l_create(f1l_handle* out, int device, const f1l_config* cfg) {
     h->cfg = c;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
+    for (int i = 0; i < 4 * F1L_EV_SLOTS && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ev[i]);
     for (int i = 0; i < N_PIPE && e == cudaSuccess; ++i) {
         e = cudaStreamCreateWithFlags(&h->pipe[i].stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->pipe[i].done, cudaEventDisableTiming);
@@ -522,7 +566,7 @@ int f1l_destroy(f1l_handle h) {
         if (p.done) cudaEventDestroy(p.done);
         if (p.stream) cudaStreamDestroy(p.stream);
     }
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 4 * F1L_EV_SLOTS; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->h_in) cudaFreeHost(h->h_in);
     if (h->h_out) cudaFreeHost(h->h_out);
@@ -763,11 +807,6 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     if (out->params) CK(cudaMemcpyAsync(out->params, h->q_params.p, (size_t)C * 16, cudaMemcpyDeviceToHost, st));
     if (out->states) CK(cudaMemcpyAsync(out->states, h->q_states.p, (size_t)C * M * 16, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (h->timing) {
-        cudaEventElapsedTime(&h->last_ms[0], h->ev[0], h->ev[1]);
-        cudaEventElapsedTime(&h->last_ms[1], h->ev[1], h->ev[2]);
-        cudaEventElapsedTime(&h->last_ms[2], h->ev[2], h->ev[3]);
-    }
     if (update_prev) {
         h->has_prev = 1;
         h->prev_m = M;
@@ -852,7 +891,7 @@ int f1l_plan_batch_dev(f1l_handle h, const double* poses_dev, const double* opp_
     return launch_pipeline(h, (cudaStream_t)stream, poses_dev, max_opp > 0 ? opp_dev : nullptr,
                            n_opp_dev, S, max_opp, nullptr, 0, 0, 0, (QueryCtx*)h->b_ctx.p,
                            (Centre*)h->b_centres.p, (unsigned long long*)h->b_best.p, nullptr, o,
-                           false);
+                           h->timing != 0);
 }
 
 int f1l_plan_batch(f1l_handle h, const double* poses, const double* opp, const int32_t* n_opp,

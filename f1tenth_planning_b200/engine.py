@@ -336,6 +336,14 @@ class Engine:
         self._ck(self._L.f1l_last_kernel_ms(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
 
+    def mean_kernel_ms(self):
+        """(sample, eval, select, n): mean device ms per kernel over the launches recorded since
+        set_timing(True) (most recent 64)."""
+        a, b, c, n = C.c_float(), C.c_float(), C.c_float(), C.c_int()
+        self._ck(self._L.f1l_mean_kernel_ms(self._h, C.byref(a), C.byref(b), C.byref(c),
+                                            C.byref(n)))
+        return a.value, b.value, c.value, n.value
+
     def measure_peaks(self):
         """(FP32 FMA TFLOP/s, MUFU Gop/s) measured on this device."""
         a, b = C.c_double(), C.c_double()

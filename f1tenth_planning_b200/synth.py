@@ -57,14 +57,16 @@ def random_poses(track, s, rng):
 
 
 def random_opponents(track, idx, k, rng):
-    """[s,k,3] map-frame (x, y, theta), 0.5..3 m ahead of each pose's waypoint along the raceline."""
+    """[s,k,3] map-frame (x, y, theta), 1..5 m ahead of each pose's waypoint along the raceline
+    (SURVEY 8d suggested 0.5..3 m, which puts an opponent inside the ego footprint at t=0 in most
+    8-opponent scenarios and makes every candidate collide)."""
     n = track.shape[0]
     s = idx.shape[0]
     arc = _arc(track)
-    ahead = rng.uniform(0.5, 3.0, size=(s, k))
+    ahead = rng.uniform(1.0, 5.0, size=(s, k))
     target = np.mod(arc[idx][:, None] + ahead, arc[-1])
     j = np.clip(np.searchsorted(arc, target, side="right") - 1, 0, n - 1)
-    lat = rng.normal(0.0, 0.3, size=(s, k))
+    lat = rng.normal(0.0, 0.4, size=(s, k))
     psi = track[j, 3]
     x = track[j, 0] - lat * np.sin(psi)
     y = track[j, 1] + lat * np.cos(psi)

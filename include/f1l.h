@@ -231,6 +231,10 @@ int64_t f1l_launch_count(f1l_handle h);
 /* on != 0: f1l_plan* record CUDA events around their three kernels (read with
  * f1l_last_kernel_ms); off by default to keep the single-query latency minimal. */
 int f1l_set_timing(f1l_handle h, int on);
+/* Mean device time (ms) of the three kernels over the pipeline launches recorded since the last
+ * f1l_set_timing call (ring of the most recent 64), and how many launches that covers. */
+int f1l_mean_kernel_ms(f1l_handle h, float* sample_ms, float* eval_ms, float* select_ms,
+                       int* n_launches);
 int f1l_last_kernel_ms(f1l_handle h, float* sample_ms, float* eval_ms, float* select_ms);
 
 /* FP32 FMA / MUFU pipe peak microbenchmarks (roofline denominators):
