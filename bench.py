@@ -118,12 +118,17 @@ def workload(seed_rank, S):
 
 
 def work_flops(flags, M, W, n_opp_mean):
-    """algorithmic FLOPs of one step from the validity flags it produced (appendix D)"""
+    """algorithmic FLOPs of one step (appendix D) from the flags it produced: a candidate that
+    failed validation stops after generation; the Newton term counts the quadrature passes the
+    candidate actually used (flag bits 4..7) instead of the nominal 8."""
     valid = (flags & 1) != 0
+    passes = (flags >> 4).astype(np.float64)
     n_full = int(valid.sum())
     n_short = int(valid.size - n_full)
-    return (n_full * F.candidate_flops(M=M, W=W, K=n_opp_mean, full=True) +
-            n_short * F.candidate_flops(M=M, W=W, K=n_opp_mean, full=False)), n_full / valid.size
+    base = (n_full * F.candidate_flops(M=M, W=W, K=n_opp_mean, I=0, full=True) +
+            n_short * F.candidate_flops(M=M, W=W, K=n_opp_mean, I=0, full=False))
+    newton = float(passes.sum()) * (44 * (F.Q_NEWTON + 1) + 110)
+    return base + newton, n_full / valid.size, float(passes.mean())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -338,7 +343,7 @@ def run_ours(args):
     value = world_size * S * C * args.steps / (ms_total * 1e-3)
 
     flags = o_flags.cpu().numpy()
-    step_flops, valid_frac = work_flops(flags, M, PLAN_CFG["window"], float(n_opp.mean()))
+    step_flops, valid_frac, mean_passes = work_flops(flags, M, PLAN_CFG["window"], float(n_opp.mean()))
     achieved_tflops = step_flops / (k_eval * 1e-3) / 1e12 if k_eval > 0 else None
     hbm_bytes = S * C * F.candidate_hbm_bytes() + S * (M * 16 + 32 + 4 + 4 + 16) + S * (32 + K_OPP * 24 + 4)
 
@@ -388,7 +393,7 @@ def run_ours(args):
                         "kappa_max off (every converged candidate does the full cost+collision work)"
                         % (S, S * C, M, PLAN_CFG["window"], K_OPP),
             "track": "ellipse N=2000 a=80 b=40", "grid": "3400x1800 @0.05 m",
-            "valid_frac": valid_frac, "feasible_frac": float(np.isfinite(o_costs.cpu().numpy()).mean()),
+            "valid_frac": valid_frac, "newton_passes_mean": mean_passes, "feasible_frac": float(np.isfinite(o_costs.cpu().numpy()).mean()),
             "l2": "per-step working set %.0f MB > 126 MB L2 (outputs rewritten every step); no explicit flush"
                   % ((hbm_bytes + S * C * 4) / 1e6),
         },

@@ -33,6 +33,8 @@ def build(force=False, verbose=False):
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
            "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
            "-o", OUT] + [os.path.join(SRC_DIR, s) for s in SOURCES]
+    for d in os.environ.get("F1L_NVCC_DEFS", "").split():
+        cmd.insert(1, "-D" + d)   # e.g. F1L_NVCC_DEFS="EVAL_MIN_BLOCKS=4" for build-time experiments
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -24,7 +24,7 @@ struct DevBuf {
 struct PipeSlot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
-    DevBuf poses, opp, nopp, ctx, centres, best, idx, cost, traj, costs, flags, ss;
+    DevBuf poses, opp, nopp, ctx, centres, best, idx, cost, traj, costs, flags, ss, near_i, near4;
 };
 
 }  // namespace
@@ -46,7 +46,8 @@ struct f1l_ctx {
     int n = 0, ncols = 0;
     DevBuf xy, v, psi, kappa, segA, segB, blk;
     // grid
-    DevBuf grid;
+    DevBuf grid, clear, clear_tmp;
+    int use_clearance = 1;
     int gh = 0, gw = 0;
     double gox = 0, goy = 0, gres = 1;
     // lut
@@ -67,7 +68,7 @@ struct f1l_ctx {
     void* h_out = nullptr;  // header + best trajectory
     size_t h_out_cap = 0;
     // batch (device-pointer API) scratch
-    DevBuf b_ctx, b_centres, b_best;
+    DevBuf b_ctx, b_centres, b_best, b_near_i, b_near4;
     // batch pipeline (host-pointer API)
     PipeSlot pipe[N_PIPE];
     // misc scratch for the pure-pursuit / intersect host APIs
@@ -130,6 +131,12 @@ TrackView track_view(f1l_handle h) {
 GridView grid_view(f1l_handle h) {
     GridView g;
     g.occ = (const uint8_t*)h->grid.p;
+    g.clear = h->use_clearance ? (const uint8_t*)h->clear.p : nullptr;
+    // all nine probes fall within ceil(r_circ / res) cells of the centre cell (+1 for rounding)
+    const double rc = 0.5 * std::sqrt(h->cfg.car_length * h->cfg.car_length +
+                                      h->cfg.car_width * h->cfg.car_width);
+    g.probe_reach = (int)std::ceil(rc / h->gres) + 1;
+    if (g.probe_reach > CLEAR_R) g.clear = nullptr;  // map too fine for the clearance radius
     g.h = h->gh;
     g.w = h->gw;
     g.ox = h->gox;
@@ -261,8 +268,8 @@ struct BatchOut {
 int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, const double* opp,
                     const int32_t* n_opp, int S, int max_opp, const float4* goals, int n_goals,
                     int c_begin, int c_end, QueryCtx* ctx, Centre* centres,
-                    unsigned long long* best, const float* prev_theta, const BatchOut& o,
-                    bool time_it) {
+                    unsigned long long* best, int32_t* near_i, double* near4,
+                    const float* prev_theta, const BatchOut& o, bool time_it) {
     if (h->n < 2) return F1L_ERR_NO_TRACK;
     const int C = goals ? n_goals : h->nL * h->nW;
     if (C <= 0) return F1L_ERR_NO_GOALS;
@@ -296,7 +303,24 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     sa.best = best;
     cudaEvent_t* ev = h->ev + 4 * h->ev_next;
     if (time_it) cudaEventRecord(ev[0], stream);
-    sample_kernel<<<S, SAMPLE_THREADS, 0, stream>>>(sa);
+    if (near_i && near4 && S >= 32) {
+        // batch: nearest_point of all scenarios by the thread-per-pose scan kernel (K1), then one
+        // warp per scenario for the lookahead intersections / context
+        PPOut po;
+        po.nearest = near4;
+        po.nearest_i = near_i;
+        po.lookahead = nullptr;
+        po.lookahead_i = nullptr;
+        po.actuation = nullptr;
+        po.status = nullptr;
+        pp_batch_kernel<<<(S + PP_THREADS - 1) / PP_THREADS, PP_THREADS, PP_SMEM_BYTES, stream>>>(
+            sa.tr, poses, 4, S, -1.0, 0.33, 0.0, po);
+        sample_warp_kernel<<<(S + SAMPLE_WARPS - 1) / SAMPLE_WARPS, SAMPLE_WARPS * 32, 0, stream>>>(
+            sa, near_i, near4, S);
+        h->launches += 1;
+    } else {
+        sample_kernel<<<S, SAMPLE_THREADS, 0, stream>>>(sa);
+    }
     if (time_it) cudaEventRecord(ev[1], stream);
 
     EvalArgs ea;
@@ -550,18 +574,18 @@ int f1l_destroy(f1l_handle h) {
     if (!h) return F1L_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    DevBuf* bufs[] = {&h->xy, &h->v, &h->psi, &h->kappa, &h->segA, &h->segB, &h->blk, &h->grid,
+    DevBuf* bufs[] = {&h->xy, &h->v, &h->psi, &h->kappa, &h->segA, &h->segB, &h->blk, &h->grid, &h->clear, &h->clear_tmp,
                       &h->lut, &h->lookaheads, &h->widths, &h->prev, &h->q_in, &h->q_goals,
                       &h->q_ctx, &h->q_centres, &h->q_best, &h->q_idx, &h->q_cost, &h->q_status,
                       &h->q_ss, &h->q_traj, &h->q_costs, &h->q_terms, &h->q_flags, &h->q_gout,
                       &h->q_params, &h->q_states, &h->q_headings, &h->b_ctx, &h->b_centres,
-                      &h->b_best, &h->m_in, &h->m_in2, &h->m_o0, &h->m_o1, &h->m_o2, &h->m_o3,
+                      &h->b_best, &h->b_near_i, &h->b_near4, &h->m_in, &h->m_in2, &h->m_o0, &h->m_o1, &h->m_o2, &h->m_o3,
                       &h->m_o4, &h->m_o5};
     for (DevBuf* b : bufs) release(*b);
     for (int i = 0; i < N_PIPE; ++i) {
         PipeSlot& p = h->pipe[i];
         DevBuf* pb[] = {&p.poses, &p.opp, &p.nopp, &p.ctx, &p.centres, &p.best, &p.idx, &p.cost,
-                        &p.traj, &p.costs, &p.flags, &p.ss};
+                        &p.traj, &p.costs, &p.flags, &p.ss, &p.near_i, &p.near4};
         for (DevBuf* b : pb) release(*b);
         if (p.done) cudaEventDestroy(p.done);
         if (p.stream) cudaStreamDestroy(p.stream);
@@ -634,6 +658,18 @@ int f1l_set_grid(f1l_handle h, const uint8_t* occ, int height, int width, double
     ENS(h->grid, (size_t)height * width);
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(h->grid.p, occ, (size_t)height * width, cudaMemcpyHostToDevice));
+    ENS(h->clear, (size_t)height * width);
+    ENS(h->clear_tmp, (size_t)height * width);
+    {
+        dim3 blk(256), grd((width + 255) / 256, height);
+        clearance_h_kernel<<<grd, blk, 0, h->stream>>>((const uint8_t*)h->grid.p, height, width,
+                                                       (uint8_t*)h->clear_tmp.p);
+        clearance_v_kernel<<<grd, blk, 0, h->stream>>>((const uint8_t*)h->clear_tmp.p, height, width,
+                                                       (uint8_t*)h->clear.p);
+        h->launches += 2;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(h->stream));
+    }
     h->gh = height;
     h->gw = width;
     h->gox = ox;
@@ -647,6 +683,8 @@ int f1l_clear_grid(f1l_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     release(h->grid);
+    release(h->clear);
+    release(h->clear_tmp);
     h->gh = h->gw = 0;
     return F1L_OK;
 }
@@ -788,8 +826,9 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     int r = launch_pipeline(h, st, (const double*)h->q_in.p,
                             n_opp ? (const double*)h->q_in.p + 4 : nullptr, nullptr, 1, n_opp,
                             d_goals, C, c_begin, c_end, (QueryCtx*)h->q_ctx.p,
-                            (Centre*)h->q_centres.p, (unsigned long long*)h->q_best.p,
-                            h->has_prev ? (const float*)h->prev.p : nullptr, o, h->timing != 0);
+                            (Centre*)h->q_centres.p, (unsigned long long*)h->q_best.p, nullptr,
+                            nullptr, h->has_prev ? (const float*)h->prev.p : nullptr, o,
+                            h->timing != 0);
     if (r != F1L_OK) return r;
 
     // results -> pinned staging -> caller
@@ -881,6 +920,8 @@ int f1l_plan_batch_dev(f1l_handle h, const double* poses_dev, const double* opp_
     ENS(h->b_ctx, sizeof(QueryCtx) * (size_t)S);
     ENS(h->b_centres, sizeof(Centre) * (size_t)S * h->nL);
     ENS(h->b_best, 8 * (size_t)S);
+    ENS(h->b_near_i, 4 * (size_t)S);
+    ENS(h->b_near4, 32 * (size_t)S);
     BatchOut o;
     o.best_idx = best_idx_dev;
     o.best_cost = best_cost_dev;
@@ -890,7 +931,8 @@ int f1l_plan_batch_dev(f1l_handle h, const double* poses_dev, const double* opp_
     o.steer_speed = steer_speed_dev;
     return launch_pipeline(h, (cudaStream_t)stream, poses_dev, max_opp > 0 ? opp_dev : nullptr,
                            n_opp_dev, S, max_opp, nullptr, 0, 0, 0, (QueryCtx*)h->b_ctx.p,
-                           (Centre*)h->b_centres.p, (unsigned long long*)h->b_best.p, nullptr, o,
+                           (Centre*)h->b_centres.p, (unsigned long long*)h->b_best.p,
+                           (int32_t*)h->b_near_i.p, (double*)h->b_near4.p, nullptr, o,
                            h->timing != 0);
 }
 
@@ -919,6 +961,8 @@ int f1l_plan_batch(f1l_handle h, const double* poses, const double* opp, const i
         ENS(p.ctx, sizeof(QueryCtx) * (size_t)n);
         ENS(p.centres, sizeof(Centre) * (size_t)n * h->nL);
         ENS(p.best, 8 * (size_t)n);
+        ENS(p.near_i, 4 * (size_t)n);
+        ENS(p.near4, 32 * (size_t)n);
         if (best_idx) ENS(p.idx, (size_t)n * 4);
         if (best_cost) ENS(p.cost, (size_t)n * 4);
         if (best_traj) ENS(p.traj, (size_t)n * M * 16);
@@ -941,7 +985,8 @@ int f1l_plan_batch(f1l_handle h, const double* poses, const double* opp, const i
                                 max_opp > 0 ? (const double*)p.opp.p : nullptr,
                                 n_opp ? (const int32_t*)p.nopp.p : nullptr, n, max_opp, nullptr, 0,
                                 0, 0, (QueryCtx*)p.ctx.p, (Centre*)p.centres.p,
-                                (unsigned long long*)p.best.p, nullptr, o, false);
+                                (unsigned long long*)p.best.p, (int32_t*)p.near_i.p,
+                                (double*)p.near4.p, nullptr, o, false);
         if (r != F1L_OK) return r;
         if (best_idx) CK(cudaMemcpyAsync(best_idx + s0, p.idx.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
         if (best_cost) CK(cudaMemcpyAsync(best_cost + s0, p.cost.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
@@ -973,7 +1018,7 @@ int f1l_pure_pursuit_batch_dev(f1l_handle h, const double* poses_dev, int n_pose
     o.status = status_dev;
     const int blocks = (n_poses + PP_THREADS - 1) / PP_THREADS;
     pp_batch_kernel<<<blocks, PP_THREADS, PP_SMEM_BYTES, (cudaStream_t)stream>>>(
-        track_view(h), poses_dev, n_poses, L, h->cfg.wheelbase, h->cfg.max_reacquire, o);
+        track_view(h), poses_dev, 3, n_poses, L, h->cfg.wheelbase, h->cfg.max_reacquire, o);
     h->launches += 1;
     CK(cudaGetLastError());
     return F1L_OK;

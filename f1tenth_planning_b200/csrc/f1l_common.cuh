@@ -31,8 +31,10 @@ struct TrackView {
 };
 
 struct GridView {
-    const uint8_t* occ;  // [h, w] row-major, 0 free
+    const uint8_t* occ;    // [h, w] row-major, 0 free
+    const uint8_t* clear;  // [h, w] Chebyshev clearance in cells (0 = occupied), or null
     int h, w;
+    int probe_reach;       // probes lie within this many cells of the footprint-centre cell
     double ox, oy, inv_res;
 };
 
@@ -106,6 +108,21 @@ __device__ __forceinline__ void nearest_segment64(double qx, double qy, double a
     const double ex = xsub(qx, px), ey = xsub(qy, py);                        // :64
     dist = __dsqrt_rn(xadd(xmul(ex, ex), xmul(ey, ey)));                      // :65
     t = tt;
+}
+
+// float64 re-evaluation of an FP32 argmin: segments [k-2, k+2], first minimum (utils.py:66)
+__device__ __forceinline__ Nearest64 refine_nearest64(const double2* __restrict__ xy, int nseg,
+                                                      double qx, double qy, int k) {
+    Nearest64 b;
+    b.dist = CUDART_INF; b.i = 0; b.px = 0.0; b.py = 0.0; b.t = 0.0;
+    const int lo = max(k - 2, 0), hi = min(k + 2, nseg - 1);
+    for (int s = lo; s <= hi; ++s) {
+        const double2 a = xy[s], c = xy[s + 1];
+        double px, py, d, t;
+        nearest_segment64(qx, qy, a.x, a.y, c.x, c.y, px, py, d, t);
+        if (d < b.dist) { b.dist = d; b.i = s; b.px = px; b.py = py; b.t = t; }
+    }
+    return b;
 }
 
 // lexicographic (dist, index) minimum == np.argmin first-minimum rule (utils.py:66)

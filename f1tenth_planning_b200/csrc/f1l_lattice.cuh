@@ -76,16 +76,21 @@ __device__ __forceinline__ void warp_allreduce8(float (&v)[8], int lane) {
     }
 }
 
-// I fixed Newton steps q <- q - J^-1 r, whole warp, lane = Simpson node (lane+1)/32 (node 0 is
-// analytic: cos 0 = 1 and every other integrand vanishes there).
-__device__ __forceinline__ void spiral_newton(SpiralF& sp, float gx, float gy, float gth,
-                                              int iters, int lane) {
+// Up to `iters` Newton steps q <- q - J^-1 r, whole warp, lane = Simpson node (lane+1)/32 (node 0
+// is analytic: cos 0 = 1 and every other integrand vanishes there).  The loop leaves as soon as
+// the residual of the current iterate is at the FP32 noise floor (warp-uniform: the whole warp
+// works on one candidate), so a LUT-seeded candidate typically spends 3-4 passes, not `iters`.
+// Returns the number of quadrature passes done.
+__device__ __forceinline__ int spiral_newton(SpiralF& sp, float gx, float gy, float gth,
+                                             int iters, int lane) {
     const float u = (float)(lane + 1) * (1.0f / 32.0f);
     const float w = (lane == 31) ? (1.0f / 96.0f) : (((lane + 1) & 1) ? (4.0f / 96.0f) : (2.0f / 96.0f));
     const float u2 = u * u;
     const float d1 = u2 * fmaf(u, fmaf(u, 3.375f, -7.5f), 4.5f);
     const float d2 = u2 * fmaf(u, fmaf(u, -3.375f, 6.0f), -2.25f);
-    for (int it = 0; it < iters; ++it) {
+    const float eps = 1.5e-6f * fmaxf(1.0f, fmaxf(fabsf(gx), fmaxf(fabsf(gy), fabsf(gth))));
+    int it = 0;
+    for (; it < iters; ++it) {
         spiral_set(sp);
         const float g = spiral_g(sp, u);
         float s, c;
@@ -98,6 +103,7 @@ __device__ __forceinline__ void spiral_newton(SpiralF& sp, float gx, float gy, f
         const float sf = sp.sf, sf2 = sf * sf;
         const float g1 = 0.125f * (sp.p0 + 3.0f * sp.p1 + 3.0f * sp.p2 + sp.p3);
         const float r0 = fmaf(sf, C0, -gx), r1 = fmaf(sf, S0, -gy), r2 = fmaf(sf, g1, -gth);
+        if (fmaxf(fabsf(r0), fmaxf(fabsf(r1), fabsf(r2))) < eps) { ++it; break; }
         const float J00 = -sf2 * S1, J01 = -sf2 * S2, J02 = fmaf(-sf, Sg, C0);
         const float J10 = sf2 * C1, J11 = sf2 * C2, J12 = fmaf(sf, Cg, S0);
         const float J20 = 0.375f * sf, J21 = J20, J22 = g1;
@@ -113,6 +119,7 @@ __device__ __forceinline__ void spiral_newton(SpiralF& sp, float gx, float gy, f
         sp.sf -= dq2;
     }
     spiral_set(sp);
+    return it;
 }
 
 // nearest-cell LUT seed
@@ -278,52 +285,18 @@ __device__ __forceinline__ double wrap_to_pi64(double a) {
     return a - 3.14159265358979323846;
 }
 
-__global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
-    __shared__ double s_d[SAMPLE_THREADS / 32];
-    __shared__ int s_i[SAMPLE_THREADS / 32];
-    __shared__ double s_t;
-    __shared__ int s_best;
-    const int s = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+// everything after the nearest-point search, shared by the two sampler kernels.  `lt` / `nt`:
+// this thread's index / the number of threads working on scenario s.
+__device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, int nt, int i_ego,
+                                            double t_ego) {
     const double px = a.poses[4 * (size_t)s], py = a.poses[4 * (size_t)s + 1];
     const double pth = a.poses[4 * (size_t)s + 2], pv = a.poses[4 * (size_t)s + 3];
     const int nseg = a.tr.n - 1;
-
-    // nearest_point (utils.py:37-67), float64, first minimum
-    double bd = CUDART_INF;
-    int bi = 0x7fffffff;
-    for (int k = tid; k < nseg; k += SAMPLE_THREADS) {
-        const double2 p0 = a.tr.xy[k], p1 = a.tr.xy[k + 1];
-        double qx, qy, d, t;
-        nearest_segment64(px, py, p0.x, p0.y, p1.x, p1.y, qx, qy, d, t);
-        if (nearest_better(d, k, bd, bi)) { bd = d; bi = k; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double od = __shfl_xor_sync(F1L_FULL, bd, o);
-        const int oi = __shfl_xor_sync(F1L_FULL, bi, o);
-        if (nearest_better(od, oi, bd, bi)) { bd = od; bi = oi; }
-    }
-    if (lane == 0) { s_d[wid] = bd; s_i[wid] = bi; }
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < SAMPLE_THREADS / 32; ++w)
-            if (nearest_better(s_d[w], s_i[w], bd, bi)) { bd = s_d[w]; bi = s_i[w]; }
-        if (bi == 0x7fffffff) bi = 0;
-        const double2 p0 = a.tr.xy[bi], p1 = a.tr.xy[bi + 1];
-        double qx, qy, d, t;
-        nearest_segment64(px, py, p0.x, p0.y, p1.x, p1.y, qx, qy, d, t);
-        s_best = bi;
-        s_t = t;
-    }
-    __syncthreads();
-    const int i_ego = s_best;
-    const double t_ego = s_t;
     const double cth = cos(pth), sth = sin(pth);
 
     // one intersect_point per lookahead row (lattice_planner.py:249-251)
     XYTrack acc{a.tr.xy};
-    for (int j = tid; j < a.nL; j += SAMPLE_THREADS) {
+    for (int j = lt; j < a.nL; j += nt) {
         const Intersect64 ip =
             intersect_point64(acc, a.tr.n, px, py, a.lookaheads[j], (double)i_ego + t_ego, true);
         Centre ce;
@@ -345,17 +318,17 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
 
     QueryCtx* q = a.ctx + s;
     const int n_opp = a.opp ? (a.n_opp ? min(a.n_opp[s], a.max_opp) : a.max_opp) : 0;
-    if (tid < F1L_MAX_OPP) {
+    for (int k = lt; k < F1L_MAX_OPP; k += nt) {
         float4 o = make_float4(1e9f, 1e9f, 1.0f, 0.0f);
-        if (tid < n_opp) {
-            const double* op = a.opp + 3 * ((size_t)s * a.max_opp + tid);
+        if (k < n_opp) {
+            const double* op = a.opp + 3 * ((size_t)s * a.max_opp + k);
             const double dx = op[0] - px, dy = op[1] - py, ph = op[2] - pth;
             o = make_float4((float)(cth * dx + sth * dy), (float)(-sth * dx + cth * dy),
                             (float)cos(ph), (float)sin(ph));
         }
-        q->opp[tid] = o;
+        q->opp[k] = o;
     }
-    if (tid == 32) {
+    if (lt == nt - 1) {
         q->px = px; q->py = py; q->th = pth; q->vel = pv;
         q->cth = (float)cth; q->sth = (float)sth;
         q->i_ego = i_ego;
@@ -381,10 +354,70 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
     }
 }
 
+// single / few queries: one CTA per scenario; nearest_point (utils.py:37-67) as a CTA-parallel
+// FP32 scan of the block-local line form + float64 re-evaluation of the winner's neighbours.
+__global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
+    __shared__ float s_d[SAMPLE_THREADS / 32];
+    __shared__ int s_i[SAMPLE_THREADS / 32];
+    __shared__ double s_t;
+    __shared__ int s_best;
+    const int s = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double px = a.poses[4 * (size_t)s], py = a.poses[4 * (size_t)s + 1];
+    const int nseg = a.tr.n - 1;
+
+    float bd = CUDART_INF_F;
+    int bi = 0x7fffffff;
+    for (int k = tid; k < nseg; k += SAMPLE_THREADS) {
+        const double2 o = a.tr.blk_origin[k >> 5];
+        const float prx = (float)(px - o.x), pry = (float)(py - o.y);
+        const float4 A = __ldg(a.tr.segA + k);
+        const float2 Bv = __ldg(a.tr.segB + k);
+        const float q = fmaf(prx, A.x, fmaf(pry, A.y, -A.z));
+        const float nn = fmaf(pry, A.x, fmaf(-prx, A.y, -A.w));
+        const float t = __saturatef(q * Bv.y);
+        const float ex = fmaf(-t, Bv.x, q);
+        const float d2 = fmaf(ex, ex, nn * nn);
+        if (d2 < bd) { bd = d2; bi = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float od = __shfl_xor_sync(F1L_FULL, bd, o);
+        const int oi = __shfl_xor_sync(F1L_FULL, bi, o);
+        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+    }
+    if (lane == 0) { s_d[wid] = bd; s_i[wid] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < SAMPLE_THREADS / 32; ++w)
+            if (s_d[w] < bd || (s_d[w] == bd && s_i[w] < bi)) { bd = s_d[w]; bi = s_i[w]; }
+        if (bi == 0x7fffffff) bi = 0;
+        const Nearest64 nr = refine_nearest64(a.tr.xy, nseg, px, py, bi);
+        s_best = nr.i;
+        s_t = nr.t;
+    }
+    __syncthreads();
+    sample_body(a, s, tid, SAMPLE_THREADS, s_best, s_t);
+}
+
+// batches: the nearest-point search of all scenarios is done by pp_batch_kernel (thread per pose,
+// track in shared memory); here one warp per scenario does the rest.
+#define SAMPLE_WARPS 4
+__global__ void __launch_bounds__(SAMPLE_WARPS * 32)
+sample_warp_kernel(SampleArgs a, const int32_t* __restrict__ near_i,
+                   const double* __restrict__ near4, int n_scenarios) {
+    const int s = blockIdx.x * SAMPLE_WARPS + (threadIdx.x >> 5);
+    if (s >= n_scenarios) return;
+    sample_body(a, s, threadIdx.x & 31, 32, near_i[s], near4[4 * (size_t)s + 3]);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3 + K4: fused generate / cost / collision, one warp per candidate
 // ---------------------------------------------------------------------------------------------
 #define EVAL_MAX_WARPS 8
+#ifndef EVAL_MIN_BLOCKS
+#define EVAL_MIN_BLOCKS 1   // raise to trade registers for resident warps (build-time experiment)
+#endif
 
 // collision predicate pieces use explicitly rounded FP32 ops (no FMA contraction) so that the
 // float32 mirror in the oracle reproduces the flags bit for bit on identical inputs.
@@ -415,7 +448,7 @@ __device__ __forceinline__ bool grid_hit(const uint8_t* __restrict__ occ, int gw
 }
 
 template <int IPL, int S, int SG>
-__global__ void __launch_bounds__(EVAL_MAX_WARPS * 32) eval_kernel(EvalArgs a) {
+__global__ void __launch_bounds__(EVAL_MAX_WARPS * 32, EVAL_MIN_BLOCKS) eval_kernel(EvalArgs a) {
     constexpr int GG = 32 / SG;
     extern __shared__ __align__(16) unsigned char ev_smem[];
     const int M = a.ep.M;
@@ -431,10 +464,12 @@ __global__ void __launch_bounds__(EVAL_MAX_WARPS * 32) eval_kernel(EvalArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const QueryCtx* __restrict__ q = a.ctx + s;
 
-    // ---- prologue: raceline window -> vehicle frame -> line form in shared memory ----
+    // ---- prologue: raceline window -> vehicle frame -> line form in shared memory.  Only the
+    //      subtraction of the pose happens in float64 (|coordinates| reach 85 m, the window is
+    //      ~25 m long); rotation, length and line coefficients are FP32 on ego-relative values.
     {
         const double px = q->px, py = q->py;
-        const double cth = cos(q->th), sth = sin(q->th);
+        const float cth = q->cth, sth = q->sth;
         const int seg0 = q->seg0, nseg = q->nseg, ns = a.tr.n - 1;
         for (int k = tid; k < a.nseg_pad; k += blockDim.x) {
             float4 A = make_float4(1.0f, 0.0f, 1e15f, 1e15f);  // padding: far away, finite
@@ -443,15 +478,15 @@ __global__ void __launch_bounds__(EVAL_MAX_WARPS * 32) eval_kernel(EvalArgs a) {
                 int sg = seg0 + k;
                 if (sg >= ns) sg -= ns;
                 const double2 p0 = a.tr.xy[sg], p1 = a.tr.xy[sg + 1];
-                const double ax = p0.x - px, ay = p0.y - py, bx = p1.x - px, by = p1.y - py;
-                const double avx = cth * ax + sth * ay, avy = -sth * ax + cth * ay;
-                const double bvx = cth * bx + sth * by, bvy = -sth * bx + cth * by;
-                const double dx = bvx - avx, dy = bvy - avy;
-                const double len = sqrt(dx * dx + dy * dy);
-                const double ux = dx / len, uy = dy / len;
-                A = make_float4((float)ux, (float)uy, (float)(avx * ux + avy * uy),
-                                (float)(-avx * uy + avy * ux));
-                Bv = make_float2((float)len, (float)(1.0 / len));
+                const float ax = (float)(p0.x - px), ay = (float)(p0.y - py);
+                const float dxm = (float)(p1.x - p0.x), dym = (float)(p1.y - p0.y);
+                const float avx = fmaf(cth, ax, sth * ay), avy = fmaf(cth, ay, -sth * ax);
+                const float dx = fmaf(cth, dxm, sth * dym), dy = fmaf(cth, dym, -sth * dxm);
+                const float l2 = fmaf(dx, dx, dy * dy);
+                const float il = rsqrtf(l2);
+                const float ux = dx * il, uy = dy * il;
+                A = make_float4(ux, uy, fmaf(avx, ux, avy * uy), fmaf(avy, ux, -avx * uy));
+                Bv = make_float2(l2 * il, il);
             }
             sA[k] = A;
             sB[k] = Bv;
@@ -478,7 +513,7 @@ __global__ void __launch_bounds__(EVAL_MAX_WARPS * 32) eval_kernel(EvalArgs a) {
         const float4 seed = lut_lookup(a.lut, gx, gy, gth);
         sp.p1 = seed.x; sp.p2 = seed.y; sp.sf = seed.z;
     }
-    spiral_newton(sp, gx, gy, gth, a.ep.n_newton, lane);
+    const int n_pass = spiral_newton(sp, gx, gy, gth, a.ep.n_newton, lane);
 
     // ---- arc samples ----
     float x[IPL], y[IPL], th[IPL], kp[IPL], cs[IPL], sn[IPL];
@@ -528,6 +563,7 @@ __global__ void __launch_bounds__(EVAL_MAX_WARPS * 32) eval_kernel(EvalArgs a) {
 
     unsigned flags = valid ? F1L_FLAG_VALID : 0u;
     if (!have_centre) flags |= F1L_FLAG_NO_CENTRE;
+    flags |= (unsigned)min(n_pass, 15) << F1L_FLAG_PASS_SHIFT;
     float t_len = 0.0f, t_maxk = 0.0f, t_meank = 0.0f, t_sim = 0.0f, t_dev = 0.0f;
     float cost = CUDART_INF_F;
 
@@ -546,6 +582,16 @@ __global__ void __launch_bounds__(EVAL_MAX_WARPS * 32) eval_kernel(EvalArgs a) {
         const float A00 = q->gA00, A01 = q->gA01, A10 = q->gA10, A11 = q->gA11;
         const float gfx = q->gfx, gfy = q->gfy;
         const int gix = q->gix, giy = q->giy;
+        // candidate-level opponent pruning: every point of a curve of length s_f from the origin
+        // to (ex, ey) lies within s_f/2 of the chord's midpoint, so an opponent farther than
+        // s_f/2 + 2 r_circ from it cannot pass the per-sample broad phase.  Exact (conservative).
+        unsigned opp_mask;
+        {
+            const float4 o = sopp[lane & (F1L_MAX_OPP - 1)];
+            const float mx = o.x - 0.5f * ex, my = o.y - 0.5f * ey;
+            const float reach = 0.5f * sp.sf + sqrtf(a.ep.rc2) + 1e-3f;
+            opp_mask = __ballot_sync(F1L_FULL, lane < n_opp && fmaf(mx, mx, my * my) <= reach * reach);
+        }
 #pragma unroll
         for (int j = 0; j < IPL; ++j) {
             const int i = lane * IPL + j;
@@ -554,35 +600,45 @@ __global__ void __launch_bounds__(EVAL_MAX_WARPS * 32) eval_kernel(EvalArgs a) {
                     const float d = th[j] - sprev[i + a.ep.n_shift];
                     sim = fmaf(d, d, sim);
                 }
-                for (int k = 0; k < n_opp; ++k) {
-                    const float4 o = sopp[k];
+                for (unsigned m = opp_mask; m; m &= m - 1) {
+                    const float4 o = sopp[__ffs(m) - 1];
                     const float tx = fs(o.x, x[j]), ty = fs(o.y, y[j]);
                     const float d2 = fa(fm(tx, tx), fm(ty, ty));
                     if (d2 <= a.ep.rc2 && sat_collide(tx, ty, cs[j], sn[j], o.z, o.w, hl, hw))
                         hit_opp = true;
                 }
                 if (has_grid) {
-                    // footprint centre and half-axes in grid-cell coordinates
+                    // footprint centre in grid-cell coordinates
                     const float ccx = fa(fa(fm(A00, x[j]), fm(A01, y[j])), gfx);
                     const float ccy = fa(fa(fm(A10, x[j]), fm(A11, y[j])), gfy);
-                    const float lx = fm(cs[j], hl), ly = fm(sn[j], hl);    // body x axis * hl
-                    const float wx = fm(-sn[j], hw), wy = fm(cs[j], hw);   // body y axis * hw
-                    const float elx = fa(fm(A00, lx), fm(A01, ly)), ely = fa(fm(A10, lx), fm(A11, ly));
-                    const float ewx = fa(fm(A00, wx), fm(A01, wy)), ewy = fa(fm(A10, wx), fm(A11, wy));
                     const uint8_t* occ = a.grid.occ;
                     const int gw = a.grid.w, gh = a.grid.h;
-                    bool h = false;
-                    // 4 corners, 4 edge mid-points, centre (SURVEY B.6, P = 9)
-                    h |= grid_hit(occ, gw, gh, gix, giy, fa(fa(ccx, elx), ewx), fa(fa(ccy, ely), ewy));
-                    h |= grid_hit(occ, gw, gh, gix, giy, fs(fa(ccx, elx), ewx), fs(fa(ccy, ely), ewy));
-                    h |= grid_hit(occ, gw, gh, gix, giy, fa(fs(ccx, elx), ewx), fa(fs(ccy, ely), ewy));
-                    h |= grid_hit(occ, gw, gh, gix, giy, fs(fs(ccx, elx), ewx), fs(fs(ccy, ely), ewy));
-                    h |= grid_hit(occ, gw, gh, gix, giy, fa(ccx, elx), fa(ccy, ely));
-                    h |= grid_hit(occ, gw, gh, gix, giy, fs(ccx, elx), fs(ccy, ely));
-                    h |= grid_hit(occ, gw, gh, gix, giy, fa(ccx, ewx), fa(ccy, ewy));
-                    h |= grid_hit(occ, gw, gh, gix, giy, fs(ccx, ewx), fs(ccy, ewy));
-                    h |= grid_hit(occ, gw, gh, gix, giy, ccx, ccy);
-                    hit_map |= h;
+                    // clearance map: clear[cell] = Chebyshev distance (cells) to the nearest
+                    // occupied / out-of-bounds cell.  All nine probes fall within
+                    // `probe_reach` cells of the centre cell, so a larger clearance proves them
+                    // free without touching them.
+                    const int ccol = gix + __float2int_rd(ccx), crow = giy + __float2int_rd(ccy);
+                    bool need = true;
+                    if (a.grid.clear && (unsigned)ccol < (unsigned)gw && (unsigned)crow < (unsigned)gh)
+                        need = __ldg(a.grid.clear + (size_t)crow * gw + ccol) <= a.grid.probe_reach;
+                    if (need) {
+                        const float lx = fm(cs[j], hl), ly = fm(sn[j], hl);    // body x axis * hl
+                        const float wx = fm(-sn[j], hw), wy = fm(cs[j], hw);   // body y axis * hw
+                        const float elx = fa(fm(A00, lx), fm(A01, ly)), ely = fa(fm(A10, lx), fm(A11, ly));
+                        const float ewx = fa(fm(A00, wx), fm(A01, wy)), ewy = fa(fm(A10, wx), fm(A11, wy));
+                        bool h = false;
+                        // 4 corners, 4 edge mid-points, centre (SURVEY B.6, P = 9)
+                        h |= grid_hit(occ, gw, gh, gix, giy, fa(fa(ccx, elx), ewx), fa(fa(ccy, ely), ewy));
+                        h |= grid_hit(occ, gw, gh, gix, giy, fs(fa(ccx, elx), ewx), fs(fa(ccy, ely), ewy));
+                        h |= grid_hit(occ, gw, gh, gix, giy, fa(fs(ccx, elx), ewx), fa(fs(ccy, ely), ewy));
+                        h |= grid_hit(occ, gw, gh, gix, giy, fs(fs(ccx, elx), ewx), fs(fs(ccy, ely), ewy));
+                        h |= grid_hit(occ, gw, gh, gix, giy, fa(ccx, elx), fa(ccy, ely));
+                        h |= grid_hit(occ, gw, gh, gix, giy, fs(ccx, elx), fs(ccy, ely));
+                        h |= grid_hit(occ, gw, gh, gix, giy, fa(ccx, ewx), fa(ccy, ewy));
+                        h |= grid_hit(occ, gw, gh, gix, giy, fs(ccx, ewx), fs(ccy, ewy));
+                        h |= grid_hit(occ, gw, gh, gix, giy, ccx, ccy);
+                        hit_map |= h;
+                    }
                 }
             }
         }
@@ -752,6 +808,39 @@ __global__ void __launch_bounds__(32) select_kernel(SelectArgs a) {
         if (a.status) { a.status[2 * s] = none ? 1 : 0; a.status[2 * s + 1] = found; }
         if (a.steer_speed) { a.steer_speed[2 * (size_t)s] = steer; a.steer_speed[2 * (size_t)s + 1] = speed; }
     }
+}
+
+// Chebyshev clearance of every cell (distance in cells to the nearest occupied or out-of-bounds
+// cell, capped at R+1), separable: horizontal pass then vertical pass.
+#define CLEAR_R 24
+__global__ void clearance_h_kernel(const uint8_t* __restrict__ occ, int h, int w,
+                                   uint8_t* __restrict__ hd) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+    if (col >= w) return;
+    const uint8_t* r = occ + (size_t)row * w;
+    int d = CLEAR_R + 1;
+    if (r[col]) d = 0;
+    else
+        for (int k = 1; k <= CLEAR_R; ++k) {
+            const int a = col - k, b = col + k;
+            if (a < 0 || b >= w || r[a] || r[b]) { d = k; break; }
+        }
+    hd[(size_t)row * w + col] = (uint8_t)d;
+}
+__global__ void clearance_v_kernel(const uint8_t* __restrict__ hd, int h, int w,
+                                   uint8_t* __restrict__ clear) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+    if (col >= w) return;
+    int best = hd[(size_t)row * w + col];
+    for (int k = 1; k <= CLEAR_R && k < best; ++k) {
+        const int a = row - k, b = row + k;
+        int da = 0, db = 0;
+        if (a >= 0) da = hd[(size_t)a * w + col];
+        if (b < h) db = hd[(size_t)b * w + col];
+        const int m = max(k, min(da, db));
+        best = min(best, m);
+    }
+    clear[(size_t)row * w + col] = (uint8_t)best;
 }
 
 __global__ void fill_f32_kernel(float* __restrict__ p, size_t n, float v) {

@@ -26,23 +26,8 @@ struct PPOut {
     int32_t* status;      // [B]
 };
 
-// float64 refinement of the FP32 argmin: segments [k-2, k+2], first minimum (utils.py:66)
-__device__ __forceinline__ Nearest64 refine_nearest64(const double2* __restrict__ xy, int nseg,
-                                                      double qx, double qy, int k) {
-    Nearest64 b;
-    b.dist = CUDART_INF; b.i = 0; b.px = 0.0; b.py = 0.0; b.t = 0.0;
-    const int lo = max(k - 2, 0), hi = min(k + 2, nseg - 1);
-    for (int s = lo; s <= hi; ++s) {
-        const double2 a = xy[s], c = xy[s + 1];
-        double px, py, d, t;
-        nearest_segment64(qx, qy, a.x, a.y, c.x, c.y, px, py, d, t);
-        if (d < b.dist) { b.dist = d; b.i = s; b.px = px; b.py = py; b.t = t; }
-    }
-    return b;
-}
-
 __global__ void __launch_bounds__(PP_THREADS)
-pp_batch_kernel(TrackView tr, const double* __restrict__ poses, int n_poses, double L, double wb,
+pp_batch_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, int n_poses, double L, double wb,
                 double max_reacquire, PPOut out) {
     extern __shared__ __align__(16) unsigned char pp_smem[];
     float4* sA = reinterpret_cast<float4*>(pp_smem);
@@ -53,8 +38,8 @@ pp_batch_kernel(TrackView tr, const double* __restrict__ poses, int n_poses, dou
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = gid < n_poses;
     const int pid = active ? gid : n_poses - 1;
-    const double qx = poses[3 * (size_t)pid], qy = poses[3 * (size_t)pid + 1];
-    const double qth = poses[3 * (size_t)pid + 2];
+    const double qx = poses[(size_t)pose_stride * pid], qy = poses[(size_t)pose_stride * pid + 1];
+    const double qth = poses[(size_t)pose_stride * pid + 2];
 
     float best = CUDART_INF_F;
     int bk = 0;

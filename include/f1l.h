@@ -49,6 +49,7 @@ typedef enum {
 #define F1L_FLAG_COLLIDE_OPP 2u  /* footprint overlaps an opponent rectangle */
 #define F1L_FLAG_COLLIDE_MAP 4u  /* a footprint probe hits an occupied / out-of-bounds cell */
 #define F1L_FLAG_NO_CENTRE 8u    /* lookahead circle found no raceline intersection for this row */
+#define F1L_FLAG_PASS_SHIFT 4    /* bits 4..7: Newton quadrature passes this candidate used */
 
 /*
  * Planner configuration.  Replaces the constructor kwargs / hard-coded numbers

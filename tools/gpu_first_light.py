@@ -43,7 +43,7 @@ def main():
         gv, ov = (d.flags & 1) != 0, (ob["flags"] & 1) != 0
         both = gv & ov
         print(name, "valid gpu/oracle/both", gv.sum(), ov.sum(), both.sum(), "flags equal",
-              (d.flags == ob["flags"]).mean())
+              ((d.flags & 15) == ob["flags"]).mean(), "newton passes", (d.flags >> 4).mean())
         if both.any():
             print("  goals maxdiff", np.abs(d.goals - ob["goals"]).max())
             print("  params maxrel", (np.abs(d.params[both, :3] - ob["params"][both, :3]) /
