@@ -217,6 +217,79 @@ __device__ inline Intersect64 intersect_point64(const P& pts, int n, double qx, 
     return o;
 }
 
+// Warp-parallel intersect_point with the same result as the sequential scan: 32 consecutive
+// segments per step in the reference's scan order (forward from int(t), then the wrap loop from
+// the closing segment -1), the reference's acceptance rules evaluated per lane in float64, the
+// lowest accepting lane wins (== first hit of the sequential loop).  `maybe(i)` is a cheap
+// conservative prefilter (false only if segment i cannot reach the circle).  Call with the whole
+// warp converged; every lane returns the same result.
+template <class P, class F>
+__device__ inline Intersect64 intersect_point_warp(const P& pts, int n, double qx, double qy,
+                                                   double r, double t, bool wrap, int lane,
+                                                   const F& maybe) {
+    Intersect64 o;
+    o.px = 0.0; o.py = 0.0; o.t = 0.0; o.i = 0; o.found = 0;
+    const int start_i = (int)t;                 // :78
+    const double start_t = fmod(t, 1.0);        // :79
+    for (int phase = 0; phase < (wrap ? 2 : 1); ++phase) {
+        const int lo = phase == 0 ? start_i : -1;          // :84 / :125
+        const int hi = phase == 0 ? n - 1 : start_i;       // exclusive
+        for (int base = lo; base < hi; base += 32) {
+            const int i = base + lane;
+            double tt = -1.0, vx = 0.0, vy = 0.0;
+            double2 s = make_double2(0.0, 0.0);
+            if (i < hi && maybe(i)) {
+                double t1, t2;
+                s = pts(pymod(i, n));
+                if (intersect_segment64(qx, qy, r, s, pts(pymod(i + 1, n)), t1, t2, vx, vy)) {
+                    if (phase == 0 && i == start_i) {       // :102-112
+                        if (t1 >= 0.0 && t1 <= 1.0 && t1 >= start_t) tt = t1;
+                        else if (t2 >= 0.0 && t2 <= 1.0 && t2 >= start_t) tt = t2;
+                    } else if (t1 >= 0.0 && t1 <= 1.0) tt = t1;   // :113 / :140
+                    else if (t2 >= 0.0 && t2 <= 1.0) tt = t2;     // :118 / :145
+                }
+            }
+            const unsigned m = __ballot_sync(F1L_FULL, tt >= 0.0);
+            if (m) {
+                const int src = __ffs(m) - 1;
+                const double px = xadd(s.x, xmul(tt, vx)), py = xadd(s.y, xmul(tt, vy));
+                o.found = 1;
+                o.i = base + src;
+                o.t = __shfl_sync(F1L_FULL, tt, src);
+                o.px = __shfl_sync(F1L_FULL, px, src);
+                o.py = __shfl_sync(F1L_FULL, py, src);
+                return o;
+            }
+        }
+    }
+    return o;
+}
+
+// prefilter on the uploaded track: FP32 distance of the query point to segment i (block-local
+// line form) against radius + 1 mm.  A root of the reference's quadratic in [0,1] is a point of
+// the (1e-6-shifted) segment at distance r from the query, so a segment farther than that cannot
+// be accepted; the closing segment (i = -1) has no line form and is always tested.
+struct TrackPrefilter {
+    const TrackView& tr;
+    double qx, qy;
+    float rr2;
+    __device__ __forceinline__ bool operator()(int i) const {
+        if (i < 0) return true;
+        const double2 o = tr.blk_origin[i >> 5];
+        const float prx = (float)(qx - o.x), pry = (float)(qy - o.y);
+        const float4 A = __ldg(tr.segA + i);
+        const float2 Bv = __ldg(tr.segB + i);
+        const float q = fmaf(prx, A.x, fmaf(pry, A.y, -A.z));
+        const float nn = fmaf(pry, A.x, fmaf(-prx, A.y, -A.w));
+        const float tc = __saturatef(q * Bv.y);
+        const float ex = fmaf(-tc, Bv.x, q);
+        return fmaf(ex, ex, nn * nn) <= rr2;
+    }
+};
+struct NoPrefilter {
+    __device__ __forceinline__ bool operator()(int) const { return true; }
+};
+
 // get_actuation (utils/utils.py:153-161): returns steer, passes speed through
 __device__ __forceinline__ double actuation_steer64(double pose_theta, double lx, double ly,
                                                     double qx, double qy, double L, double wb) {

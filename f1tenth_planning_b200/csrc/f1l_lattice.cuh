@@ -294,26 +294,32 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
     const int nseg = a.tr.n - 1;
     const double cth = cos(pth), sth = sin(pth);
 
-    // one intersect_point per lookahead row (lattice_planner.py:249-251)
+    // one intersect_point per lookahead row (lattice_planner.py:249-251); a warp per row
     XYTrack acc{a.tr.xy};
-    for (int j = lt; j < a.nL; j += nt) {
+    const int lane = lt & 31;
+    for (int j = lt >> 5; j < a.nL; j += nt >> 5) {
+        const double L = a.lookaheads[j];
+        const float rr = (float)L + 1e-3f;
+        const TrackPrefilter pf{a.tr, px, py, rr * rr};
         const Intersect64 ip =
-            intersect_point64(acc, a.tr.n, px, py, a.lookaheads[j], (double)i_ego + t_ego, true);
-        Centre ce;
-        const int r = ip.found ? pymod(ip.i, a.tr.n) : 0;
-        const double2 c = a.tr.xy[r];
-        const double psi = a.tr.psi[r];
-        const double dx = c.x - px, dy = c.y - py;
-        const double prel = wrap_to_pi64(psi - pth);
-        ce.cx = ip.found ? (float)(cth * dx + sth * dy) : 0.0f;
-        ce.cy = ip.found ? (float)(-sth * dx + cth * dy) : 0.0f;
-        ce.psi_rel = ip.found ? (float)prel : 0.0f;
-        ce.kappa_g = (float)a.tr.kappa[r];
-        ce.nx = ip.found ? (float)(-sin(prel)) : 0.0f;
-        ce.ny = ip.found ? (float)cos(prel) : 0.0f;
-        ce.v = (float)a.tr.v[r];
-        ce.ok = ip.found ? 1.0f : 0.0f;
-        a.centres[(size_t)s * a.nL + j] = ce;
+            intersect_point_warp(acc, a.tr.n, px, py, L, (double)i_ego + t_ego, true, lane, pf);
+        if (lane == 0) {
+            Centre ce;
+            const int r = ip.found ? pymod(ip.i, a.tr.n) : 0;
+            const double2 c = a.tr.xy[r];
+            const double psi = a.tr.psi[r];
+            const double dx = c.x - px, dy = c.y - py;
+            const double prel = wrap_to_pi64(psi - pth);
+            ce.cx = ip.found ? (float)(cth * dx + sth * dy) : 0.0f;
+            ce.cy = ip.found ? (float)(-sth * dx + cth * dy) : 0.0f;
+            ce.psi_rel = ip.found ? (float)prel : 0.0f;
+            ce.kappa_g = (float)a.tr.kappa[r];
+            ce.nx = ip.found ? (float)(-sin(prel)) : 0.0f;
+            ce.ny = ip.found ? (float)cos(prel) : 0.0f;
+            ce.v = (float)a.tr.v[r];
+            ce.ok = ip.found ? 1.0f : 0.0f;
+            a.centres[(size_t)s * a.nL + j] = ce;
+        }
     }
 
     QueryCtx* q = a.ctx + s;
@@ -777,32 +783,33 @@ __global__ void __launch_bounds__(32) select_kernel(SelectArgs a) {
         const int oi = __shfl_xor_sync(F1L_FULL, bi, o);
         if (nearest_better(od, oi, bd, bi)) { bd = od; bi = oi; }
     }
-    if (lane == 0) {
-        int found = 0;
-        double steer = 0.0, speed = 0.0;
-        if (bi != 0x7fffffff) {
-            const double2 p0 = acc(bi), p1 = acc(bi + 1);
-            double ux, uy, d, t;
-            nearest_segment64(qx, qy, p0.x, p0.y, p1.x, p1.y, ux, uy, d, t);
-            const double v_track = literal ? (double)s_traj[bi].z
-                                           : (v_ref >= 0.0f ? (double)v_ref : q->vel);
-            double lx = 0.0, ly = 0.0;
-            if (d < L) {                                        // pure_pursuit.py:70
-                const Intersect64 ip = intersect_point64(acc, M, qx, qy, L, (double)bi + t, true);
-                if (ip.found) {
-                    const int r = pymod(ip.i, M);
-                    lx = acc(r).x; ly = acc(r).y;
-                    found = 1;
-                }
-            } else if (d < a.ep.max_reacquire) {                 // :80
-                lx = p0.x; ly = p0.y;
+    int found = 0;
+    double steer = 0.0, speed = 0.0;
+    if (bi != 0x7fffffff) {   // warp-uniform
+        const double2 p0 = acc(bi), p1 = acc(bi + 1);
+        double ux, uy, d, t;
+        nearest_segment64(qx, qy, p0.x, p0.y, p1.x, p1.y, ux, uy, d, t);
+        const double v_track = literal ? (double)s_traj[bi].z
+                                       : (v_ref >= 0.0f ? (double)v_ref : q->vel);
+        double lx = 0.0, ly = 0.0;
+        if (d < L) {                                        // pure_pursuit.py:70
+            const Intersect64 ip = intersect_point_warp(acc, M, qx, qy, L, (double)bi + t, true,
+                                                        lane, NoPrefilter());
+            if (ip.found) {
+                const int r = pymod(ip.i, M);
+                lx = acc(r).x; ly = acc(r).y;
                 found = 1;
             }
-            if (found) {
-                steer = actuation_steer64(qth, lx, ly, qx, qy, L, wb);
-                speed = v_track;
-            }
+        } else if (d < a.ep.max_reacquire) {                 // :80
+            lx = p0.x; ly = p0.y;
+            found = 1;
         }
+        if (found) {
+            steer = actuation_steer64(qth, lx, ly, qx, qy, L, wb);
+            speed = v_track;
+        }
+    }
+    if (lane == 0) {
         if (a.best_idx) a.best_idx[s] = idx;
         if (a.best_cost) a.best_cost[s] = cost;
         if (a.status) { a.status[2 * s] = none ? 1 : 0; a.status[2 * s + 1] = found; }
