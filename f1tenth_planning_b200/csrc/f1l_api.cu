@@ -210,13 +210,29 @@ typedef void (*eval_fn)(EvalArgs);
 typedef void (*select_fn)(SelectArgs);
 typedef void (*generate_fn)(LutView, EvalParams, const float4*, int, float4*, float4*, uint8_t*);
 
-eval_fn eval_entry(int M) {
-    if (M <= 32) return eval_kernel<1, 4, 8>;
-    if (M <= 64) return eval_kernel<2, 8, 8>;
-    if (M <= 104) return eval_kernel<4, 13, 8>;
-    if (M <= 128) return eval_kernel<4, 16, 8>;
-    if (M <= 208) return eval_kernel<7, 13, 16>;
-    return eval_kernel<8, 16, 16>;
+// NW = 7 (four resident CTAs of 7 warps at <= 72 registers) serves candidate counts that are a
+// small multiple of 7 -- the default 4x7 goal grid; everything else runs 8-warp CTAs.
+#ifndef EVAL_MINB8
+#define EVAL_MINB8 3
+#endif
+#ifndef EVAL_MINB7
+#define EVAL_MINB7 4
+#endif
+eval_fn eval_entry(int M, int nw) {
+    if (nw == 7) {
+        if (M <= 32) return eval_kernel<1, 4, 8, 7, EVAL_MINB7>;
+        if (M <= 64) return eval_kernel<2, 8, 8, 7, EVAL_MINB7>;
+        if (M <= 104) return eval_kernel<4, 13, 8, 7, EVAL_MINB7>;
+        if (M <= 128) return eval_kernel<4, 16, 8, 7, EVAL_MINB7>;
+        if (M <= 208) return eval_kernel<7, 13, 16, 7, EVAL_MINB7>;
+        return eval_kernel<8, 16, 16, 7, EVAL_MINB7>;
+    }
+    if (M <= 32) return eval_kernel<1, 4, 8, 8, EVAL_MINB8>;
+    if (M <= 64) return eval_kernel<2, 8, 8, 8, EVAL_MINB8>;
+    if (M <= 104) return eval_kernel<4, 13, 8, 8, EVAL_MINB8>;
+    if (M <= 128) return eval_kernel<4, 16, 8, 8, EVAL_MINB8>;
+    if (M <= 208) return eval_kernel<7, 13, 16, 8, EVAL_MINB8>;
+    return eval_kernel<8, 16, 16, 8, EVAL_MINB8>;
 }
 select_fn select_entry(int M) {
     if (M <= 32) return select_kernel<1>;
@@ -233,15 +249,12 @@ generate_fn generate_entry(int M) {
     return generate_kernel<8>;
 }
 
-int pick_warps_per_cta(int n_cand) {
-    if (n_cand >= 64) return 8;
-    for (int w = 8; w >= 4; --w)
-        if (n_cand % w == 0) return w;
-    return n_cand < 8 ? (n_cand > 0 ? n_cand : 1) : 8;
+int pick_warps_per_cta(int n_cand, int M) {
+    return (n_cand % 7 == 0 && n_cand <= 56 && M <= 128) ? 7 : 8;
 }
 
 size_t eval_smem_bytes(int nseg_pad, int warps, int M) {
-    size_t b = (size_t)nseg_pad * (sizeof(float4) + sizeof(float2));
+    size_t b = (size_t)(nseg_pad + EVAL_SEG_PAD) * (sizeof(float4) + sizeof(float2));
     b += (size_t)warps * M * sizeof(float2);
     b += (size_t)((M + 3) & ~3) * sizeof(float);
     b += F1L_MAX_OPP * sizeof(float4);
@@ -284,7 +297,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     if (nseg <= 0 || nseg > nsegs) nseg = nsegs;
     const int nseg_pad = (nseg + 31) & ~31;
     const int n_cand = c_end - c_begin;
-    const int wpc = pick_warps_per_cta(n_cand);
+    const int wpc = pick_warps_per_cta(n_cand, M);
     const size_t smem = eval_smem_bytes(nseg_pad, wpc, M);
     if (smem > 227 * 1024) return F1L_ERR_TOO_LARGE;
 
@@ -338,7 +351,19 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     ea.C = C;
     ea.c_begin = c_begin;
     ea.c_end = c_end;
-    ea.ctas_per_scn = (n_cand + wpc - 1) / wpc;
+    {
+        // enough CTAs to fill the machine twice; a CTA works through `chunk` candidates
+        const long long target = 2LL * h->sm_count * 3;
+        long long per = (target + S - 1) / S;
+        const long long max_per = (n_cand + wpc - 1) / wpc;
+        if (per > max_per) per = max_per;
+        if (per < 1) per = 1;
+        int chunk = (int)((n_cand + per - 1) / per);
+        chunk = ((chunk + wpc - 1) / wpc) * wpc;
+        ea.chunk = chunk;
+        ea.ctas_per_scn = (n_cand + chunk - 1) / chunk;
+    }
+    ea.inv_nW = 1.0f / (float)(h->nW > 0 ? h->nW : 1);
     ea.nseg_pad = nseg_pad;
     ea.costs = o.costs;
     ea.terms = o.terms;
@@ -350,7 +375,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     ea.best = best;
     const long long n_ctas = (long long)S * ea.ctas_per_scn;
     if (n_ctas > 0x7fffffffLL) return F1L_ERR_TOO_LARGE;
-    eval_entry(M)<<<(unsigned)n_ctas, wpc * 32, smem, stream>>>(ea);
+    eval_entry(M, wpc)<<<(unsigned)n_ctas, wpc * 32, smem, stream>>>(ea);
     if (time_it) cudaEventRecord(ev[2], stream);
 
     SelectArgs se;
@@ -362,6 +387,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     se.widths = ea.widths;
     se.nL = h->nL;
     se.nW = h->nW;
+    se.inv_nW = 1.0f / (float)(h->nW > 0 ? h->nW : 1);
     se.goals = goals;
     se.C = C;
     se.c_begin = c_begin;
@@ -547,12 +573,11 @@ int f1l_create(f1l_handle* out, int device, const f1l_config* cfg) {
         if (sm > 0) h->sm_count = sm;
         // opt in to large dynamic shared memory for every eval instantiation + the scan kernel
         const int big = 227 * 1024;
-        cudaFuncSetAttribute(eval_kernel<1, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute(eval_kernel<2, 8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute(eval_kernel<4, 13, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute(eval_kernel<4, 16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute(eval_kernel<7, 13, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute(eval_kernel<8, 16, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        for (int nw = 7; nw <= 8; ++nw) {
+            const int ms[] = {32, 64, 100, 128, 200, 256};
+            for (int m : ms)
+                cudaFuncSetAttribute(eval_entry(m, nw), cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        }
         e = cudaFuncSetAttribute(pp_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)PP_SMEM_BYTES);
     }

@@ -213,7 +213,9 @@ struct EvalArgs {
     const float* prev_theta; // [M] or null
     int C;                   // candidates per scenario
     int c_begin, c_end;      // evaluated range
-    int ctas_per_scn;
+    int ctas_per_scn;        // CTAs per scenario
+    int chunk;               // candidates per CTA
+    float inv_nW;            // 1 / nW (row = floor((c + 0.5) / nW) without an integer division)
     int nseg_pad;            // shared-memory window capacity (multiple of 32)
     // outputs (nullable)
     float* costs;            // [S,C]
@@ -234,6 +236,7 @@ struct SelectArgs {
     const Centre* centres;
     const float* widths;
     int nL, nW;
+    float inv_nW;
     const float4* goals;
     int C, c_begin;
     const unsigned long long* best;
@@ -250,7 +253,8 @@ struct SelectArgs {
 __device__ __forceinline__ void candidate_goal(const Centre* __restrict__ centres,
                                                const float* __restrict__ widths,
                                                const float4* __restrict__ goals, int nL, int nW,
-                                               int C, int s, int c, bool use_goal_kappa, float& gx,
+                                               float inv_nW, int C, int s, int c,
+                                               bool use_goal_kappa, float& gx,
                                                float& gy, float& gth, float& p3, bool& have_centre,
                                                float& v_ref) {
     if (goals) {
@@ -259,7 +263,8 @@ __device__ __forceinline__ void candidate_goal(const Centre* __restrict__ centre
         have_centre = true;
         v_ref = -1.0f;
     } else {
-        const int row = c / nW, k = c - row * nW;
+        // (c + 0.5) / nW is at least 0.5 / nW away from an integer: exact in FP32 for c < 2^22
+        const int row = __float2int_rd(((float)c + 0.5f) * inv_nW), k = c - row * nW;
         const Centre* ce = centres + (size_t)s * nL + row;
         const float4 a = __ldg(reinterpret_cast<const float4*>(ce));
         const float4 b = __ldg(reinterpret_cast<const float4*>(ce) + 1);
@@ -421,9 +426,6 @@ sample_warp_kernel(SampleArgs a, const int32_t* __restrict__ near_i,
 // K3 + K4: fused generate / cost / collision, one warp per candidate
 // ---------------------------------------------------------------------------------------------
 #define EVAL_MAX_WARPS 8
-#ifndef EVAL_MIN_BLOCKS
-#define EVAL_MIN_BLOCKS 1   // raise to trade registers for resident warps (build-time experiment)
-#endif
 
 // collision predicate pieces use explicitly rounded FP32 ops (no FMA contraction) so that the
 // float32 mirror in the oracle reproduces the flags bit for bit on identical inputs.
@@ -453,22 +455,39 @@ __device__ __forceinline__ bool grid_hit(const uint8_t* __restrict__ occ, int gw
     return __ldg(occ + (size_t)row * gw + col) != 0;
 }
 
-template <int IPL, int S, int SG>
-__global__ void __launch_bounds__(EVAL_MAX_WARPS * 32, EVAL_MIN_BLOCKS) eval_kernel(EvalArgs a) {
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+#define EVAL_SEG_PAD 32   // readable slack behind the window tables (software-pipelined loads)
+
+// One CTA per (scenario, candidate chunk).  The CTA builds the scenario's raceline window once,
+// then its NW warps pull candidates of the chunk from a shared counter until it is exhausted
+// (warps that finish an early-exit candidate immediately take the next one).
+template <int IPL, int S, int SG, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
     constexpr int GG = 32 / SG;
     extern __shared__ __align__(16) unsigned char ev_smem[];
+    __shared__ int s_next;
+    __shared__ float s_gf[6];
+    __shared__ int s_gi[4];
     const int M = a.ep.M;
-    const int nwarps = blockDim.x >> 5;
+    const int ntab = a.nseg_pad + EVAL_SEG_PAD;
     float4* sA = reinterpret_cast<float4*>(ev_smem);
-    float2* sB = reinterpret_cast<float2*>(sA + a.nseg_pad);
-    float4* sopp = reinterpret_cast<float4*>(sB + a.nseg_pad);               // [F1L_MAX_OPP]
+    float2* sB = reinterpret_cast<float2*>(sA + ntab);
+    float4* sopp = reinterpret_cast<float4*>(sB + ntab);                     // [F1L_MAX_OPP]
     float* sprev = reinterpret_cast<float*>(sopp + F1L_MAX_OPP);             // [M] (padded to 4)
-    float2* slab_all = reinterpret_cast<float2*>(sprev + ((M + 3) & ~3));    // [nwarps][M]
+    float2* slab_all = reinterpret_cast<float2*>(sprev + ((M + 3) & ~3));    // [NW][M]
 
-    const int s = blockIdx.x / a.ctas_per_scn;
-    const int cta = blockIdx.x - s * a.ctas_per_scn;
+    int s, cta;
+    if (a.ctas_per_scn == 1) { s = blockIdx.x; cta = 0; }
+    else { s = blockIdx.x / a.ctas_per_scn; cta = blockIdx.x - s * a.ctas_per_scn; }
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const QueryCtx* __restrict__ q = a.ctx + s;
+    const int cb = a.c_begin + cta * a.chunk;
+    const int ce = min(cb + a.chunk, a.c_end);
 
     // ---- prologue: raceline window -> vehicle frame -> line form in shared memory.  Only the
     //      subtraction of the pose happens in float64 (|coordinates| reach 85 m, the window is
@@ -477,7 +496,7 @@ __global__ void __launch_bounds__(EVAL_MAX_WARPS * 32, EVAL_MIN_BLOCKS) eval_ker
         const double px = q->px, py = q->py;
         const float cth = q->cth, sth = q->sth;
         const int seg0 = q->seg0, nseg = q->nseg, ns = a.tr.n - 1;
-        for (int k = tid; k < a.nseg_pad; k += blockDim.x) {
+        for (int k = tid; k < ntab; k += NW * 32) {
             float4 A = make_float4(1.0f, 0.0f, 1e15f, 1e15f);  // padding: far away, finite
             float2 Bv = make_float2(1.0f, 1.0f);
             if (k < nseg) {
@@ -498,136 +517,159 @@ __global__ void __launch_bounds__(EVAL_MAX_WARPS * 32, EVAL_MIN_BLOCKS) eval_ker
             sB[k] = Bv;
         }
         if (a.prev_theta)
-            for (int i = tid; i < M; i += blockDim.x) sprev[i] = a.prev_theta[i];
+            for (int i = tid; i < M; i += NW * 32) sprev[i] = a.prev_theta[i];
         if (tid < F1L_MAX_OPP) sopp[tid] = q->opp[tid];
+        if (tid == 0) s_next = cb + NW;
+        // per-scenario collision constants live in shared memory, not in registers, so that the
+        // candidate loop does not carry them through the deviation pass
+        if (tid == 32 % (NW * 32)) {
+            s_gf[0] = q->gA00; s_gf[1] = q->gA01; s_gf[2] = q->gA10; s_gf[3] = q->gA11;
+            s_gf[4] = q->gfx; s_gf[5] = q->gfy;
+            s_gi[0] = q->gix; s_gi[1] = q->giy; s_gi[2] = q->n_opp; s_gi[3] = q->has_grid;
+        }
     }
     __syncthreads();
 
-    const int c = a.c_begin + cta * nwarps + wid;
-    if (c >= a.c_end) return;
     float2* slab = slab_all + (size_t)wid * M;
 
-    // ---- goal, seed, Newton ----
-    float gx, gy, gth, p3, v_ref;
-    bool have_centre;
-    candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.C, s, c, a.ep.use_goal_kappa != 0,
-                   gx, gy, gth, p3, have_centre, v_ref);
-    SpiralF sp;
-    sp.p0 = 0.0f;
-    sp.p3 = p3;
-    {
-        const float4 seed = lut_lookup(a.lut, gx, gy, gth);
-        sp.p1 = seed.x; sp.p2 = seed.y; sp.sf = seed.z;
-    }
-    const int n_pass = spiral_newton(sp, gx, gy, gth, a.ep.n_newton, lane);
-
-    // ---- arc samples ----
-    float x[IPL], y[IPL], th[IPL], kp[IPL], cs[IPL], sn[IPL];
-    spiral_sample<IPL>(sp, M, lane, x, y, th, kp, cs, sn);
-
-    const size_t cand = (size_t)s * a.C + c;
-    if (a.states) {
-#pragma unroll
-        for (int j = 0; j < IPL; ++j) {
-            const int i = lane * IPL + j;
-            if (i < M) a.states[cand * M + i] = make_float4(x[j], y[j], th[j], kp[j]);
-        }
-    }
-    if (a.headings) {
-#pragma unroll
-        for (int j = 0; j < IPL; ++j) {
-            const int i = lane * IPL + j;
-            if (i < M) a.headings[cand * M + i] = make_float2(cs[j], sn[j]);
-        }
-    }
-
-    // ---- curvature terms, endpoint, validity ----
-    float maxk = 0.0f, sumk = 0.0f, ex = 0.0f, ey = 0.0f, eth = 0.0f;
-#pragma unroll
-    for (int j = 0; j < IPL; ++j) {
-        const int i = lane * IPL + j;
-        if (i < M) {
-            const float ak = fabsf(kp[j]);
-            maxk = fmaxf(maxk, ak);
-            sumk += ak;
-            slab[i] = make_float2(x[j], y[j]);
-            if (i == M - 1) { ex = x[j]; ey = y[j]; eth = th[j]; }
-        }
-    }
-    const int last_lane = (M - 1) / IPL;
-    ex = __shfl_sync(F1L_FULL, ex, last_lane);
-    ey = __shfl_sync(F1L_FULL, ey, last_lane);
-    eth = __shfl_sync(F1L_FULL, eth, last_lane);
-    maxk = warp_max(maxk);
-    sumk = warp_sum(sumk);
-    const float gn = sqrtf(fmaf(gx, gx, fmaf(gy, gy, gth * gth)));
-    const float tol = a.ep.tol * fmaxf(gn, 1.0f);
-    bool valid = have_centre && isfinite(sp.p1) && isfinite(sp.p2) && isfinite(sp.sf) &&
-                 sp.sf > 0.0f && fabsf(ex - gx) < tol && fabsf(ey - gy) < tol &&
-                 fabsf(eth - gth) < tol;
-    if (valid && a.ep.kappa_max > 0.0f && !(maxk <= a.ep.kappa_max)) valid = false;
-
-    unsigned flags = valid ? F1L_FLAG_VALID : 0u;
-    if (!have_centre) flags |= F1L_FLAG_NO_CENTRE;
-    flags |= (unsigned)min(n_pass, 15) << F1L_FLAG_PASS_SHIFT;
-    float t_len = 0.0f, t_maxk = 0.0f, t_meank = 0.0f, t_sim = 0.0f, t_dev = 0.0f;
-    float cost = CUDART_INF_F;
-
-    if (valid) {  // warp-uniform
-        t_len = __fdividef(1.0f, sp.sf);       // lattice_planner.py:271
-        t_maxk = maxk;                         // :277
-        t_meank = sumk / (float)M;             // :284
-
-        // ---- similarity (lattice_planner.py:287-296), collision ----
-        float sim = 0.0f;
-        bool hit_opp = false, hit_map = false;
-        const int lim = M - a.ep.n_shift - a.ep.n_cull;
-        const int n_opp = q->n_opp;
-        const bool has_grid = q->has_grid != 0;
-        const float hl = a.ep.half_l, hw = a.ep.half_w;
-        const float A00 = q->gA00, A01 = q->gA01, A10 = q->gA10, A11 = q->gA11;
-        const float gfx = q->gfx, gfy = q->gfy;
-        const int gix = q->gix, giy = q->giy;
-        // candidate-level opponent pruning: every point of a curve of length s_f from the origin
-        // to (ex, ey) lies within s_f/2 of the chord's midpoint, so an opponent farther than
-        // s_f/2 + 2 r_circ from it cannot pass the per-sample broad phase.  Exact (conservative).
-        unsigned opp_mask;
+    for (int c = cb + wid; c < ce;) {
+        // ---- goal, seed, Newton ----
+        float gx, gy, gth, p3, v_ref;
+        bool have_centre;
+        candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.inv_nW, a.C, s, c,
+                       a.ep.use_goal_kappa != 0, gx, gy, gth, p3, have_centre, v_ref);
+        SpiralF sp;
+        sp.p0 = 0.0f;
+        sp.p3 = p3;
         {
-            const float4 o = sopp[lane & (F1L_MAX_OPP - 1)];
-            const float mx = o.x - 0.5f * ex, my = o.y - 0.5f * ey;
-            const float reach = 0.5f * sp.sf + sqrtf(a.ep.rc2) + 1e-3f;
-            opp_mask = __ballot_sync(F1L_FULL, lane < n_opp && fmaf(mx, mx, my * my) <= reach * reach);
+            const float4 seed = lut_lookup(a.lut, gx, gy, gth);
+            sp.p1 = seed.x; sp.p2 = seed.y; sp.sf = seed.z;
         }
+        const int n_pass = spiral_newton(sp, gx, gy, gth, a.ep.n_newton, lane);
+
+        // ---- arc samples ----
+        float x[IPL], y[IPL], th[IPL], kp[IPL], cs[IPL], sn[IPL];
+        spiral_sample<IPL>(sp, M, lane, x, y, th, kp, cs, sn);
+
+        const size_t cand = (size_t)s * a.C + c;
+        if (a.states) {
+#pragma unroll
+            for (int j = 0; j < IPL; ++j) {
+                const int i = lane * IPL + j;
+                if (i < M) a.states[cand * M + i] = make_float4(x[j], y[j], th[j], kp[j]);
+            }
+        }
+        if (a.headings) {
+#pragma unroll
+            for (int j = 0; j < IPL; ++j) {
+                const int i = lane * IPL + j;
+                if (i < M) a.headings[cand * M + i] = make_float2(cs[j], sn[j]);
+            }
+        }
+
+        // ---- curvature terms, endpoint, validity ----
+        float maxk = 0.0f, sumk = 0.0f, ex = 0.0f, ey = 0.0f, eth = 0.0f;
+        __syncwarp();   // the previous candidate's deviation pass has finished reading the slab
 #pragma unroll
         for (int j = 0; j < IPL; ++j) {
             const int i = lane * IPL + j;
             if (i < M) {
-                if (a.prev_theta && i < lim) {
-                    const float d = th[j] - sprev[i + a.ep.n_shift];
-                    sim = fmaf(d, d, sim);
-                }
-                for (unsigned m = opp_mask; m; m &= m - 1) {
-                    const float4 o = sopp[__ffs(m) - 1];
-                    const float tx = fs(o.x, x[j]), ty = fs(o.y, y[j]);
-                    const float d2 = fa(fm(tx, tx), fm(ty, ty));
-                    if (d2 <= a.ep.rc2 && sat_collide(tx, ty, cs[j], sn[j], o.z, o.w, hl, hw))
-                        hit_opp = true;
-                }
-                if (has_grid) {
-                    // footprint centre in grid-cell coordinates
+                const float ak = fabsf(kp[j]);
+                maxk = fmaxf(maxk, ak);
+                sumk += ak;
+                slab[i] = make_float2(x[j], y[j]);
+                if (i == M - 1) { ex = x[j]; ey = y[j]; eth = th[j]; }
+            }
+        }
+        const int last_lane = (M - 1) / IPL;
+        ex = __shfl_sync(F1L_FULL, ex, last_lane);
+        ey = __shfl_sync(F1L_FULL, ey, last_lane);
+        eth = __shfl_sync(F1L_FULL, eth, last_lane);
+        maxk = warp_max(maxk);
+        sumk = warp_sum(sumk);
+        const float gn = sqrtf(fmaf(gx, gx, fmaf(gy, gy, gth * gth)));
+        const float tol = a.ep.tol * fmaxf(gn, 1.0f);
+        bool valid = have_centre && isfinite(sp.p1) && isfinite(sp.p2) && isfinite(sp.sf) &&
+                     sp.sf > 0.0f && fabsf(ex - gx) < tol && fabsf(ey - gy) < tol &&
+                     fabsf(eth - gth) < tol;
+        if (valid && a.ep.kappa_max > 0.0f && !(maxk <= a.ep.kappa_max)) valid = false;
+
+        unsigned flags = valid ? F1L_FLAG_VALID : 0u;
+        if (!have_centre) flags |= F1L_FLAG_NO_CENTRE;
+        flags |= (unsigned)min(n_pass, 15) << F1L_FLAG_PASS_SHIFT;
+        float t_len = 0.0f, t_maxk = 0.0f, t_meank = 0.0f, t_sim = 0.0f, t_dev = 0.0f;
+        float cost = CUDART_INF_F;
+
+        if (valid) {  // warp-uniform
+            t_len = __fdividef(1.0f, sp.sf);       // lattice_planner.py:271
+            t_maxk = maxk;                         // :277
+            t_meank = sumk / (float)M;             // :284
+
+            // ---- similarity (lattice_planner.py:287-296), collision ----
+            float sim = 0.0f;
+            bool hit_opp = false, hit_map = false;
+            const uint8_t* occ = a.grid.occ;
+            const int gw = a.grid.w, gh = a.grid.h;
+            const int n_opp = s_gi[2];
+            const bool has_grid = s_gi[3] != 0;
+            const float hl = a.ep.half_l, hw = a.ep.half_w;
+            const float A00 = s_gf[0], A01 = s_gf[1], A10 = s_gf[2], A11 = s_gf[3];
+            const float gfx = s_gf[4], gfy = s_gf[5];
+            const int gix = s_gi[0], giy = s_gi[1];
+            const int lim = M - a.ep.n_shift - a.ep.n_cull;
+            const float reach_pad = sqrtf(a.ep.rc2) + 1e-3f;
+            // clearance map: clear[cell] = Chebyshev distance (cells) to the nearest occupied /
+            // out-of-bounds cell.  All nine probes fall within `probe_reach` cells of the
+            // footprint-centre cell, so a larger clearance proves them free without touching
+            // them.  The loads are issued first, the opponent tests cover their latency.
+            int clr[IPL];
+#pragma unroll
+            for (int j = 0; j < IPL; ++j) {
+                const int i = lane * IPL + j;
+                clr[j] = 0;
+                if (has_grid && a.grid.clear && i < M) {
                     const float ccx = fa(fa(fm(A00, x[j]), fm(A01, y[j])), gfx);
                     const float ccy = fa(fa(fm(A10, x[j]), fm(A11, y[j])), gfy);
-                    const uint8_t* occ = a.grid.occ;
-                    const int gw = a.grid.w, gh = a.grid.h;
-                    // clearance map: clear[cell] = Chebyshev distance (cells) to the nearest
-                    // occupied / out-of-bounds cell.  All nine probes fall within
-                    // `probe_reach` cells of the centre cell, so a larger clearance proves them
-                    // free without touching them.
                     const int ccol = gix + __float2int_rd(ccx), crow = giy + __float2int_rd(ccy);
-                    bool need = true;
-                    if (a.grid.clear && (unsigned)ccol < (unsigned)gw && (unsigned)crow < (unsigned)gh)
-                        need = __ldg(a.grid.clear + (size_t)crow * gw + ccol) <= a.grid.probe_reach;
-                    if (need) {
+                    if ((unsigned)ccol < (unsigned)gw && (unsigned)crow < (unsigned)gh)
+                        clr[j] = __ldg(a.grid.clear + (size_t)crow * gw + ccol);
+                }
+            }
+            // candidate-level opponent pruning: every point of a curve of length s_f from the
+            // origin to (ex, ey) lies within s_f/2 of the chord's midpoint, so an opponent
+            // farther than s_f/2 + 2 r_circ from it cannot pass the per-sample broad phase.
+            unsigned opp_mask;
+            {
+                const float4 o = sopp[lane & (F1L_MAX_OPP - 1)];
+                const float mx = o.x - 0.5f * ex, my = o.y - 0.5f * ey;
+                const float reach = 0.5f * sp.sf + reach_pad;
+                opp_mask = __ballot_sync(F1L_FULL, lane < n_opp && fmaf(mx, mx, my * my) <= reach * reach);
+            }
+#pragma unroll
+            for (int j = 0; j < IPL; ++j) {
+                const int i = lane * IPL + j;
+                if (i < M) {
+                    if (a.prev_theta && i < lim) {
+                        const float d = th[j] - sprev[i + a.ep.n_shift];
+                        sim = fmaf(d, d, sim);
+                    }
+                    for (unsigned m = opp_mask; m; m &= m - 1) {
+                        const float4 o = sopp[__ffs(m) - 1];
+                        const float tx = fs(o.x, x[j]), ty = fs(o.y, y[j]);
+                        const float d2 = fa(fm(tx, tx), fm(ty, ty));
+                        if (d2 <= a.ep.rc2 && sat_collide(tx, ty, cs[j], sn[j], o.z, o.w, hl, hw))
+                            hit_opp = true;
+                    }
+                }
+            }
+            if (has_grid) {
+#pragma unroll
+                for (int j = 0; j < IPL; ++j) {
+                    const int i = lane * IPL + j;
+                    if (i < M && clr[j] <= a.grid.probe_reach) {
+                        // footprint centre and half-axes in grid-cell coordinates
+                        const float ccx = fa(fa(fm(A00, x[j]), fm(A01, y[j])), gfx);
+                        const float ccy = fa(fa(fm(A10, x[j]), fm(A11, y[j])), gfy);
                         const float lx = fm(cs[j], hl), ly = fm(sn[j], hl);    // body x axis * hl
                         const float wx = fm(-sn[j], hw), wy = fm(cs[j], hw);   // body y axis * hw
                         const float elx = fa(fm(A00, lx), fm(A01, ly)), ely = fa(fm(A10, lx), fm(A11, ly));
@@ -647,76 +689,86 @@ __global__ void __launch_bounds__(EVAL_MAX_WARPS * 32, EVAL_MIN_BLOCKS) eval_ker
                     }
                 }
             }
-        }
-        t_sim = warp_sum(sim);
-        hit_opp = __any_sync(F1L_FULL, hit_opp);
-        hit_map = __any_sync(F1L_FULL, hit_map);
-        if (hit_opp) flags |= F1L_FLAG_COLLIDE_OPP;
-        if (hit_map) flags |= F1L_FLAG_COLLIDE_MAP;
+            t_sim = warp_sum(sim);
+            hit_opp = __any_sync(F1L_FULL, hit_opp);
+            hit_map = __any_sync(F1L_FULL, hit_map);
+            if (hit_opp) flags |= F1L_FLAG_COLLIDE_OPP;
+            if (hit_map) flags |= F1L_FLAG_COLLIDE_MAP;
 
-        // ---- raceline deviation: mean over samples of the nearest distance to the window
-        //      (nearest_point semantics, utils.py:53-66).  Lane = (sample group sg, segment
-        //      group gg); each lane keeps S samples in registers and walks every GG-th segment.
-        __syncwarp();
-        {
-            const int sgi = lane / GG, ggi = lane - sgi * GG;
-            float sx[S], sy[S], bd[S];
-#pragma unroll
-            for (int j = 0; j < S; ++j) {
-                const int i = j * SG + sgi;
-                const float2 p = slab[i < M ? i : M - 1];
-                sx[j] = p.x; sy[j] = p.y; bd[j] = CUDART_INF_F;
-            }
-            const int nq = a.nseg_pad;
-#pragma unroll 2
-            for (int k = ggi; k < nq; k += GG) {
-                const float4 A = sA[k];
-                const float2 Bv = sB[k];
+            // ---- raceline deviation: mean over samples of the nearest distance to the window
+            //      (nearest_point semantics, utils.py:53-66).  Lane = (sample group sg, segment
+            //      group gg); each lane keeps S samples in registers and walks every GG-th
+            //      segment, the next segment's table entry already in flight.
+            __syncwarp();
+            {
+                const int sgi = lane / GG, ggi = lane - sgi * GG;
+                float sx[S], sy[S], bd[S];
 #pragma unroll
                 for (int j = 0; j < S; ++j) {
-                    const float qq = fmaf(sx[j], A.x, fmaf(sy[j], A.y, -A.z));
-                    const float nn = fmaf(sy[j], A.x, fmaf(-sx[j], A.y, -A.w));
-                    const float t = __saturatef(qq * Bv.y);
-                    const float e = fmaf(-t, Bv.x, qq);
-                    bd[j] = fminf(bd[j], fmaf(e, e, nn * nn));
+                    const int i = j * SG + sgi;
+                    const float2 p = slab[i < M ? i : M - 1];
+                    sx[j] = p.x; sy[j] = p.y; bd[j] = CUDART_INF_F;
                 }
-            }
+                const int nq = a.nseg_pad;
+                float4 A = sA[ggi];
+                float2 Bv = sB[ggi];
+#pragma unroll 2
+                for (int k = ggi; k < nq; k += GG) {
+                    const float4 An = sA[k + GG];   // table has EVAL_SEG_PAD entries of slack
+                    const float2 Bn = sB[k + GG];
 #pragma unroll
-            for (int o = 1; o < GG; o <<= 1) {
+                    for (int j = 0; j < S; ++j) {
+                        const float qq = fmaf(sx[j], A.x, fmaf(sy[j], A.y, -A.z));
+                        const float nn = fmaf(sy[j], A.x, fmaf(-sx[j], A.y, -A.w));
+                        const float t = __saturatef(qq * Bv.y);
+                        const float e = fmaf(-t, Bv.x, qq);
+                        bd[j] = fminf(bd[j], fmaf(e, e, nn * nn));
+                    }
+                    A = An;
+                    Bv = Bn;
+                }
 #pragma unroll
-                for (int j = 0; j < S; ++j) bd[j] = fminf(bd[j], __shfl_xor_sync(F1L_FULL, bd[j], o));
-            }
-            float dsum = 0.0f;
+                for (int o = 1; o < GG; o <<= 1) {
 #pragma unroll
-            for (int j = 0; j < S; ++j) {
-                const int i = j * SG + sgi;
-                if ((j % GG) == ggi && i < M) dsum += sqrtf(bd[j]);
+                    for (int j = 0; j < S; ++j) bd[j] = fminf(bd[j], __shfl_xor_sync(F1L_FULL, bd[j], o));
+                }
+                // every lane of a sample group now holds the same S minima: sum them on all
+                // lanes (branch-free) and divide by the group size
+                float dsum = 0.0f;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const int i = j * SG + sgi;
+                    dsum += (i < M) ? fast_sqrt(bd[j]) : 0.0f;
+                }
+                t_dev = warp_sum(dsum) * (1.0f / (float)GG) / (float)M;
             }
-            t_dev = warp_sum(dsum) / (float)M;
+
+            if (!(flags & (F1L_FLAG_COLLIDE_OPP | F1L_FLAG_COLLIDE_MAP))) {
+                cost = a.ep.w[0] * t_len + a.ep.w[1] * t_maxk + a.ep.w[2] * t_meank +
+                       a.ep.w[3] * t_sim + a.ep.w[4] * t_dev;
+                if (!isfinite(cost)) cost = CUDART_INF_F;
+            }
         }
 
-        if (!(flags & (F1L_FLAG_COLLIDE_OPP | F1L_FLAG_COLLIDE_MAP))) {
-            cost = a.ep.w[0] * t_len + a.ep.w[1] * t_maxk + a.ep.w[2] * t_meank +
-                   a.ep.w[3] * t_sim + a.ep.w[4] * t_dev;
-            if (!isfinite(cost)) cost = CUDART_INF_F;
+        int c_next = 0;
+        if (lane == 0) {
+            if (a.costs) a.costs[cand] = cost;
+            if (a.flags) a.flags[cand] = (uint8_t)flags;
+            if (a.terms) {
+                float* t = a.terms + cand * F1L_N_TERMS;
+                t[0] = t_len; t[1] = t_maxk; t[2] = t_meank; t[3] = t_sim; t[4] = t_dev;
+            }
+            if (a.goals_out) {
+                float* g = a.goals_out + cand * 3;
+                g[0] = gx; g[1] = gy; g[2] = gth;
+            }
+            if (a.params) a.params[cand] = make_float4(sp.p1, sp.p2, sp.sf, sp.p3);
+            const unsigned long long key =
+                ((unsigned long long)float_orderable(cost) << 32) | (unsigned)c;
+            atomicMin(a.best + s, key);
+            c_next = atomicAdd(&s_next, 1);
         }
-    }
-
-    if (lane == 0) {
-        if (a.costs) a.costs[cand] = cost;
-        if (a.flags) a.flags[cand] = (uint8_t)flags;
-        if (a.terms) {
-            float* t = a.terms + cand * F1L_N_TERMS;
-            t[0] = t_len; t[1] = t_maxk; t[2] = t_meank; t[3] = t_sim; t[4] = t_dev;
-        }
-        if (a.goals_out) {
-            float* g = a.goals_out + cand * 3;
-            g[0] = gx; g[1] = gy; g[2] = gth;
-        }
-        if (a.params) a.params[cand] = make_float4(sp.p1, sp.p2, sp.sf, sp.p3);
-        const unsigned long long key =
-            ((unsigned long long)float_orderable(cost) << 32) | (unsigned)c;
-        atomicMin(a.best + s, key);
+        c = __shfl_sync(F1L_FULL, c_next, 0);
     }
 }
 
@@ -737,7 +789,7 @@ __global__ void __launch_bounds__(32) select_kernel(SelectArgs a) {
 
     float gx, gy, gth, p3, v_ref;
     bool have_centre;
-    candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.C, s, idx,
+    candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.inv_nW, a.C, s, idx,
                    a.ep.use_goal_kappa != 0, gx, gy, gth, p3, have_centre, v_ref);
     SpiralF sp;
     sp.p0 = 0.0f;
