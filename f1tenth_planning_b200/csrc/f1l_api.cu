@@ -299,7 +299,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     const int n_cand = c_end - c_begin;
     const int wpc = pick_warps_per_cta(n_cand, M);
     const size_t smem = eval_smem_bytes(nseg_pad, wpc, M);
-    if (smem > 227 * 1024) return F1L_ERR_TOO_LARGE;
+    if (smem > 226 * 1024) return F1L_ERR_TOO_LARGE;
 
     SampleArgs sa;
     sa.tr = track_view(h);
@@ -352,8 +352,9 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     ea.c_begin = c_begin;
     ea.c_end = c_end;
     {
-        // enough CTAs to fill the machine twice; a CTA works through `chunk` candidates
-        const long long target = 2LL * h->sm_count * 3;
+        // enough CTAs for ~8 waves (tail < 1/8 of a dense single query); a CTA works through
+        // `chunk` candidates, so batches of small queries get one CTA per scenario
+        const long long target = 8LL * h->sm_count * 3;
         long long per = (target + S - 1) / S;
         const long long max_per = (n_cand + wpc - 1) / wpc;
         if (per > max_per) per = max_per;
@@ -572,14 +573,18 @@ int f1l_create(f1l_handle* out, int device, const f1l_config* cfg) {
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
         if (sm > 0) h->sm_count = sm;
         // opt in to large dynamic shared memory for every eval instantiation + the scan kernel
-        const int big = 227 * 1024;
+        const int big = 226 * 1024;  // opt-in maximum is 227 KB per block INCLUDING static shared memory
         for (int nw = 7; nw <= 8; ++nw) {
             const int ms[] = {32, 64, 100, 128, 200, 256};
-            for (int m : ms)
-                cudaFuncSetAttribute(eval_entry(m, nw), cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+            for (int m : ms) {
+                cudaError_t e2 = cudaFuncSetAttribute(
+                    eval_entry(m, nw), cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+                if (e2 != cudaSuccess && e == cudaSuccess) e = e2;
+            }
         }
-        e = cudaFuncSetAttribute(pp_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)PP_SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(pp_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)PP_SMEM_BYTES);
     }
     if (e != cudaSuccess) {
         fail(h, e, "f1l_create");

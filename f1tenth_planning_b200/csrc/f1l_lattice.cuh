@@ -461,6 +461,9 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     return r;
 }
 
+#ifndef EVAL_SEG_UNROLL
+#define EVAL_SEG_UNROLL 2
+#endif
 #define EVAL_SEG_PAD 32   // readable slack behind the window tables (software-pipelined loads)
 
 // One CTA per (scenario, candidate chunk).  The CTA builds the scenario's raceline window once,
@@ -469,6 +472,7 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 template <int IPL, int S, int SG, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
     constexpr int GG = 32 / SG;
+    constexpr int kSegUnroll = EVAL_SEG_UNROLL;
     extern __shared__ __align__(16) unsigned char ev_smem[];
     __shared__ int s_next;
     __shared__ float s_gf[6];
@@ -712,7 +716,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 const int nq = a.nseg_pad;
                 float4 A = sA[ggi];
                 float2 Bv = sB[ggi];
-#pragma unroll 2
+#pragma unroll kSegUnroll
                 for (int k = ggi; k < nq; k += GG) {
                     const float4 An = sA[k + GG];   // table has EVAL_SEG_PAD entries of slack
                     const float2 Bn = sB[k + GG];
