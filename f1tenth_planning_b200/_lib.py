@@ -42,7 +42,7 @@ class PlanResult(C.Structure):
                 ("no_feasible", C.c_int32), ("tracker_found", C.c_int32),
                 ("n_candidates", C.c_int32), ("best_cost", C.c_float), ("reserved", C.c_int32),
                 ("best_traj", _fp), ("costs", _fp), ("terms", _fp), ("flags", _bp),
-                ("goals", _fp), ("params", _fp), ("states", _fp)]
+                ("goals", _fp), ("params", _fp), ("states", _fp), ("headings", _fp)]
 
 
 # name -> (restype, argtypes); must list every symbol include/f1l.h declares

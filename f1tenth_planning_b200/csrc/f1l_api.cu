@@ -815,6 +815,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     if (out->goals) ENS(h->q_gout, (size_t)C * 3 * 4);
     if (out->params) ENS(h->q_params, (size_t)C * 16);
     if (out->states) ENS(h->q_states, (size_t)C * M * 16);
+    if (out->headings) ENS(h->q_headings, (size_t)C * M * 8);
     CK(cudaMemcpyAsync(h->q_in.p, hin, (4 + 3 * (size_t)n_opp) * sizeof(double),
                        cudaMemcpyHostToDevice, st));
     const float4* d_goals = nullptr;
@@ -844,6 +845,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     o.goals_out = out->goals ? (float*)h->q_gout.p : nullptr;
     o.params = out->params ? (float4*)h->q_params.p : nullptr;
     o.states = out->states ? (float4*)h->q_states.p : nullptr;
+    o.headings = out->headings ? (float2*)h->q_headings.p : nullptr;
     o.prev_out = update_prev ? (float*)h->prev.p : nullptr;
     if (c_begin != 0 || (c_end > 0 && c_end < C)) {
         // sharded evaluation: untouched candidates keep +inf / zero flags
@@ -875,6 +877,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     if (out->goals) CK(cudaMemcpyAsync(out->goals, h->q_gout.p, (size_t)C * 12, cudaMemcpyDeviceToHost, st));
     if (out->params) CK(cudaMemcpyAsync(out->params, h->q_params.p, (size_t)C * 16, cudaMemcpyDeviceToHost, st));
     if (out->states) CK(cudaMemcpyAsync(out->states, h->q_states.p, (size_t)C * M * 16, cudaMemcpyDeviceToHost, st));
+    if (out->headings) CK(cudaMemcpyAsync(out->headings, h->q_headings.p, (size_t)C * M * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (update_prev) {
         h->has_prev = 1;

@@ -18,7 +18,7 @@ _dp, _fp, _ip, _bp = _lib._dp, _lib._fp, _lib._ip, _lib._bp
 
 PlanDetail = namedtuple("PlanDetail", [
     "steer", "speed", "best_traj", "best_idx", "best_cost", "costs", "terms", "flags", "goals",
-    "params", "states", "no_feasible", "tracker_found"])
+    "params", "states", "no_feasible", "tracker_found", "headings"])
 
 BatchPlan = namedtuple("BatchPlan", ["best_idx", "best_cost", "best_traj", "costs", "flags",
                                      "steer_speed"])
@@ -154,7 +154,7 @@ class Engine:
         self._ck(self._L.f1l_set_prev_path(self._h, _ptr(t, _fp), t.size))
 
     # -- single query -----------------------------------------------------------------------
-    def _result(self, C_, detail, want_states):
+    def _result(self, C_, detail, want_states, want_headings=False):
         M = self.n_samples
         res = _lib.PlanResult()
         bufs = {"best_traj": np.zeros((M, 4), np.float32)}
@@ -173,6 +173,9 @@ class Engine:
         if want_states:
             bufs["states"] = np.zeros((C_, M, 4), np.float32)
             res.states = _ptr(bufs["states"], _fp)
+        if want_headings:
+            bufs["headings"] = np.zeros((C_, M, 2), np.float32)
+            res.headings = _ptr(bufs["headings"], _fp)
         return res, bufs
 
     @staticmethod
@@ -180,7 +183,7 @@ class Engine:
         return PlanDetail(res.steer, res.speed, bufs["best_traj"], res.best_idx, res.best_cost,
                           bufs.get("costs"), bufs.get("terms"), bufs.get("flags"),
                           bufs.get("goals"), bufs.get("params"), bufs.get("states"),
-                          bool(res.no_feasible), bool(res.tracker_found))
+                          bool(res.no_feasible), bool(res.tracker_found), bufs.get("headings"))
 
     @staticmethod
     def _opp(opponent_poses):
@@ -192,14 +195,14 @@ class Engine:
         return (o, o.shape[0]) if o.shape[0] else (None, 0)
 
     def plan(self, pose, opponent_poses=None, update_prev=True, detail=True, want_states=False,
-             shard=None):
+             shard=None, want_headings=False):
         """One query.  pose = (x, y, theta, velocity).  shard = (c_begin, c_end) evaluates a
         candidate range only (dense-sweep sharding across GPUs)."""
         pose = _f64(pose).ravel()
         if pose.size != 4:
             raise ValueError("pose must be (x, y, theta, velocity)")
         opp, k = self._opp(opponent_poses)
-        res, bufs = self._result(self.n_candidates, detail, want_states)
+        res, bufs = self._result(self.n_candidates, detail, want_states, want_headings)
         if shard is None:
             code = self._L.f1l_plan(self._h, _ptr(pose, _dp), _ptr(opp, _dp), k,
                                     int(bool(update_prev)), C.byref(res))

@@ -147,6 +147,8 @@ typedef struct {
     float* goals;            /* [C,3] local goals (x, y, theta) fed to the generator */
     float* params;           /* [C,4] solved spiral (p1, p2, s_f, p3) */
     float* states;           /* [C,M,4] every trajectory (debug / custom cost functions) */
+    float* headings;         /* [C,M,2] (cos, sin) of the sample headings used by the footprint
+                                (teacher-forced collision tests) */
 } f1l_plan_result;
 
 /*

@@ -680,3 +680,73 @@ int64_t f1o_plan_batch(const f1o_config* cfg, const f1o_world* w, const double* 
     }
     return (int64_t)s * C;
 }
+
+/* ------------------------------------------------------------------------- */
+/* float32 mirror of the device collision predicate (teacher-forced checks)    */
+/* ------------------------------------------------------------------------- */
+/* Same operations in the same order and rounding as eval_kernel's collision block
+ * (f1tenth_planning_b200/csrc/f1l_lattice.cuh: sat_collide / grid_hit and the explicitly
+ * rounded fm/fa/fs arithmetic); compiled with -ffp-contract=off so that no FMA is formed.
+ * Inputs are the device's own float32 states, footprint headings and per-query constants, so
+ * the flags must agree bit for bit. */
+static int sat_collide_f32(float tx, float ty, float c, float s, float oc, float os, float hl,
+                           float hw) {
+    const float cc = fabsf(c * oc + s * os);
+    const float ss = fabsf(s * oc - c * os);
+    const float rl = hl + (hl * cc + hw * ss);
+    const float rw = hw + (hl * ss + hw * cc);
+    const float e0 = fabsf(tx * c + ty * s);
+    const float e1 = fabsf(ty * c - tx * s);
+    const float e2 = fabsf(tx * oc + ty * os);
+    const float e3 = fabsf(ty * oc - tx * os);
+    return e0 < rl && e1 < rw && e2 < rl && e3 < rw;
+}
+
+static int grid_hit_f32(const uint8_t* occ, int gw, int gh, int ix0, int iy0, float cx, float cy) {
+    const int col = ix0 + (int)floorf(cx), row = iy0 + (int)floorf(cy);
+    if (col < 0 || row < 0 || col >= gw || row >= gh) return 1;
+    return occ[(size_t)row * gw + col] != 0;
+}
+
+void f1o_collide_f32(const float* states, const float* headings, int c, int m,
+                     const float* opp_local, int n_opp, const float* grid_xf,
+                     const int32_t* grid_i0, const uint8_t* grid, int gh, int gw, float half_l,
+                     float half_w, float rc2, uint8_t* flags_out) {
+    const float hl = half_l, hw = half_w;
+    for (int k = 0; k < c; ++k) {
+        int hit_opp = 0, hit_map = 0;
+        for (int i = 0; i < m; ++i) {
+            const float x = states[4 * ((size_t)k * m + i)], y = states[4 * ((size_t)k * m + i) + 1];
+            const float cs = headings[2 * ((size_t)k * m + i)], sn = headings[2 * ((size_t)k * m + i) + 1];
+            for (int o = 0; o < n_opp; ++o) {
+                const float tx = opp_local[4 * o] - x, ty = opp_local[4 * o + 1] - y;
+                const float d2 = tx * tx + ty * ty;
+                if (d2 <= rc2 && sat_collide_f32(tx, ty, cs, sn, opp_local[4 * o + 2],
+                                                 opp_local[4 * o + 3], hl, hw))
+                    hit_opp = 1;
+            }
+            if (grid) {
+                const float A00 = grid_xf[0], A01 = grid_xf[1], A10 = grid_xf[2], A11 = grid_xf[3];
+                const float ccx = (A00 * x + A01 * y) + grid_xf[4];
+                const float ccy = (A10 * x + A11 * y) + grid_xf[5];
+                const float lx = cs * hl, ly = sn * hl;
+                const float wx = -sn * hw, wy = cs * hw;
+                const float elx = A00 * lx + A01 * ly, ely = A10 * lx + A11 * ly;
+                const float ewx = A00 * wx + A01 * wy, ewy = A10 * wx + A11 * wy;
+                const int ix0 = grid_i0[0], iy0 = grid_i0[1];
+                int h = 0;
+                h |= grid_hit_f32(grid, gw, gh, ix0, iy0, (ccx + elx) + ewx, (ccy + ely) + ewy);
+                h |= grid_hit_f32(grid, gw, gh, ix0, iy0, (ccx + elx) - ewx, (ccy + ely) - ewy);
+                h |= grid_hit_f32(grid, gw, gh, ix0, iy0, (ccx - elx) + ewx, (ccy - ely) + ewy);
+                h |= grid_hit_f32(grid, gw, gh, ix0, iy0, (ccx - elx) - ewx, (ccy - ely) - ewy);
+                h |= grid_hit_f32(grid, gw, gh, ix0, iy0, ccx + elx, ccy + ely);
+                h |= grid_hit_f32(grid, gw, gh, ix0, iy0, ccx - elx, ccy - ely);
+                h |= grid_hit_f32(grid, gw, gh, ix0, iy0, ccx + ewx, ccy + ewy);
+                h |= grid_hit_f32(grid, gw, gh, ix0, iy0, ccx - ewx, ccy - ewy);
+                h |= grid_hit_f32(grid, gw, gh, ix0, iy0, ccx, ccy);
+                hit_map |= h;
+            }
+        }
+        flags_out[k] = (uint8_t)((hit_opp ? F1O_FLAG_COLLIDE_OPP : 0) | (hit_map ? F1O_FLAG_COLLIDE_MAP : 0));
+    }
+}

@@ -122,7 +122,7 @@ int64_t f1o_plan_batch(const f1o_config* cfg, const f1o_world* w, const double* 
 void f1o_collide_f32(const float* states, const float* headings, int c, int m,
                      const float* opp_local, int n_opp, const float* grid_xf,
                      const int32_t* grid_i0, const uint8_t* grid, int gh, int gw,
-                     float half_l, float half_w, uint8_t* flags_out);
+                     float half_l, float half_w, float rc2, uint8_t* flags_out);
 
 int f1o_max_threads(void);
 

@@ -79,6 +79,9 @@ def lib():
         L.f1o_default_config.argtypes = [C.POINTER(Config)]
         L.f1o_default_config.restype = None
         L.f1o_max_threads.restype = C.c_int
+        L.f1o_collide_f32.argtypes = [_fp, _fp, C.c_int, C.c_int, _fp, C.c_int, _fp, _ip, _bp,
+                                      C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _bp]
+        L.f1o_collide_f32.restype = None
         _lib = L
     return _lib
 
@@ -295,3 +298,22 @@ def plan_batch(cfg, world, poses, opp=None, n_opp=None, n_threads=1, want_traj=T
 
 def max_threads():
     return int(lib().f1o_max_threads())
+
+
+def collide_f32(states, headings, opp_local, n_opp, grid_xf, grid_i0, grid, half_l, half_w, rc2):
+    """float32 mirror of the device collision predicate on the device's own states -> flags [C]"""
+    st = np.ascontiguousarray(states, dtype=np.float32)
+    hd = np.ascontiguousarray(headings, dtype=np.float32)
+    op = np.ascontiguousarray(opp_local, dtype=np.float32)
+    xf = np.ascontiguousarray(grid_xf, dtype=np.float32)
+    i0 = np.ascontiguousarray(grid_i0, dtype=np.int32)
+    Cn, M = st.shape[0], st.shape[1]
+    out = np.zeros(Cn, np.uint8)
+    g = None if grid is None else np.ascontiguousarray(grid, dtype=np.uint8)
+    lib().f1o_collide_f32(st.ctypes.data_as(_fp), hd.ctypes.data_as(_fp), Cn, M,
+                          op.ctypes.data_as(_fp), int(n_opp), xf.ctypes.data_as(_fp),
+                          i0.ctypes.data_as(_ip), g.ctypes.data_as(_bp) if g is not None else _bp(),
+                          g.shape[0] if g is not None else 0, g.shape[1] if g is not None else 0,
+                          np.float32(half_l), np.float32(half_w), np.float32(rc2),
+                          out.ctypes.data_as(_bp))
+    return out

@@ -184,3 +184,27 @@ def test_batch_device_pointer_api(ellipse):
     b = eng.plan_batch(poses, opp, n_opp)
     assert np.array_equal(idx.cpu().numpy(), b.best_idx)
     assert np.array_equal(costs.cpu().numpy(), b.costs)
+
+
+def test_collision_flags_bit_exact_on_device_states(ellipse):
+    """Teacher-forced: the float32 mirror of the collision predicate, fed the device's own float32
+    states / headings / per-query constants, reproduces the opponent and map flags bit for bit
+    (the end-to-end comparison against the float64 oracle above tolerates boundary cases)."""
+    la, wd = synth.goal_grid(3)
+    grid = synth.corridor_grid(half_width=1.0)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, grid=grid)
+    n_checked = 0
+    for seed in (1003, 2, 3):
+        pose, opp = H.scenario(ellipse, seed, 8)
+        d = eng.plan(pose, opp, update_prev=False, want_states=True, want_headings=True)
+        f, i = eng.debug_query_ctx()
+        hl, hw = np.float32(0.5 * cfg.car_length), np.float32(0.5 * cfg.car_width)
+        rc2 = np.float32(4.0 * ((0.5 * cfg.car_length) ** 2 + (0.5 * cfg.car_width) ** 2))
+        mirror = co.collide_f32(d.states, d.headings, f[8:].reshape(16, 4), int(i[5]), f[2:8],
+                                i[0:2], grid[0], hl, hw, rc2)
+        valid = (d.flags & 1) != 0
+        assert valid.sum() > 1000
+        assert np.array_equal(mirror[valid], d.flags[valid] & 6)
+        assert (mirror[valid] & 2).any() and (mirror[valid] & 4).any() and (mirror[valid] == 0).any()
+        n_checked += int(valid.sum())
+    assert n_checked > 5000
