@@ -406,7 +406,10 @@ def run_ours(args):
             "kernel_share_of_step": k_eval / (ms_total / args.steps) if k_eval else None,
             "flops_per_launch": step_flops,
             "mufu_peak_gops": mufu_peak,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one eval_kernel launch of this workload
+            # (ncu --set full; profiles/r1_eval_kernel.md) -- bench.py cannot run under ncu itself
+            "traffic": 52218368 if S == S_PER_GPU else None,
+            "traffic_source": "profiles/r1_eval_kernel.md",
             "hbm": {"algorithmic_bytes_per_step": hbm_bytes,
                     "achieved_gbs": hbm_bytes / (ms_total / args.steps * 1e-3) / 1e9},
         },

@@ -1,0 +1,102 @@
+"""Writes the judged profile summaries under profiles/ from the scratch ncu outputs in gpurun_out/.
+
+    python tools/make_profile_summary.py <tag> <launches.csv> <eval.ncu-rep> [<pp.ncu-rep>]
+"""
+import csv
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag, launches, eval_rep = sys.argv[1], sys.argv[2], sys.argv[3]
+pp_rep = sys.argv[4] if len(sys.argv) > 4 else None
+out_dir = os.path.join(ROOT, "profiles")
+os.makedirs(out_dir, exist_ok=True)
+
+
+def launch_table(path):
+    rows = list(csv.reader(open(path)))
+    for k, r in enumerate(rows):
+        if "Kernel Name" in r:
+            hdr, start = r, k + 1
+            break
+    ix = {h: i for i, h in enumerate(hdr)}
+    seq = []
+    for r in rows[start:]:
+        if len(r) < len(hdr):
+            continue
+        v = float(r[ix["Metric Value"]].replace(",", ""))
+        u = r[ix["Metric Unit"]]
+        v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0}.get(u, 1.0)
+        seq.append((r[ix["Kernel Name"]].split("(")[0].replace("void ", ""), r[ix["Grid Size"]], v))
+    return seq
+
+
+seq = launch_table(launches)
+# the device-resident steps are the launches whose eval grid is the full 100000-scenario batch
+big = [i for i, (n, g, v) in enumerate(seq) if n.startswith("eval_kernel") and g.startswith("(100000")]
+lines = ["# ncu launch list, %s" % tag, "",
+         "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py "
+         "--steps 2 --warmup 1 --scenarios 100000 --no-extras --no-cpu-baseline` (cold-cache, serialised "
+         "launches: compare shares, not absolutes).", "",
+         "%d launches captured; the device-resident steps (eval grid = 100000 CTAs):" % len(seq), "",
+         "| step | kernel | grid | ms | share of step |", "|---|---|---|---|---|"]
+for si, i in enumerate(big):
+    grp = seq[i - 2:i + 2]
+    tot = sum(v for _, _, v in grp)
+    for n, g, v in grp:
+        lines.append("| %d | %s | %s | %.4f | %.1f %% |" % (si, n, g, v, 100 * v / tot))
+lines += ["", "Other launches: LUT build, clearance map (2), peak microbenchmarks (6), and the chunked "
+          "end-to-end arm (8192-scenario chunks of the same four kernels)."]
+open(os.path.join(out_dir, "%s_launches.md" % tag), "w").write("\n".join(lines) + "\n")
+
+
+def raw_metrics(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    return dict(zip(rows[0], zip(rows[1], rows[2])))
+
+
+WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed",
+        "smsp__thread_inst_executed_per_inst_executed.ratio",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.max",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum"]
+
+
+def kernel_summary(rep, title, kern_sub, name):
+    m = raw_metrics(rep)
+    src_csv = os.path.join(ROOT, "gpurun_out", name + "_src.csv")
+    with open(src_csv, "w") as f:
+        f.write(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True,
+                               text=True).stdout)
+    by_line = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), src_csv, kern_sub,
+                              os.path.join(ROOT, "f1tenth_planning_b200", "lib", "libf1l.so"), "30"],
+                             capture_output=True, text=True).stdout
+    mix = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_sass_summary.py"), src_csv],
+                         capture_output=True, text=True).stdout
+    lines = ["# %s" % title, "", "`ncu --set full --clock-control none --import-source on`, one launch; "
+             "read with `ncu -i ... --page raw|source --csv` and tools/ncu_by_line.py.", "", "## metrics", "",
+             "| metric | value | unit |", "|---|---|---|"]
+    for k in WANT:
+        if k in m:
+            lines.append("| %s | %s | %s |" % (k, m[k][1], m[k][0]))
+    lines += ["", "## instruction mix (warp-instructions executed)", "", "```", mix.strip(), "```", "",
+              "## stall samples by CUDA source line", "", "```", by_line.strip(), "```"]
+    open(os.path.join(out_dir, "%s.md" % name), "w").write("\n".join(lines) + "\n")
+
+
+kernel_summary(eval_rep, "eval_kernel<4,13,8,7,4> (K3+K4), bench workload, %s" % tag,
+               "eval_kernelILi4ELi13ELi8ELi7", "%s_eval_kernel" % tag)
+if pp_rep:
+    kernel_summary(pp_rep, "pp_batch_kernel (K1), 10^5 poses x 1999 segments, %s" % tag, "pp_batch_kernel",
+                   "%s_pp_batch_kernel" % tag)
+print("written to", out_dir)
