@@ -254,7 +254,7 @@ int pick_warps_per_cta(int n_cand, int M) {
 }
 
 size_t eval_smem_bytes(int nseg_pad, int warps, int M) {
-    size_t b = (size_t)(nseg_pad + EVAL_SEG_PAD) * (sizeof(float4) + sizeof(float2));
+    size_t b = (size_t)(nseg_pad + EVAL_SEG_PAD) * (2 * sizeof(float4));
     b += (size_t)warps * M * sizeof(float2);
     b += (size_t)((M + 3) & ~3) * sizeof(float);
     b += F1L_MAX_OPP * sizeof(float4);
@@ -1175,6 +1175,38 @@ int f1l_measure_peaks(f1l_handle h, double* fp32_tflops, double* mufu_gops) {
     if (mufu_gops)
         *mufu_gops = (double)PEAK_CHAINS * iters * blocks * threads / (ms * 1e-3) / 1e9;
     CK(cudaGetLastError());
+    return F1L_OK;
+}
+
+// extended pipe probes: out[0] FFMA TFLOP/s, out[1] MUFU Gop/s, out[2] packed FFMA2 TFLOP/s,
+// out[3] warp-instructions per clock per SM of an 8 FFMA + 8 FMNMX mix (shared issue slot probe)
+int f1l_measure_peaks_ex(f1l_handle h, double* out, int n) {
+    if (!h || !out || n < 4) return F1L_ERR_INVALID_ARG;
+    int r = f1l_measure_peaks(h, &out[0], &out[1]);
+    if (r != F1L_OK) return r;
+    cudaStream_t st = h->stream;
+    const int blocks = h->sm_count * 8, threads = 256, iters = 4096;
+    float ms = 0.f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(h->ev[0], st));
+        ffma2_peak_kernel<<<blocks, threads, 0, st>>>((float*)h->m_o0.p, iters, 1.0001f, 0.5f);
+        CK(cudaEventRecord(h->ev[1], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    }
+    out[2] = 4.0 * PEAK_CHAINS * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    for (int rep = 0; rep < 3; ++rep) {
+        CK(cudaEventRecord(h->ev[0], st));
+        mixed_peak_kernel<<<blocks, threads, 0, st>>>((float*)h->m_o0.p, iters, 1.0001f, 0.5f);
+        CK(cudaEventRecord(h->ev[1], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+    }
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+    const double warp_inst = 16.0 * iters * (double)blocks * threads / 32.0;
+    out[3] = warp_inst / (ms * 1e-3) / ((double)khz * 1e3) / h->sm_count;
+    h->launches += 6;
     return F1L_OK;
 }
 

@@ -479,9 +479,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
     __shared__ int s_gi[4];
     const int M = a.ep.M;
     const int ntab = a.nseg_pad + EVAL_SEG_PAD;
-    float4* sA = reinterpret_cast<float4*>(ev_smem);
-    float2* sB = reinterpret_cast<float2*>(sA + ntab);
-    float4* sopp = reinterpret_cast<float4*>(sB + ntab);                     // [F1L_MAX_OPP]
+    // window table, two float4 per segment: T0 = (ux, uy, -uy, 1/len), T1 = (-a.u, -a.n, -len, 0)
+    float4* sT = reinterpret_cast<float4*>(ev_smem);
+    float4* sopp = sT + 2 * (size_t)ntab;                                    // [F1L_MAX_OPP]
     float* sprev = reinterpret_cast<float*>(sopp + F1L_MAX_OPP);             // [M] (padded to 4)
     float2* slab_all = reinterpret_cast<float2*>(sprev + ((M + 3) & ~3));    // [NW][M]
 
@@ -501,8 +501,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
         const float cth = q->cth, sth = q->sth;
         const int seg0 = q->seg0, nseg = q->nseg, ns = a.tr.n - 1;
         for (int k = tid; k < ntab; k += NW * 32) {
-            float4 A = make_float4(1.0f, 0.0f, 1e15f, 1e15f);  // padding: far away, finite
-            float2 Bv = make_float2(1.0f, 1.0f);
+            float4 T0 = make_float4(1.0f, 0.0f, -0.0f, 1.0f);      // padding: far away, finite
+            float4 T1 = make_float4(-1e15f, -1e15f, -1.0f, 0.0f);
             if (k < nseg) {
                 int sg = seg0 + k;
                 if (sg >= ns) sg -= ns;
@@ -514,11 +514,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 const float l2 = fmaf(dx, dx, dy * dy);
                 const float il = rsqrtf(l2);
                 const float ux = dx * il, uy = dy * il;
-                A = make_float4(ux, uy, fmaf(avx, ux, avy * uy), fmaf(avy, ux, -avx * uy));
-                Bv = make_float2(l2 * il, il);
+                T0 = make_float4(ux, uy, -uy, il);
+                T1 = make_float4(-fmaf(avx, ux, avy * uy), -fmaf(avy, ux, -avx * uy), -(l2 * il), 0.0f);
             }
-            sA[k] = A;
-            sB[k] = Bv;
+            sT[2 * k] = T0;
+            sT[2 * k + 1] = T1;
         }
         if (a.prev_theta)
             for (int i = tid; i < M; i += NW * 32) sprev[i] = a.prev_theta[i];
@@ -705,45 +705,75 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             //      segment, the next segment's table entry already in flight.
             __syncwarp();
             {
+                // samples are processed in pairs with packed FP32x2 instructions (FFMA2 / FMUL2,
+                // sm_100): the same FMA-pipe work in half the issue slots -- the loop is issue-bound
+                // otherwise (1 warp-instruction per clock per scheduler, 9 per sample x segment).
+                constexpr int SP = S / 2;
+                constexpr bool ODD = (S & 1) != 0;
                 const int sgi = lane / GG, ggi = lane - sgi * GG;
-                float sx[S], sy[S], bd[S];
+                float2 sx2[SP], sy2[SP], bd2[SP];
+                float sxl = 0.0f, syl = 0.0f, bdl = CUDART_INF_F;
 #pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    const int i = j * SG + sgi;
-                    const float2 p = slab[i < M ? i : M - 1];
-                    sx[j] = p.x; sy[j] = p.y; bd[j] = CUDART_INF_F;
+                for (int j = 0; j < SP; ++j) {
+                    const int ia = (2 * j) * SG + sgi, ib = (2 * j + 1) * SG + sgi;
+                    const float2 pa = slab[ia < M ? ia : M - 1], pb = slab[ib < M ? ib : M - 1];
+                    sx2[j] = make_float2(pa.x, pb.x);
+                    sy2[j] = make_float2(pa.y, pb.y);
+                    bd2[j] = make_float2(CUDART_INF_F, CUDART_INF_F);
+                }
+                if (ODD) {
+                    const int il = (S - 1) * SG + sgi;
+                    const float2 pl = slab[il < M ? il : M - 1];
+                    sxl = pl.x; syl = pl.y;
                 }
                 const int nq = a.nseg_pad;
-                float4 A = sA[ggi];
-                float2 Bv = sB[ggi];
+                float4 T0 = sT[2 * ggi], T1 = sT[2 * ggi + 1];
 #pragma unroll kSegUnroll
                 for (int k = ggi; k < nq; k += GG) {
-                    const float4 An = sA[k + GG];   // table has EVAL_SEG_PAD entries of slack
-                    const float2 Bn = sB[k + GG];
+                    const float4 N0 = sT[2 * (k + GG)];       // EVAL_SEG_PAD entries of slack
+                    const float4 N1 = sT[2 * (k + GG) + 1];
+                    const float2 ux = make_float2(T0.x, T0.x), uy = make_float2(T0.y, T0.y);
+                    const float2 nuy = make_float2(T0.z, T0.z), nc = make_float2(T1.x, T1.x);
+                    const float2 ne = make_float2(T1.y, T1.y), nlen = make_float2(T1.z, T1.z);
 #pragma unroll
-                    for (int j = 0; j < S; ++j) {
-                        const float qq = fmaf(sx[j], A.x, fmaf(sy[j], A.y, -A.z));
-                        const float nn = fmaf(sy[j], A.x, fmaf(-sx[j], A.y, -A.w));
-                        const float t = __saturatef(qq * Bv.y);
-                        const float e = fmaf(-t, Bv.x, qq);
-                        bd[j] = fminf(bd[j], fmaf(e, e, nn * nn));
+                    for (int j = 0; j < SP; ++j) {
+                        const float2 q2 = __ffma2_rn(sx2[j], ux, __ffma2_rn(sy2[j], uy, nc));
+                        const float2 n2 = __ffma2_rn(sy2[j], ux, __ffma2_rn(sx2[j], nuy, ne));
+                        const float2 t2 = make_float2(__saturatef(q2.x * T0.w), __saturatef(q2.y * T0.w));
+                        const float2 e2 = __ffma2_rn(t2, nlen, q2);
+                        const float2 d2 = __ffma2_rn(e2, e2, __fmul2_rn(n2, n2));
+                        bd2[j].x = fminf(bd2[j].x, d2.x);
+                        bd2[j].y = fminf(bd2[j].y, d2.y);
                     }
-                    A = An;
-                    Bv = Bn;
+                    if (ODD) {
+                        const float qq = fmaf(sxl, T0.x, fmaf(syl, T0.y, T1.x));
+                        const float nn = fmaf(syl, T0.x, fmaf(sxl, T0.z, T1.y));
+                        const float t = __saturatef(qq * T0.w);
+                        const float e = fmaf(t, T1.z, qq);
+                        bdl = fminf(bdl, fmaf(e, e, nn * nn));
+                    }
+                    T0 = N0;
+                    T1 = N1;
                 }
 #pragma unroll
                 for (int o = 1; o < GG; o <<= 1) {
 #pragma unroll
-                    for (int j = 0; j < S; ++j) bd[j] = fminf(bd[j], __shfl_xor_sync(F1L_FULL, bd[j], o));
+                    for (int j = 0; j < SP; ++j) {
+                        bd2[j].x = fminf(bd2[j].x, __shfl_xor_sync(F1L_FULL, bd2[j].x, o));
+                        bd2[j].y = fminf(bd2[j].y, __shfl_xor_sync(F1L_FULL, bd2[j].y, o));
+                    }
+                    if (ODD) bdl = fminf(bdl, __shfl_xor_sync(F1L_FULL, bdl, o));
                 }
                 // every lane of a sample group now holds the same S minima: sum them on all
                 // lanes (branch-free) and divide by the group size
                 float dsum = 0.0f;
 #pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    const int i = j * SG + sgi;
-                    dsum += (i < M) ? fast_sqrt(bd[j]) : 0.0f;
+                for (int j = 0; j < SP; ++j) {
+                    const int ia = (2 * j) * SG + sgi, ib = (2 * j + 1) * SG + sgi;
+                    dsum += (ia < M) ? fast_sqrt(bd2[j].x) : 0.0f;
+                    dsum += (ib < M) ? fast_sqrt(bd2[j].y) : 0.0f;
                 }
+                if (ODD) dsum += ((S - 1) * SG + sgi < M) ? fast_sqrt(bdl) : 0.0f;
                 t_dev = warp_sum(dsum) * (1.0f / (float)GG) / (float)M;
             }
 

@@ -353,6 +353,13 @@ class Engine:
         self._ck(self._L.f1l_measure_peaks(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def measure_peaks_ex(self):
+        """dict: ffma_tflops, mufu_gops, ffma2_tflops (packed fma.rn.f32x2), mixed_ipc_per_sm"""
+        out = np.zeros(4)
+        self._ck(self._L.f1l_measure_peaks_ex(self._h, _ptr(out, _dp), 4))
+        return dict(ffma_tflops=out[0], mufu_gops=out[1], ffma2_tflops=out[2],
+                    mixed_ipc_per_sm=out[3])
+
     def debug_query_ctx(self):
         f = np.zeros(8 + 4 * MAX_OPP, np.float32)
         i = np.zeros(6, np.int32)

@@ -243,6 +243,9 @@ int f1l_last_kernel_ms(f1l_handle h, float* sample_ms, float* eval_ms, float* se
 /* FP32 FMA / MUFU pipe peak microbenchmarks (roofline denominators):
  * returns achieved TFLOP/s (FMA = 2 FLOP) and MUFU Gop/s on the handle's device. */
 int f1l_measure_peaks(f1l_handle h, double* fp32_tflops, double* mufu_gops);
+/* Extended probes: out[0] FFMA TFLOP/s, out[1] MUFU Gop/s, out[2] packed FFMA2 (fma.rn.f32x2)
+ * TFLOP/s, out[3] warp-instructions per clock per SM of an FFMA + FMNMX mix (n >= 4). */
+int f1l_measure_peaks_ex(f1l_handle h, double* out, int n);
 
 /* Debug / test hook: the float32 per-query constants of the last f1l_plan* call, for
  * teacher-forced collision checks.  out_f[72]: cos, sin of the pose heading; grid transform A00
