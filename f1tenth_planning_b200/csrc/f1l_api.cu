@@ -254,8 +254,9 @@ int pick_warps_per_cta(int n_cand, int M) {
 }
 
 size_t eval_smem_bytes(int nseg_pad, int warps, int M) {
+    const EvalShape sh = eval_shape(M);
     size_t b = (size_t)(nseg_pad + EVAL_SEG_PAD) * (2 * sizeof(float4));
-    b += (size_t)warps * M * sizeof(float2);
+    b += (size_t)warps * 2 * (((sh.s + 1) / 2) * sh.sg * 2) * sizeof(float);   // pair-layout slabs
     b += (size_t)((M + 3) & ~3) * sizeof(float);
     b += F1L_MAX_OPP * sizeof(float4);
     return b;

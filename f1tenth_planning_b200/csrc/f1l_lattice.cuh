@@ -461,6 +461,29 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     return r;
 }
 
+// packed FP32x2 helpers (sm_100 FFMA2 / FMUL2).  Values live in 64-bit registers so that ptxas
+// keeps each pair in an aligned register pair across the loop (float2 halves are independent
+// 32-bit values to the allocator and get MOVed together before every use).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 #ifndef EVAL_SEG_UNROLL
 #define EVAL_SEG_UNROLL 2
 #endif
@@ -483,7 +506,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
     float4* sT = reinterpret_cast<float4*>(ev_smem);
     float4* sopp = sT + 2 * (size_t)ntab;                                    // [F1L_MAX_OPP]
     float* sprev = reinterpret_cast<float*>(sopp + F1L_MAX_OPP);             // [M] (padded to 4)
-    float2* slab_all = reinterpret_cast<float2*>(sprev + ((M + 3) & ~3));    // [NW][M]
+    // per-warp sample slab in the pair layout of the deviation pass: element (j, sg, half) holds
+    // sample (2j + half) * SG + sg, so that one 64-bit load yields a packed pair of samples
+    constexpr int SROWS = (S + 1) / 2;
+    constexpr int SLAB = SROWS * SG * 2;                                     // floats per coordinate
+    float* slab_all = sprev + ((M + 3) & ~3);                                // [NW][2][SLAB]
 
     int s, cta;
     if (a.ctas_per_scn == 1) { s = blockIdx.x; cta = 0; }
@@ -534,7 +561,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
     }
     __syncthreads();
 
-    float2* slab = slab_all + (size_t)wid * M;
+    float* slab_x = slab_all + (size_t)wid * (2 * SLAB);
+    float* slab_y = slab_x + SLAB;
+    for (int i = M + lane; i < S * SG; i += 32) {   // unused slots of the last rows: finite dummies
+        const int r = i / SG, g = i - r * SG;
+        slab_x[((r >> 1) * SG + g) * 2 + (r & 1)] = 0.0f;
+        slab_y[((r >> 1) * SG + g) * 2 + (r & 1)] = 0.0f;
+    }
 
     for (int c = cb + wid; c < ce;) {
         // ---- goal, seed, Newton ----
@@ -581,7 +614,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 const float ak = fabsf(kp[j]);
                 maxk = fmaxf(maxk, ak);
                 sumk += ak;
-                slab[i] = make_float2(x[j], y[j]);
+                {
+                    const int r = i / SG, g = i - r * SG;
+                    const int at = ((r >> 1) * SG + g) * 2 + (r & 1);
+                    slab_x[at] = x[j];
+                    slab_y[at] = y[j];
+                }
                 if (i == M - 1) { ex = x[j]; ey = y[j]; eth = th[j]; }
             }
         }
@@ -711,20 +749,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 constexpr int SP = S / 2;
                 constexpr bool ODD = (S & 1) != 0;
                 const int sgi = lane / GG, ggi = lane - sgi * GG;
-                float2 sx2[SP], sy2[SP], bd2[SP];
+                f32x2 sx2[SP], sy2[SP];
+                float bdx[SP], bdy[SP];
                 float sxl = 0.0f, syl = 0.0f, bdl = CUDART_INF_F;
 #pragma unroll
                 for (int j = 0; j < SP; ++j) {
-                    const int ia = (2 * j) * SG + sgi, ib = (2 * j + 1) * SG + sgi;
-                    const float2 pa = slab[ia < M ? ia : M - 1], pb = slab[ib < M ? ib : M - 1];
-                    sx2[j] = make_float2(pa.x, pb.x);
-                    sy2[j] = make_float2(pa.y, pb.y);
-                    bd2[j] = make_float2(CUDART_INF_F, CUDART_INF_F);
+                    sx2[j] = *reinterpret_cast<const f32x2*>(slab_x + (j * SG + sgi) * 2);
+                    sy2[j] = *reinterpret_cast<const f32x2*>(slab_y + (j * SG + sgi) * 2);
+                    bdx[j] = CUDART_INF_F;
+                    bdy[j] = CUDART_INF_F;
                 }
                 if (ODD) {
-                    const int il = (S - 1) * SG + sgi;
-                    const float2 pl = slab[il < M ? il : M - 1];
-                    sxl = pl.x; syl = pl.y;
+                    sxl = slab_x[(SP * SG + sgi) * 2];
+                    syl = slab_y[(SP * SG + sgi) * 2];
                 }
                 const int nq = a.nseg_pad;
                 float4 T0 = sT[2 * ggi], T1 = sT[2 * ggi + 1];
@@ -732,18 +769,22 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 for (int k = ggi; k < nq; k += GG) {
                     const float4 N0 = sT[2 * (k + GG)];       // EVAL_SEG_PAD entries of slack
                     const float4 N1 = sT[2 * (k + GG) + 1];
-                    const float2 ux = make_float2(T0.x, T0.x), uy = make_float2(T0.y, T0.y);
-                    const float2 nuy = make_float2(T0.z, T0.z), nc = make_float2(T1.x, T1.x);
-                    const float2 ne = make_float2(T1.y, T1.y), nlen = make_float2(T1.z, T1.z);
+                    const f32x2 ux = pack2(T0.x, T0.x), uy = pack2(T0.y, T0.y);
+                    const f32x2 nuy = pack2(T0.z, T0.z), nc = pack2(T1.x, T1.x);
+                    const f32x2 ne = pack2(T1.y, T1.y), nlen = pack2(T1.z, T1.z);
 #pragma unroll
                     for (int j = 0; j < SP; ++j) {
-                        const float2 q2 = __ffma2_rn(sx2[j], ux, __ffma2_rn(sy2[j], uy, nc));
-                        const float2 n2 = __ffma2_rn(sy2[j], ux, __ffma2_rn(sx2[j], nuy, ne));
-                        const float2 t2 = make_float2(__saturatef(q2.x * T0.w), __saturatef(q2.y * T0.w));
-                        const float2 e2 = __ffma2_rn(t2, nlen, q2);
-                        const float2 d2 = __ffma2_rn(e2, e2, __fmul2_rn(n2, n2));
-                        bd2[j].x = fminf(bd2[j].x, d2.x);
-                        bd2[j].y = fminf(bd2[j].y, d2.y);
+                        const f32x2 q2 = ffma2(sx2[j], ux, ffma2(sy2[j], uy, nc));
+                        const f32x2 n2 = ffma2(sy2[j], ux, ffma2(sx2[j], nuy, ne));
+                        float qa, qb;
+                        unpack2(q2, qa, qb);
+                        const f32x2 t2 = pack2(__saturatef(qa * T0.w), __saturatef(qb * T0.w));
+                        const f32x2 e2 = ffma2(t2, nlen, q2);
+                        const f32x2 d2 = ffma2(e2, e2, fmul2(n2, n2));
+                        float da, db;
+                        unpack2(d2, da, db);
+                        bdx[j] = fminf(bdx[j], da);
+                        bdy[j] = fminf(bdy[j], db);
                     }
                     if (ODD) {
                         const float qq = fmaf(sxl, T0.x, fmaf(syl, T0.y, T1.x));
@@ -759,8 +800,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 for (int o = 1; o < GG; o <<= 1) {
 #pragma unroll
                     for (int j = 0; j < SP; ++j) {
-                        bd2[j].x = fminf(bd2[j].x, __shfl_xor_sync(F1L_FULL, bd2[j].x, o));
-                        bd2[j].y = fminf(bd2[j].y, __shfl_xor_sync(F1L_FULL, bd2[j].y, o));
+                        bdx[j] = fminf(bdx[j], __shfl_xor_sync(F1L_FULL, bdx[j], o));
+                        bdy[j] = fminf(bdy[j], __shfl_xor_sync(F1L_FULL, bdy[j], o));
                     }
                     if (ODD) bdl = fminf(bdl, __shfl_xor_sync(F1L_FULL, bdl, o));
                 }
@@ -770,8 +811,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
 #pragma unroll
                 for (int j = 0; j < SP; ++j) {
                     const int ia = (2 * j) * SG + sgi, ib = (2 * j + 1) * SG + sgi;
-                    dsum += (ia < M) ? fast_sqrt(bd2[j].x) : 0.0f;
-                    dsum += (ib < M) ? fast_sqrt(bd2[j].y) : 0.0f;
+                    dsum += (ia < M) ? fast_sqrt(bdx[j]) : 0.0f;
+                    dsum += (ib < M) ? fast_sqrt(bdy[j]) : 0.0f;
                 }
                 if (ODD) dsum += ((S - 1) * SG + sgi < M) ? fast_sqrt(bdl) : 0.0f;
                 t_dev = warp_sum(dsum) * (1.0f / (float)GG) / (float)M;
