@@ -1,6 +1,7 @@
 // f1l_api.cu -- C-ABI (include/f1l.h) over the sm_100a kernels.  No torch types, no exceptions
 // across the boundary; every launch goes on the handle's (or the caller's) stream.
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -61,7 +62,7 @@ struct f1l_ctx {
     DevBuf prev;
     int has_prev = 0, prev_m = 0;
     // single-query device buffers
-    DevBuf q_in, q_goals, q_ctx, q_centres, q_best, q_idx, q_cost, q_status, q_ss, q_traj, q_costs,
+    DevBuf q_res, q_in, q_goals, q_ctx, q_centres, q_best, q_idx, q_cost, q_status, q_ss, q_traj, q_costs,
         q_terms, q_flags, q_gout, q_params, q_states, q_headings;
     // pinned staging for the single query
     void* h_in = nullptr;   // pose + opponents
@@ -249,8 +250,37 @@ generate_fn generate_entry(int M) {
     return generate_kernel<8>;
 }
 
-int pick_warps_per_cta(int n_cand, int M) {
-    return (n_cand % 7 == 0 && n_cand <= 56 && M <= 128) ? 7 : 8;
+// CTA plan of the eval kernel: NW warps per CTA, `chunk` candidates per CTA.  NW = 7 runs four
+// resident CTAs per SM (72 registers, 28 warps), NW = 8 three (80 registers, 24 warps); besides
+// exact divisibility (no idle warp in the last round of a CTA) the choice minimises the number
+// of CTA waves, which is what decides the latency of one dense query.
+struct CtaPlan {
+    int nw, chunk, ctas_per_scn;
+};
+
+CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count) {
+    CtaPlan best{8, 8, 1};
+    double best_cost = 1e300;
+    for (int nw = 7; nw <= 8; ++nw) {
+        if (nw == 7 && M > 128) continue;   // the 7-warp build of the M = 200 shape spills
+        const int resident = (nw == 7 ? 4 : 3) * sm_count;
+        // enough CTAs for ~8 waves; batches of small queries get one CTA per scenario
+        long long per = (8LL * resident + S - 1) / S;
+        const long long max_per = (n_cand + nw - 1) / nw;
+        if (per > max_per) per = max_per;
+        if (per < 1) per = 1;
+        int chunk = (int)((n_cand + per - 1) / per);
+        chunk = ((chunk + nw - 1) / nw) * nw;
+        const int cps = (n_cand + chunk - 1) / chunk;
+        const double ctas = (double)S * cps;
+        const double waves = std::ceil(ctas / resident);
+        const double rounds = std::ceil((double)chunk / nw);        // candidates per warp
+        // time ~ waves x rounds, in units of one candidate per warp; slightly favour the
+        // configuration with more resident warps on ties
+        const double cost = waves * rounds * (nw == 7 ? 0.999 : 1.0);
+        if (cost < best_cost) { best_cost = cost; best = {nw, chunk, cps}; }
+    }
+    return best;
 }
 
 size_t eval_smem_bytes(int nseg_pad, int warps, int M) {
@@ -298,7 +328,8 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     if (nseg <= 0 || nseg > nsegs) nseg = nsegs;
     const int nseg_pad = (nseg + 31) & ~31;
     const int n_cand = c_end - c_begin;
-    const int wpc = pick_warps_per_cta(n_cand, M);
+    const CtaPlan cp = plan_ctas(n_cand, S, M, h->sm_count);
+    const int wpc = cp.nw;
     const size_t smem = eval_smem_bytes(nseg_pad, wpc, M);
     if (smem > 226 * 1024) return F1L_ERR_TOO_LARGE;
 
@@ -333,7 +364,14 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
             sa, near_i, near4, S);
         h->launches += 1;
     } else {
-        sample_kernel<<<S, SAMPLE_THREADS, 0, stream>>>(sa);
+        // a lone dense query: one warp per ~2 lookahead rows; small batches: 8 warps each
+        int st_threads = SAMPLE_THREADS;
+        if (S <= 4 && sa.nL > 8) {
+            st_threads = ((sa.nL + 1) / 2) * 32;
+            if (st_threads > SAMPLE_THREADS_MAX) st_threads = SAMPLE_THREADS_MAX;
+            if (st_threads < SAMPLE_THREADS) st_threads = SAMPLE_THREADS;
+        }
+        sample_kernel<<<S, st_threads, 0, stream>>>(sa);
     }
     if (time_it) cudaEventRecord(ev[1], stream);
 
@@ -352,19 +390,8 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     ea.C = C;
     ea.c_begin = c_begin;
     ea.c_end = c_end;
-    {
-        // enough CTAs for ~8 waves (tail < 1/8 of a dense single query); a CTA works through
-        // `chunk` candidates, so batches of small queries get one CTA per scenario
-        const long long target = 8LL * h->sm_count * 3;
-        long long per = (target + S - 1) / S;
-        const long long max_per = (n_cand + wpc - 1) / wpc;
-        if (per > max_per) per = max_per;
-        if (per < 1) per = 1;
-        int chunk = (int)((n_cand + per - 1) / per);
-        chunk = ((chunk + wpc - 1) / wpc) * wpc;
-        ea.chunk = chunk;
-        ea.ctas_per_scn = (n_cand + chunk - 1) / chunk;
-    }
+    ea.chunk = cp.chunk;
+    ea.ctas_per_scn = cp.ctas_per_scn;
     ea.inv_nW = 1.0f / (float)(h->nW > 0 ? h->nW : 1);
     ea.nseg_pad = nseg_pad;
     ea.costs = o.costs;
@@ -413,11 +440,17 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     return F1L_OK;
 }
 
+// device / pinned-host result block of a single query: header then the best trajectory, so
+// that one D2H copy brings everything a plain plan() call returns
 struct QHeader {
-    double steer, speed;
-    int32_t best_idx, no_feasible, tracker_found, pad;
-    float best_cost, pad2;
+    double steer, speed;                 // +0
+    int32_t best_idx;                    // +16
+    int32_t no_feasible, tracker_found;  // +20
+    int32_t pad;                         // +28
+    float best_cost;                     // +32
+    float pad2[3];                       // -> 48 bytes, keeps the float4 trajectory 16-aligned
 };
+static_assert(sizeof(QHeader) == 48, "QHeader layout");
 
 }  // namespace
 
@@ -606,7 +639,7 @@ int f1l_destroy(f1l_handle h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->xy, &h->v, &h->psi, &h->kappa, &h->segA, &h->segB, &h->blk, &h->grid, &h->clear, &h->clear_tmp,
-                      &h->lut, &h->lookaheads, &h->widths, &h->prev, &h->q_in, &h->q_goals,
+                      &h->lut, &h->lookaheads, &h->widths, &h->prev, &h->q_res, &h->q_in, &h->q_goals,
                       &h->q_ctx, &h->q_centres, &h->q_best, &h->q_idx, &h->q_cost, &h->q_status,
                       &h->q_ss, &h->q_traj, &h->q_costs, &h->q_terms, &h->q_flags, &h->q_gout,
                       &h->q_params, &h->q_states, &h->q_headings, &h->b_ctx, &h->b_centres,
@@ -834,12 +867,14 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
         d_goals = (const float4*)h->q_goals.p;
     }
 
+    ENS(h->q_res, sizeof(QHeader) + F1L_MAX_M * sizeof(float4));
+    char* dres = (char*)h->q_res.p;
     BatchOut o;
-    o.best_idx = (int32_t*)h->q_idx.p;
-    o.best_cost = (float*)h->q_cost.p;
-    o.status = (int32_t*)h->q_status.p;
-    o.steer_speed = (double*)h->q_ss.p;
-    o.best_traj = (float4*)h->q_traj.p;
+    o.steer_speed = (double*)(dres + offsetof(QHeader, steer));
+    o.best_idx = (int32_t*)(dres + offsetof(QHeader, best_idx));
+    o.status = (int32_t*)(dres + offsetof(QHeader, no_feasible));
+    o.best_cost = (float*)(dres + offsetof(QHeader, best_cost));
+    o.best_traj = (float4*)(dres + sizeof(QHeader));
     o.costs = (float*)h->q_costs.p;
     o.terms = out->terms ? (float*)h->q_terms.p : nullptr;
     o.flags = out->flags ? (uint8_t*)h->q_flags.p : nullptr;
@@ -867,11 +902,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     // results -> pinned staging -> caller
     QHeader* hd = (QHeader*)h->h_out;
     float* htraj = (float*)((char*)h->h_out + sizeof(QHeader));
-    CK(cudaMemcpyAsync(&hd->steer, h->q_ss.p, 16, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&hd->best_idx, h->q_idx.p, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&hd->no_feasible, h->q_status.p, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&hd->best_cost, h->q_cost.p, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(htraj, h->q_traj.p, (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hd, h->q_res.p, sizeof(QHeader) + (size_t)M * 16, cudaMemcpyDeviceToHost, st));
     if (out->costs) CK(cudaMemcpyAsync(out->costs, h->q_costs.p, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
     if (out->terms) CK(cudaMemcpyAsync(out->terms, h->q_terms.p, (size_t)C * F1L_N_TERMS * 4, cudaMemcpyDeviceToHost, st));
     if (out->flags) CK(cudaMemcpyAsync(out->flags, h->q_flags.p, (size_t)C, cudaMemcpyDeviceToHost, st));

@@ -281,7 +281,8 @@ __device__ __forceinline__ void candidate_goal(const Centre* __restrict__ centre
 // ---------------------------------------------------------------------------------------------
 // K2: sampler
 // ---------------------------------------------------------------------------------------------
-#define SAMPLE_THREADS 256
+#define SAMPLE_THREADS 256        // batches of a few queries
+#define SAMPLE_THREADS_MAX 1024   // a single query gets one warp per ~2 lookahead rows
 
 __device__ __forceinline__ double wrap_to_pi64(double a) {
     const double two_pi = 6.283185307179586476925286766559;
@@ -367,19 +368,20 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
 
 // single / few queries: one CTA per scenario; nearest_point (utils.py:37-67) as a CTA-parallel
 // FP32 scan of the block-local line form + float64 re-evaluation of the winner's neighbours.
-__global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
-    __shared__ float s_d[SAMPLE_THREADS / 32];
-    __shared__ int s_i[SAMPLE_THREADS / 32];
+__global__ void __launch_bounds__(SAMPLE_THREADS_MAX) sample_kernel(SampleArgs a) {
+    __shared__ float s_d[SAMPLE_THREADS_MAX / 32];
+    __shared__ int s_i[SAMPLE_THREADS_MAX / 32];
     __shared__ double s_t;
     __shared__ int s_best;
     const int s = blockIdx.x;
+    const int nthreads = blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double px = a.poses[4 * (size_t)s], py = a.poses[4 * (size_t)s + 1];
     const int nseg = a.tr.n - 1;
 
     float bd = CUDART_INF_F;
     int bi = 0x7fffffff;
-    for (int k = tid; k < nseg; k += SAMPLE_THREADS) {
+    for (int k = tid; k < nseg; k += nthreads) {
         const double2 o = a.tr.blk_origin[k >> 5];
         const float prx = (float)(px - o.x), pry = (float)(py - o.y);
         const float4 A = __ldg(a.tr.segA + k);
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
     if (lane == 0) { s_d[wid] = bd; s_i[wid] = bi; }
     __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < SAMPLE_THREADS / 32; ++w)
+        for (int w = 1; w < (nthreads >> 5); ++w)
             if (s_d[w] < bd || (s_d[w] == bd && s_i[w] < bi)) { bd = s_d[w]; bi = s_i[w]; }
         if (bi == 0x7fffffff) bi = 0;
         const Nearest64 nr = refine_nearest64(a.tr.xy, nseg, px, py, bi);
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(SampleArgs a) {
         s_t = nr.t;
     }
     __syncthreads();
-    sample_body(a, s, tid, SAMPLE_THREADS, s_best, s_t);
+    sample_body(a, s, tid, nthreads, s_best, s_t);
 }
 
 // batches: the nearest-point search of all scenarios is done by pp_batch_kernel (thread per pose,
