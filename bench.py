@@ -132,10 +132,19 @@ def work_flops(flags, M, W, n_opp_mean):
 
 
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """all host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the oracle's
+    OpenMP loops take an explicit num_threads, so that default does not apply)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_reference_rate(track, grid, la, wd, poses, opp, n_opp, seconds, threads=None):
     """oracle port on the host cores: (cand/s, sample size, threads)"""
     from oracle import c_oracle as co
-    threads = threads or co.max_threads()
+    threads = threads or host_threads()
     world = co.World_(track, la, wd, grid=grid[0], grid_origin=grid[1], grid_res=grid[2])
     cfg = co.default_config(**PLAN_CFG)
     C = world.n_candidates
@@ -158,7 +167,7 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import c_oracle as co
-    threads = co.max_threads()
+    threads = host_threads()
     track, grid, la, wd, poses, opp, n_opp = workload(0, 20000)
     world = co.World_(track, la, wd, grid=grid[0], grid_origin=grid[1], grid_res=grid[2])
     cfg = co.default_config(**PLAN_CFG)
@@ -287,6 +296,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world_size > 1:
+        # NCCL prints its version banner on stdout at VERSION level; keep stdout to the JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     S = args.scenarios
