@@ -358,7 +358,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
         po.lookahead_i = nullptr;
         po.actuation = nullptr;
         po.status = nullptr;
-        pp_batch_kernel<<<(S + PP_POSES_PER_CTA - 1) / PP_POSES_PER_CTA, PP_THREADS, PP_SMEM_BYTES, stream>>>(
+        pp_batch_kernel<<<(S + PP_THREADS - 1) / PP_THREADS, PP_THREADS, PP_SMEM_BYTES, stream>>>(
             sa.tr, poses, 4, S, -1.0, 0.33, 0.0, po);
         sample_warp_kernel<<<(S + SAMPLE_WARPS - 1) / SAMPLE_WARPS, SAMPLE_WARPS * 32, 0, stream>>>(
             sa, near_i, near4, S);
@@ -1081,7 +1081,7 @@ int f1l_pure_pursuit_batch_dev(f1l_handle h, const double* poses_dev, int n_pose
     o.lookahead_i = lookahead_i_dev;
     o.actuation = actuation_dev;
     o.status = status_dev;
-    const int blocks = (n_poses + PP_POSES_PER_CTA - 1) / PP_POSES_PER_CTA;
+    const int blocks = (n_poses + PP_THREADS - 1) / PP_THREADS;
     pp_batch_kernel<<<blocks, PP_THREADS, PP_SMEM_BYTES, (cudaStream_t)stream>>>(
         track_view(h), poses_dev, 3, n_poses, L, h->cfg.wheelbase, h->cfg.max_reacquire, o);
     h->launches += 1;
