@@ -420,7 +420,7 @@ def run_ours(args):
             "mufu_peak_gops": mufu_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one eval_kernel launch of this workload
             # (ncu --set full; profiles/r1_eval_kernel.md) -- bench.py cannot run under ncu itself
-            "traffic": 52218368 if S == S_PER_GPU else None,
+            "traffic": 50935808 if S == S_PER_GPU else None,
             "traffic_source": "profiles/r1_eval_kernel.md",
             "hbm": {"algorithmic_bytes_per_step": hbm_bytes,
                     "achieved_gbs": hbm_bytes / (ms_total / args.steps * 1e-3) / 1e9},

@@ -13,6 +13,7 @@ _LAZY = {
     "LatticePlanner": ("lattice_planner", "LatticePlanner"),
     "sample_lookahead_square": ("lattice_planner", "sample_lookahead_square"),
     "PurePursuitPlanner": ("pure_pursuit", "PurePursuitPlanner"),
+    "StanleyPlanner": ("stanley", "StanleyPlanner"),
     "Engine": ("engine", "Engine"),
     "F1LError": ("_lib", "F1LError"),
     "nearest_point": ("utils", "nearest_point"),

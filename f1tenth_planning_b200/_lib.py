@@ -77,6 +77,8 @@ SIGNATURES = {
                                              _vp, _vp, _vp]),
     "f1l_pure_pursuit_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp,
                                          _vp]),
+    "f1l_front_axle_batch_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp]),
+    "f1l_front_axle_batch": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.c_double, _vp, _vp]),
     "f1l_intersect_point_batch": (C.c_int, [_vp, _dp, _dp, C.c_int, C.c_double, C.c_int, _dp,
                                             _ip]),
     "f1l_get_actuation_batch": (C.c_int, [_vp, _dp, C.c_int, C.c_double, _dp]),

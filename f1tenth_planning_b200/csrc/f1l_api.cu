@@ -358,8 +358,9 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
         po.lookahead_i = nullptr;
         po.actuation = nullptr;
         po.status = nullptr;
+        po.front = nullptr;
         pp_batch_kernel<<<(S + PP_THREADS - 1) / PP_THREADS, PP_THREADS, PP_SMEM_BYTES, stream>>>(
-            sa.tr, poses, 4, S, -1.0, 0.33, 0.0, po);
+            sa.tr, poses, 4, S, -1.0, 0.33, 0.0, 0, 0.0, po);
         sample_warp_kernel<<<(S + SAMPLE_WARPS - 1) / SAMPLE_WARPS, SAMPLE_WARPS * 32, 0, stream>>>(
             sa, near_i, near4, S);
         h->launches += 1;
@@ -1081,9 +1082,10 @@ int f1l_pure_pursuit_batch_dev(f1l_handle h, const double* poses_dev, int n_pose
     o.lookahead_i = lookahead_i_dev;
     o.actuation = actuation_dev;
     o.status = status_dev;
+    o.front = nullptr;
     const int blocks = (n_poses + PP_THREADS - 1) / PP_THREADS;
     pp_batch_kernel<<<blocks, PP_THREADS, PP_SMEM_BYTES, (cudaStream_t)stream>>>(
-        track_view(h), poses_dev, 3, n_poses, L, h->cfg.wheelbase, h->cfg.max_reacquire, o);
+        track_view(h), poses_dev, 3, n_poses, L, h->cfg.wheelbase, h->cfg.max_reacquire, 0, 0.0, o);
     h->launches += 1;
     CK(cudaGetLastError());
     return F1L_OK;
@@ -1115,6 +1117,46 @@ int f1l_pure_pursuit_batch(f1l_handle h, const double* poses, int n, double L, d
     if (lookahead_i) CK(cudaMemcpyAsync(lookahead_i, h->m_o3.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     if (actuation) CK(cudaMemcpyAsync(actuation, h->m_o4.p, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
     if (status) CK(cudaMemcpyAsync(status, h->m_o5.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return F1L_OK;
+}
+
+int f1l_front_axle_batch_dev(f1l_handle h, const double* poses_dev, int n_poses, double wheelbase,
+                             double k_path, double* front_dev, int32_t* nearest_i_dev,
+                             void* stream) {
+    if (!h || !poses_dev || n_poses <= 0 || !front_dev) return F1L_ERR_INVALID_ARG;
+    if (h->n < 2) return F1L_ERR_NO_TRACK;
+    CK(cudaSetDevice(h->device));
+    PPOut o;
+    o.nearest = nullptr;
+    o.nearest_i = nearest_i_dev;
+    o.lookahead = nullptr;
+    o.lookahead_i = nullptr;
+    o.actuation = nullptr;
+    o.status = nullptr;
+    o.front = front_dev;
+    const int blocks = (n_poses + PP_THREADS - 1) / PP_THREADS;
+    pp_batch_kernel<<<blocks, PP_THREADS, PP_SMEM_BYTES, (cudaStream_t)stream>>>(
+        track_view(h), poses_dev, 4, n_poses, 0.0, wheelbase, 0.0, 1, k_path, o);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    return F1L_OK;
+}
+
+int f1l_front_axle_batch(f1l_handle h, const double* poses, int n, double wheelbase, double k_path,
+                         double* front, int32_t* nearest_i) {
+    if (!h || !poses || n <= 0 || !front) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    ENS(h->m_in, (size_t)n * 32);
+    ENS(h->m_o0, (size_t)n * 48);
+    if (nearest_i) ENS(h->m_o1, (size_t)n * 4);
+    CK(cudaMemcpyAsync(h->m_in.p, poses, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    int r = f1l_front_axle_batch_dev(h, (const double*)h->m_in.p, n, wheelbase, k_path,
+                                     (double*)h->m_o0.p, nearest_i ? (int32_t*)h->m_o1.p : nullptr, st);
+    if (r != F1L_OK) return r;
+    CK(cudaMemcpyAsync(front, h->m_o0.p, (size_t)n * 48, cudaMemcpyDeviceToHost, st));
+    if (nearest_i) CK(cudaMemcpyAsync(nearest_i, h->m_o1.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return F1L_OK;
 }

@@ -24,11 +24,21 @@ struct PPOut {
     int32_t* lookahead_i; // [B]
     double* actuation;    // [B,2] steer, speed
     int32_t* status;      // [B]
+    double* front;        // [B,6] front-axle mode: theta_e, ef, theta_raceline, kappa_ref,
+                          //       goal_velocity, delta (Stanley steering for k_path)
 };
+
+// pi_2_pi (utils/utils.py:276-283)
+__device__ __forceinline__ double pi_2_pi64(double a) {
+    const double pi = 3.14159265358979323846;
+    if (a > pi) return a - 2.0 * pi;
+    if (a < -pi) return a + 2.0 * pi;
+    return a;
+}
 
 __global__ void __launch_bounds__(PP_THREADS)
 pp_batch_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, int n_poses, double L, double wb,
-                double max_reacquire, PPOut out) {
+                double max_reacquire, int front_axle, double k_path, PPOut out) {
     extern __shared__ __align__(16) unsigned char pp_smem[];
     float4* sA = reinterpret_cast<float4*>(pp_smem);
     float2* sB = reinterpret_cast<float2*>(sA + PP_CHUNK);
@@ -38,8 +48,12 @@ pp_batch_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride,
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = gid < n_poses;
     const int pid = active ? gid : n_poses - 1;
-    const double qx = poses[(size_t)pose_stride * pid], qy = poses[(size_t)pose_stride * pid + 1];
+    double qx = poses[(size_t)pose_stride * pid], qy = poses[(size_t)pose_stride * pid + 1];
     const double qth = poses[(size_t)pose_stride * pid + 2];
+    if (front_axle) {   // query point = front axle centre (stanley.py:66-68, lqr.py:76-78)
+        qx = xadd(qx, xmul(wb, cos(qth)));
+        qy = xadd(qy, xmul(wb, sin(qth)));
+    }
 
     float best = CUDART_INF_F;
     int bk = 0;
@@ -88,6 +102,28 @@ pp_batch_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride,
 
     // float64 epilogue: exact nearest among the neighbours, then pure_pursuit.py:69-83
     const Nearest64 nr = refine_nearest64(tr.xy, nseg, qx, qy, bk);
+    if (front_axle) {
+        // stanley.py:69-85 / lqr.py:79-102: cross-track error of the front axle along the
+        // vehicle's right-hand normal, heading error against the nearest waypoint's heading
+        const double vx = xsub(qx, nr.px), vy = xsub(qy, nr.py);
+        const double half_pi = 3.14159265358979323846 / 2.0;
+        const double ef = xadd(xmul(vx, cos(qth - half_pi)), xmul(vy, sin(qth - half_pi)));
+        const double th_ref = tr.psi[nr.i];
+        const double th_e = pi_2_pi64(th_ref - qth);
+        const double vel = pose_stride > 3 ? poses[(size_t)pose_stride * pid + 3] : 0.0;
+        if (out.front) {
+            double* f = out.front + 6 * (size_t)gid;
+            f[0] = th_e; f[1] = ef; f[2] = th_ref; f[3] = tr.kappa[nr.i]; f[4] = tr.v[nr.i];
+            f[5] = atan2(xmul(k_path, ef), vel) + th_e;   // stanley.py:108-110
+        }
+        if (out.nearest) {
+            double2* o = reinterpret_cast<double2*>(out.nearest + 4 * (size_t)gid);
+            o[0] = make_double2(nr.px, nr.py);
+            o[1] = make_double2(nr.dist, nr.t);
+        }
+        if (out.nearest_i) out.nearest_i[gid] = nr.i;
+        return;
+    }
     Intersect64 ip;
     ip.px = 0.0; ip.py = 0.0; ip.t = 0.0; ip.i = 0; ip.found = 0;
     int status = 0;

@@ -308,6 +308,16 @@ class Engine:
             _vp(nearest_i), _vp(lookahead), _vp(lookahead_i), _vp(actuation), _vp(status),
             C.c_void_p(st)))
 
+    def front_axle_batch(self, states, wheelbase, k_path=5.0):
+        """states [B,4] (x, y, theta, velocity) -> (front [B,6], target_index [B]); front columns:
+        theta_e, ef, theta_raceline, kappa_ref, goal_velocity, Stanley delta."""
+        st = _f64(states).reshape(-1, 4)
+        front = np.zeros((st.shape[0], 6))
+        idx = np.zeros(st.shape[0], np.int32)
+        self._ck(self._L.f1l_front_axle_batch(self._h, _vp(st), st.shape[0], float(wheelbase),
+                                              float(k_path), _vp(front), _vp(idx)))
+        return front, idx
+
     def intersect_point_batch(self, points, t_start, radius, wrap):
         pts = _f64(points).reshape(-1, 2)
         t0 = _f64(t_start).ravel()

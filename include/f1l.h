@@ -217,6 +217,22 @@ int f1l_pure_pursuit_batch(f1l_handle h, const double* poses, int n_poses,
                            double* lookahead, int32_t* lookahead_i, double* actuation,
                            int32_t* status);
 
+/*
+ * Front-axle tracking errors for B vehicle states on the uploaded track: the nearest_point
+ * consumer shared by the Stanley and LQR controllers.  Replaces StanleyPlanner.calc_theta_and_ef
+ * + controller (control/stanley/stanley.py:57-112) and LQRPlanner.calc_control_points
+ * (control/lqr/lqr.py:60-102).
+ *   poses [B,4] f64 (x, y, theta, velocity)
+ *   front [B,6] f64 = (theta_e, ef, theta_raceline, kappa_ref, goal_velocity,
+ *                      delta = atan2(k_path * ef, velocity) + theta_e)
+ *   nearest_i [B] i32 (target_index) or NULL
+ */
+int f1l_front_axle_batch_dev(f1l_handle h, const double* poses_dev, int n_poses, double wheelbase,
+                             double k_path, double* front_dev, int32_t* nearest_i_dev,
+                             void* stream);
+int f1l_front_axle_batch(f1l_handle h, const double* poses, int n_poses, double wheelbase,
+                         double k_path, double* front, int32_t* nearest_i);
+
 /* intersect_point (utils/utils.py:69-151) for B independent queries on the uploaded track:
  * points [B,2], radius, start parameter t [B]; out [B,4] = (p_x, p_y, t, found), out_i [B]. */
 int f1l_intersect_point_batch(f1l_handle h, const double* points, const double* t_start,

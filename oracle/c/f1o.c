@@ -189,6 +189,33 @@ int f1o_pure_pursuit(const double* wpts, int n, int ncols, double px, double py,
     return status;
 }
 
+/* stanley.py:57-112 / lqr.py:60-102: out6 = theta_e, ef, theta_raceline, kappa_ref, goal_velocity,
+ * delta */
+static double pi_2_pi(double a) { /* utils/utils.py:276-283 */
+    if (a > PI) return a - 2.0 * PI;
+    if (a < -PI) return a + 2.0 * PI;
+    return a;
+}
+
+void f1o_front_axle(const double* wpts, int n, int ncols, const double state[4], double wheelbase,
+                    double k_path, double* out6, int32_t* target_index) {
+    const double fx = state[0] + wheelbase * cos(state[2]);      /* stanley.py:66 */
+    const double fy = state[1] + wheelbase * sin(state[2]);      /* :67 */
+    const double f[2] = {fx, fy};
+    double proj[2], dist, t;
+    int32_t i;
+    f1o_nearest_point(f, wpts, n, ncols, proj, &dist, &t, &i);   /* :69 */
+    const double vx = fx - proj[0], vy = fy - proj[1];           /* :70 */
+    const double ef = vx * cos(state[2] - PI / 2.0) + vy * sin(state[2] - PI / 2.0); /* :73-75 */
+    const double th_ref = ncols > 3 ? wpts[(size_t)i * ncols + 3] : 0.0;             /* :79 */
+    const double th_e = pi_2_pi(th_ref - state[2]);                                   /* :80 */
+    out6[0] = th_e; out6[1] = ef; out6[2] = th_ref;
+    out6[3] = ncols > 4 ? wpts[(size_t)i * ncols + 4] : 0.0;     /* lqr.py:96 */
+    out6[4] = ncols > 2 ? wpts[(size_t)i * ncols + 2] : 0.0;     /* stanley.py:83 */
+    out6[5] = atan2(k_path * ef, state[3]) + th_e;               /* :108-110 */
+    if (target_index) *target_index = i;
+}
+
 void f1o_pure_pursuit_batch(const double* wpts, int n, int ncols, const double* poses, int b,
                             double lookahead, double wheelbase, double max_reacquire,
                             double* nearest4, int32_t* nearest_i, double* look4, int32_t* look_i,

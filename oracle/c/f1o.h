@@ -93,6 +93,11 @@ void f1o_pure_pursuit_batch(const double* wpts, int n, int ncols, const double* 
                             double* nearest4, int32_t* nearest_i, double* look4, int32_t* look_i,
                             double* act2, int32_t* status, int n_threads);
 
+/* stanley.py:57-112, lqr.py:60-102: front-axle errors; out6 = theta_e, ef, theta_raceline,
+ * kappa_ref, goal_velocity, delta */
+void f1o_front_axle(const double* wpts, int n, int ncols, const double state[4], double wheelbase,
+                    double k_path, double* out6, int32_t* target_index);
+
 /* LUT build (continuation from the straight line), [nx,ny,nt,4] float */
 void f1o_lut_build(const int32_t dims[3], const double ranges[6], float* lut, int n_threads);
 

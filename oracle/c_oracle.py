@@ -79,6 +79,8 @@ def lib():
         L.f1o_default_config.argtypes = [C.POINTER(Config)]
         L.f1o_default_config.restype = None
         L.f1o_max_threads.restype = C.c_int
+        L.f1o_front_axle.argtypes = [_dp, C.c_int, C.c_int, _dp, C.c_double, C.c_double, _dp, _ip]
+        L.f1o_front_axle.restype = None
         L.f1o_collide_f32.argtypes = [_fp, _fp, C.c_int, C.c_int, _fp, C.c_int, _fp, _ip, _bp,
                                       C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _bp]
         L.f1o_collide_f32.restype = None
@@ -317,3 +319,17 @@ def collide_f32(states, headings, opp_local, n_opp, grid_xf, grid_i0, grid, half
                           np.float32(half_l), np.float32(half_w), np.float32(rc2),
                           out.ctypes.data_as(_bp))
     return out
+
+
+def front_axle_batch(wpts, states, wheelbase=0.33, k_path=5.0):
+    """stanley.py:57-112 / lqr.py:60-102 for B states [B,4] -> (front [B,6], target_index [B])"""
+    wpts = _as_f64(wpts)
+    st = _as_f64(states).reshape(-1, 4)
+    out = np.zeros((st.shape[0], 6))
+    idx = np.zeros(st.shape[0], np.int32)
+    for k in range(st.shape[0]):
+        i = C.c_int32()
+        lib().f1o_front_axle(_d(wpts), wpts.shape[0], wpts.shape[1], _d(st[k]), float(wheelbase),
+                             float(k_path), _d(out[k]), C.byref(i))
+        idx[k] = i.value
+    return out, idx

@@ -121,3 +121,27 @@ def test_planner_class_api(golden_spielberg):
     far = PurePursuitPlanner(waypoints=g["waypoints"])
     with pytest.warns(UserWarning):
         assert far.plan(500.0, 500.0, 0.0, 0.8) == (0.0, 0.0)
+
+
+def test_stanley_front_axle_matches_reference(golden_spielberg):
+    """front-axle mode of K1 vs the golden vectors of the reference Stanley / LQR controllers"""
+    import os
+    from f1tenth_planning_b200 import StanleyPlanner
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "stanley.npz"))
+    wp = golden_spielberg["waypoints"]
+    pl = StanleyPlanner(waypoints=wp)
+    front, idx = pl.front_axle_errors(g["states"], k_path=5.0)
+    same = idx == g["target_index"]
+    assert (~same).mean() < 0.02
+    np.testing.assert_allclose(front[same], g["front"][same], rtol=1e-9, atol=1e-9)
+    steer, speed = pl.plan_batch(g["states"], 5.0)
+    np.testing.assert_allclose(np.stack([steer, speed], 1)[same], g["plan"][same], rtol=1e-9, atol=1e-9)
+    s = g["states"][0]
+    d, v = pl.plan(s[0], s[1], s[2], s[3], 5.0)
+    np.testing.assert_allclose([d, v], g["plan"][0], rtol=1e-9, atol=1e-9)
+    th_e, ef, ti, gv = pl.calc_theta_and_ef(s, wp)
+    assert ti == g["target_index"][0] and abs(th_e - g["front"][0, 0]) < 1e-9
+    with pytest.raises(ValueError):
+        StanleyPlanner().plan(0.0, 0.0, 0.0, 1.0)
+    with pytest.raises(ValueError):
+        pl.plan(0.0, 0.0, 0.0, 1.0, waypoints=np.zeros((5, 3)))

@@ -97,3 +97,14 @@ def test_live_reference_functions(ellipse):
         rq, ri2, rt2 = intersect_point(pos, 1.7, xy, float(ri + rt), wrap=True)
         q2, i2, t2 = co.intersect_point(pos, 1.7, xy, i + t, wrap=True)
         assert i2 == ri2 and abs(t2 - rt2) < 1e-9
+
+
+def test_front_axle_errors_match_stanley_and_lqr(golden_spielberg):
+    """StanleyPlanner.calc_theta_and_ef / controller / plan (stanley.py:57-139) and
+    LQRPlanner.calc_control_points (lqr.py:60-102)"""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "stanley.npz"))
+    front, idx = co.front_axle_batch(golden_spielberg["waypoints"], g["states"],
+                                     float(g["wheelbase"]), float(g["k_path"]))
+    assert np.array_equal(idx, g["target_index"])
+    np.testing.assert_allclose(front, g["front"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(front[:, [5, 4]], g["plan"], rtol=0, atol=1e-12)

@@ -79,7 +79,7 @@ def kernel_summary(rep, title, kern_sub, name):
         f.write(subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True,
                                text=True).stdout)
     by_line = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), src_csv, kern_sub,
-                              os.path.join(ROOT, "f1tenth_planning_b200", "lib", "libf1l.so"), "30"],
+                              os.environ.get("F1L_PROFILE_SO", os.path.join(ROOT, "f1tenth_planning_b200", "lib", "libf1l.so")), "30"],
                              capture_output=True, text=True).stdout
     mix = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_sass_summary.py"), src_csv],
                          capture_output=True, text=True).stdout
