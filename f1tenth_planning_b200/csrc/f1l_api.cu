@@ -171,6 +171,7 @@ EvalParams eval_params(f1l_handle h) {
     e.n_cull = c.n_cull;
     e.literal_tracker = c.literal_tracker;
     e.use_goal_kappa = c.use_goal_kappa;
+    e.generator = c.generator;
     for (int i = 0; i < F1L_N_TERMS; ++i) e.w[i] = (float)c.weights[i];
     e.kappa_max = (float)c.kappa_max;
     e.half_l = (float)(0.5 * c.car_length);
@@ -189,6 +190,7 @@ int check_config(const f1l_config* c) {
     if (c->n_samples < 2 || c->n_samples > F1L_MAX_M) return F1L_ERR_INVALID_ARG;
     if (c->n_newton < 0 || c->n_newton > 64) return F1L_ERR_INVALID_ARG;
     if (c->n_shift < 0 || c->n_cull < 0) return F1L_ERR_INVALID_ARG;
+    if (c->generator < 0 || c->generator > 1) return F1L_ERR_INVALID_ARG;
     if (!(c->car_length > 0) || !(c->car_width > 0)) return F1L_ERR_INVALID_ARG;
     return F1L_OK;
 }

@@ -52,6 +52,7 @@ struct EvalParams {
     int window;       // requested window (<=0: all)
     int n_shift, n_cull;
     int literal_tracker, use_goal_kappa;
+    int generator;    // 0 cubic spiral, 1 G1 clothoid
     float w[F1L_N_TERMS];
     float kappa_max;  // <= 0: off
     float half_l, half_w;

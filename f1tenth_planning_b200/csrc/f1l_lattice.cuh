@@ -133,6 +133,73 @@ __device__ __forceinline__ float4 lut_lookup(const LutView& lut, float gx, float
     return __ldg(lut.cells + ((size_t)ix * lut.ny + iy) * lut.nt + it);
 }
 
+// G1 Hermite clothoid from (0,0,0) to the goal -- the generator the reference calls
+// (Clothoid.G1Hermite, lattice_planner.py:196); Bertolazzi & Frego 2015.  With the chord as x
+// axis: phi0 = -phi, phi1 = gth - phi, delta = phi1 - phi0; 1-D Newton on
+//   g(A) = int_0^1 sin(A t^2 + (delta - A) t + phi0) dt = 0      from A = 3 (phi0 + phi1),
+// then L = r / int cos, kappa0 = (delta - A)/L, dkappa = 2A/L^2.  Lane = Simpson node
+// (lane+1)/32; node 0 contributes sin/cos(phi0)/96 to g and X and nothing to g'.  The clothoid
+// is the cubic spiral with linear curvature, so the result is returned as a SpiralF and shares
+// the sampling / cost / collision code.  Returns the number of quadrature passes.
+__device__ __forceinline__ float wrap_pi_f(float a) {
+    const float two_pi = 6.283185307179586f, pi = 3.14159265358979f;
+    a -= two_pi * rintf(a * (1.0f / two_pi));
+    if (a <= -pi) a += two_pi;
+    if (a > pi) a -= two_pi;
+    return a;
+}
+
+__device__ __forceinline__ int clothoid_g1(SpiralF& sp, float gx, float gy, float gth, int iters,
+                                           int lane) {
+    const float r = sqrtf(fmaf(gx, gx, gy * gy));
+    const float phi = atan2f(gy, gx);
+    const float phi0 = wrap_pi_f(-phi), phi1 = wrap_pi_f(gth - phi);
+    const float delta = phi1 - phi0;
+    const float t = (float)(lane + 1) * (1.0f / 32.0f);
+    const float w = (lane == 31) ? (1.0f / 96.0f) : (((lane + 1) & 1) ? (4.0f / 96.0f) : (2.0f / 96.0f));
+    const float tt = t * t, dt = tt - t;
+    float s0, c0;
+    __sincosf(phi0, &s0, &c0);
+    float A = 3.0f * (phi0 + phi1), X = 1.0f;
+    int it = 0;
+    for (;; ++it) {
+        float sn, cs;
+        __sincosf(fmaf(A, tt, fmaf(delta - A, t, phi0)), &sn, &cs);
+        float g = w * sn, x = w * cs, dg = x * dt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            g += __shfl_xor_sync(F1L_FULL, g, o);
+            x += __shfl_xor_sync(F1L_FULL, x, o);
+            dg += __shfl_xor_sync(F1L_FULL, dg, o);
+        }
+        g = fmaf(s0, 1.0f / 96.0f, g);
+        X = fmaf(c0, 1.0f / 96.0f, x);
+        if (fabsf(g) < 1.5e-6f || it >= iters) { ++it; break; }
+        A -= __fdividef(g, dg);
+    }
+    const float L = __fdividef(r, X);
+    sp.sf = L;
+    sp.p0 = __fdividef(delta - A, L);          // kappa0
+    sp.b1 = 2.0f * A * __fdividef(1.0f, L);    // dkappa * L
+    sp.b2 = 0.0f; sp.b3 = 0.0f;
+    sp.h1 = 0.5f * sp.b1; sp.h2 = 0.0f; sp.h3 = 0.0f;
+    sp.p1 = sp.p0 + sp.b1 * (1.0f / 3.0f);
+    sp.p2 = sp.p0 + sp.b1 * (2.0f / 3.0f);
+    sp.p3 = sp.p0 + sp.b1;
+    return it;
+}
+
+// generator dispatch (warp-uniform): fills `sp` for the goal, returns the quadrature passes
+__device__ __forceinline__ int generate_spiral(SpiralF& sp, const LutView& lut, const EvalParams& ep,
+                                               float gx, float gy, float gth, float p3, int lane) {
+    if (ep.generator == 1) return clothoid_g1(sp, gx, gy, gth, ep.n_newton, lane);
+    sp.p0 = 0.0f;
+    sp.p3 = p3;
+    const float4 seed = lut_lookup(lut, gx, gy, gth);
+    sp.p1 = seed.x; sp.p2 = seed.y; sp.sf = seed.z;
+    return spiral_newton(sp, gx, gy, gth, ep.n_newton, lane);
+}
+
 // M arc samples, lane l owns samples [l*IPL, (l+1)*IPL).  Per-interval Simpson
 // dx_i = h/6 (cos th_{i-1} + 4 cos th_{i-1/2} + cos th_i), inclusive prefix by a warp scan.
 template <int IPL>
@@ -558,13 +625,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
         candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.inv_nW, a.C, s, c,
                        a.ep.use_goal_kappa != 0, gx, gy, gth, p3, have_centre, v_ref);
         SpiralF sp;
-        sp.p0 = 0.0f;
-        sp.p3 = p3;
-        {
-            const float4 seed = lut_lookup(a.lut, gx, gy, gth);
-            sp.p1 = seed.x; sp.p2 = seed.y; sp.sf = seed.z;
-        }
-        const int n_pass = spiral_newton(sp, gx, gy, gth, a.ep.n_newton, lane);
+        const int n_pass = generate_spiral(sp, a.lut, a.ep, gx, gy, gth, p3, lane);
 
         // ---- arc samples ----
         float x[IPL], y[IPL], th[IPL], kp[IPL], cs[IPL], sn[IPL];
@@ -826,7 +887,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 float* g = a.goals_out + cand * 3;
                 g[0] = gx; g[1] = gy; g[2] = gth;
             }
-            if (a.params) a.params[cand] = make_float4(sp.p1, sp.p2, sp.sf, sp.p3);
+            if (a.params)   // cubic: (p1, p2, s_f, p3); clothoid: (kappa0, dkappa, L, kappa_end)
+                a.params[cand] = a.ep.generator == 1
+                                     ? make_float4(sp.p0, __fdividef(sp.b1, sp.sf), sp.sf, sp.p3)
+                                     : make_float4(sp.p1, sp.p2, sp.sf, sp.p3);
             const unsigned long long key =
                 ((unsigned long long)float_orderable(cost) << 32) | (unsigned)c;
             atomicMin(a.best + s, key);
@@ -856,13 +920,7 @@ __global__ void __launch_bounds__(32) select_kernel(SelectArgs a) {
     candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.inv_nW, a.C, s, idx,
                    a.ep.use_goal_kappa != 0, gx, gy, gth, p3, have_centre, v_ref);
     SpiralF sp;
-    sp.p0 = 0.0f;
-    sp.p3 = p3;
-    {
-        const float4 seed = lut_lookup(a.lut, gx, gy, gth);
-        sp.p1 = seed.x; sp.p2 = seed.y; sp.sf = seed.z;
-    }
-    spiral_newton(sp, gx, gy, gth, a.ep.n_newton, lane);
+    generate_spiral(sp, a.lut, a.ep, gx, gy, gth, p3, lane);
     float x[IPL], y[IPL], th[IPL], kp[IPL], cs[IPL], sn[IPL];
     spiral_sample<IPL>(sp, M, lane, x, y, th, kp, cs, sn);
 #pragma unroll
@@ -985,11 +1043,7 @@ generate_kernel(LutView lut, EvalParams ep, const float4* __restrict__ goals, in
     const int M = ep.M;
     const float4 g = __ldg(goals + c);
     SpiralF sp;
-    sp.p0 = 0.0f;
-    sp.p3 = g.w;
-    const float4 seed = lut_lookup(lut, g.x, g.y, g.z);
-    sp.p1 = seed.x; sp.p2 = seed.y; sp.sf = seed.z;
-    spiral_newton(sp, g.x, g.y, g.z, ep.n_newton, lane);
+    generate_spiral(sp, lut, ep, g.x, g.y, g.z, g.w, lane);
     float x[IPL], y[IPL], th[IPL], kp[IPL], cs[IPL], sn[IPL];
     spiral_sample<IPL>(sp, M, lane, x, y, th, kp, cs, sn);
     float maxk = 0.0f, ex = 0.0f, ey = 0.0f, eth = 0.0f;
@@ -1013,7 +1067,9 @@ generate_kernel(LutView lut, EvalParams ep, const float4* __restrict__ goals, in
                  fabsf(ex - g.x) < tol && fabsf(ey - g.y) < tol && fabsf(eth - g.z) < tol;
     if (valid && ep.kappa_max > 0.0f && !(maxk <= ep.kappa_max)) valid = false;
     if (lane == 0) {
-        if (params) params[c] = make_float4(sp.p1, sp.p2, sp.sf, sp.p3);
+        if (params)
+            params[c] = ep.generator == 1 ? make_float4(sp.p0, __fdividef(sp.b1, sp.sf), sp.sf, sp.p3)
+                                          : make_float4(sp.p1, sp.p2, sp.sf, sp.p3);
         if (flags) flags[c] = valid ? F1L_FLAG_VALID : 0;
     }
 }

@@ -68,7 +68,9 @@ typedef struct {
     int32_t literal_tracker; /* 1: reproduce lattice_planner.py:208-212 literally (map pose vs
                                 vehicle-frame trajectory, "speed" = theta column) */
     int32_t use_goal_kappa;  /* 1: end curvature p3 = raceline kappa at the goal centre; 0: p3 = 0 */
-    int32_t reserved0;
+    int32_t generator;       /* 0: cubic spiral (LUT seed + Newton on p1, p2, s_f); 1: G1 clothoid as
+                                the reference's Clothoid.G1Hermite(0,0,0,gx,gy,gtheta)
+                                (lattice_planner.py:196), 1-D Newton */
     double weights[F1L_N_TERMS]; /* cost weights (lattice_planner.py:130-156) */
     double kappa_max;        /* candidates with max|kappa| above it are invalid; <=0 disables */
     double car_length;       /* 0.58 */

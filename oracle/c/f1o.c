@@ -332,6 +332,57 @@ void f1o_spiral_sample(const double q[3], double p0, double p3, int m, double* s
     }
 }
 
+/* ------------------------------------------------------------------------- */
+/* G1 Hermite clothoid (the generator lattice_planner.py:196 calls) */
+/* ------------------------------------------------------------------------- */
+/* Bertolazzi & Frego, "G1 fitting with clothoids" (2015): with the chord as x axis,
+ * phi0 = theta0 - phi, phi1 = theta1 - phi, delta = phi1 - phi0, find A with
+ *   g(A) = int_0^1 sin(A t^2 + (delta - A) t + phi0) dt = 0          (1-D Newton from 3(phi0+phi1))
+ * then L = r / int_0^1 cos(...), kappa0 = (delta - A)/L, dkappa = 2A/L^2.  Integrals by the same
+ * composite Simpson rule (Q = 32) as the cubic-spiral Newton.  pyclothoids is absent here, so
+ * this stage is parity-unpinned; tests check it against scipy.integrate. */
+static double normalize_angle(double a) {
+    while (a > PI) a -= 2.0 * PI;
+    while (a <= -PI) a += 2.0 * PI;
+    return a;
+}
+
+int f1o_clothoid_g1(const double goal[3], int n_newton, double out[3]) {
+    const double r = sqrt(goal[0] * goal[0] + goal[1] * goal[1]);
+    const double phi = atan2(goal[1], goal[0]);
+    const double phi0 = normalize_angle(-phi), phi1 = normalize_angle(goal[2] - phi);
+    const double delta = phi1 - phi0;
+    double A = 3.0 * (phi0 + phi1);
+    double X = 1.0;
+    int ok = 0;
+    for (int it = 0; it <= n_newton; ++it) {
+        double g = 0.0, dg = 0.0;
+        X = 0.0;
+        for (int j = 0; j <= F1O_Q; ++j) {
+            const double t = (double)j / F1O_Q;
+            const double w = ((j == 0 || j == F1O_Q) ? 1.0 : ((j & 1) ? 4.0 : 2.0)) / (3.0 * F1O_Q);
+            const double ph = A * t * t + (delta - A) * t + phi0;
+            const double c = cos(ph), s = sin(ph);
+            g += w * s; X += w * c; dg += w * c * (t * t - t);
+        }
+        if (fabs(g) < 1e-12) { ok = 1; break; }
+        if (it == n_newton) break;
+        A -= g / dg;
+    }
+    const double L = r / X;
+    out[0] = (delta - A) / L;
+    out[1] = 2.0 * A / (L * L);
+    out[2] = L;
+    return ok && isfinite(L) && L > 0.0;
+}
+
+void f1o_clothoid_sample(const double kdl[3], int m, double* st) {
+    /* a clothoid is the cubic spiral with linear curvature: knots on the line kappa0 + dkappa s */
+    const double L = kdl[2], k0 = kdl[0], k1 = kdl[0] + kdl[1] * L;
+    const double q[3] = {k0 + (k1 - k0) / 3.0, k0 + 2.0 * (k1 - k0) / 3.0, L};
+    f1o_spiral_sample(q, k0, k1, m, st);
+}
+
 /* heuristic seed */
 static void heuristic_seed(const double goal[3], double q[3]) {
     const double d = sqrt(goal[0] * goal[0] + goal[1] * goal[1]);
@@ -554,9 +605,17 @@ int f1o_plan(const f1o_config* cfg, const f1o_world* w, const double pose[4], co
         if (cfg->use_goal_kappa && !goals_in && w->ncols > 4)
             p3 = w->wpts[(size_t)centre_i[row] * w->ncols + 4];
         double q[3];
-        lut_seed(w, g, q);
-        f1o_spiral_solve(g, 0.0, p3, cfg->n_newton, q);
-        f1o_spiral_sample(q, 0.0, p3, M, st);
+        if (cfg->generator == 1) {
+            double kdl[3];
+            f1o_clothoid_g1(g, cfg->n_newton, kdl);
+            f1o_clothoid_sample(kdl, M, st);
+            q[0] = kdl[0]; q[1] = kdl[1]; q[2] = kdl[2];   /* params = (kappa0, dkappa, L) */
+            p3 = kdl[0] + kdl[1] * kdl[2];
+        } else {
+            lut_seed(w, g, q);
+            f1o_spiral_solve(g, 0.0, p3, cfg->n_newton, q);
+            f1o_spiral_sample(q, 0.0, p3, M, st);
+        }
         /* validity (B.2) */
         const double gn = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
         const double tol = cfg->converge_tol * (gn > 1.0 ? gn : 1.0);
@@ -648,9 +707,15 @@ int f1o_plan(const f1o_config* cfg, const f1o_world* w, const double pose[4], co
         double p3 = 0.0, q[3];
         if (cfg->use_goal_kappa && !goals_in && w->ncols > 4)
             p3 = w->wpts[(size_t)centre_i[best_row] * w->ncols + 4];
-        lut_seed(w, g, q);
-        f1o_spiral_solve(g, 0.0, p3, cfg->n_newton, q);
-        f1o_spiral_sample(q, 0.0, p3, M, best_st);
+        if (cfg->generator == 1) {
+            double kdl[3];
+            f1o_clothoid_g1(g, cfg->n_newton, kdl);
+            f1o_clothoid_sample(kdl, M, best_st);
+        } else {
+            lut_seed(w, g, q);
+            f1o_spiral_solve(g, 0.0, p3, cfg->n_newton, q);
+            f1o_spiral_sample(q, 0.0, p3, M, best_st);
+        }
     }
     out->best_idx = best_idx;
     out->best_cost = best_cost;

@@ -36,7 +36,7 @@ extern "C" {
 #define F1O_FLAG_NO_CENTRE 8u
 
 typedef struct {
-    int32_t n_samples, n_newton, window, n_shift, n_cull, literal_tracker, use_goal_kappa, reserved0;
+    int32_t n_samples, n_newton, window, n_shift, n_cull, literal_tracker, use_goal_kappa, generator;
     double weights[F1O_N_TERMS];
     double kappa_max, car_length, car_width, converge_tol, tracker_lookahead, wheelbase,
         max_reacquire;
@@ -105,6 +105,10 @@ void f1o_lut_build(const int32_t dims[3], const double ranges[6], float* lut, in
  * q = (p1, p2, s_f) in/out; states [M,4] = x, y, theta, kappa(signed). */
 void f1o_spiral_solve(const double goal[3], double p0, double p3, int n_newton, double q[3]);
 void f1o_spiral_sample(const double q[3], double p0, double p3, int m, double* states);
+/* G1 Hermite clothoid (0,0,0) -> goal (Bertolazzi & Frego 2015; what pyclothoids'
+ * Clothoid.G1Hermite solves): out = (kappa0, dkappa, L); returns 1 if converged */
+int f1o_clothoid_g1(const double goal[3], int n_newton, double out[3]);
+void f1o_clothoid_sample(const double kdl[3], int m, double* states);
 
 /* sampler B.1: goals [C,3] vehicle frame, centre waypoint index per lookahead row,
  * nearest index i_ego; returns C */

@@ -21,7 +21,7 @@ _bp = C.POINTER(C.c_uint8)
 class Config(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("n_newton", C.c_int32), ("window", C.c_int32),
                 ("n_shift", C.c_int32), ("n_cull", C.c_int32), ("literal_tracker", C.c_int32),
-                ("use_goal_kappa", C.c_int32), ("reserved0", C.c_int32),
+                ("use_goal_kappa", C.c_int32), ("generator", C.c_int32),
                 ("weights", C.c_double * N_TERMS), ("kappa_max", C.c_double),
                 ("car_length", C.c_double), ("car_width", C.c_double),
                 ("converge_tol", C.c_double), ("tracker_lookahead", C.c_double),
@@ -79,6 +79,10 @@ def lib():
         L.f1o_default_config.argtypes = [C.POINTER(Config)]
         L.f1o_default_config.restype = None
         L.f1o_max_threads.restype = C.c_int
+        L.f1o_clothoid_g1.argtypes = [_dp, C.c_int, _dp]
+        L.f1o_clothoid_g1.restype = C.c_int
+        L.f1o_clothoid_sample.argtypes = [_dp, C.c_int, _dp]
+        L.f1o_clothoid_sample.restype = None
         L.f1o_front_axle.argtypes = [_dp, C.c_int, C.c_int, _dp, C.c_double, C.c_double, _dp, _ip]
         L.f1o_front_axle.restype = None
         L.f1o_collide_f32.argtypes = [_fp, _fp, C.c_int, C.c_int, _fp, C.c_int, _fp, _ip, _bp,
@@ -333,3 +337,13 @@ def front_axle_batch(wpts, states, wheelbase=0.33, k_path=5.0):
                              float(k_path), _d(out[k]), C.byref(i))
         idx[k] = i.value
     return out, idx
+
+
+def clothoid(goal, n_newton=8, m=100):
+    """G1 Hermite clothoid (0,0,0) -> goal: ((kappa0, dkappa, L), states [m,4], converged)"""
+    goal = _as_f64(goal)
+    kdl = np.zeros(3)
+    ok = lib().f1o_clothoid_g1(_d(goal), int(n_newton), _d(kdl))
+    st = np.zeros((m, 4))
+    lib().f1o_clothoid_sample(_d(kdl), m, _d(st))
+    return kdl, st, bool(ok)

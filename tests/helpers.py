@@ -14,7 +14,7 @@ REL = 1e-4
 ABS = 1e-5
 
 CFG_FIELDS = ["n_samples", "n_newton", "window", "n_shift", "n_cull", "literal_tracker",
-              "use_goal_kappa", "kappa_max", "car_length", "car_width", "converge_tol",
+              "use_goal_kappa", "generator", "kappa_max", "car_length", "car_width", "converge_tol",
               "tracker_lookahead", "wheelbase", "max_reacquire"]
 
 

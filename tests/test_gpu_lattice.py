@@ -208,3 +208,27 @@ def test_collision_flags_bit_exact_on_device_states(ellipse):
         assert (mirror[valid] & 2).any() and (mirror[valid] & 4).any() and (mirror[valid] == 0).any()
         n_checked += int(valid.sum())
     assert n_checked > 5000
+
+
+def test_g1_clothoid_generator(ellipse, corridor):
+    """generator=1: the reference's G1-clothoid generator through the same
+    cost / collision / argmin pipeline."""
+    la, wd = np.linspace(0.6, 3.8, 16), np.linspace(-1.1, 1.1, 15)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, grid=corridor, generator=1, kappa_max=3.0)
+    n_valid = 0
+    for seed in (51, 52, 53):
+        pose, opp = H.scenario(ellipse, seed, 4)
+        d, o, st = _run(eng, cfg, world, pose, opp)
+        n_valid += st["n_both_valid"]
+        both = ((d.flags & 1) != 0) & ((o["flags"] & 1) != 0)
+        # linear curvature: kappa_i = kappa0 + dkappa * s_i
+        s = np.linspace(0, 1, cfg.n_samples)[None, :] * d.params[both, 2:3]
+        np.testing.assert_allclose(d.states[both][:, :, 3], d.params[both, 0:1] + d.params[both, 1:2] * s,
+                                   rtol=1e-4, atol=1e-4)
+    assert n_valid > 300
+    goals = np.array([[1.0, 1.0, 0.0], [2.0, 0.3, 0.2], [3.0, -0.5, -0.3]])
+    states, params, valid = eng.generate(goals)
+    assert valid.all()
+    for g, stt in zip(goals, states):
+        ref = co.clothoid(g, n_newton=cfg.n_newton, m=cfg.n_samples)[1]
+        assert H.close(stt, ref, scale=H.traj_scale(ref)).all()

@@ -184,3 +184,23 @@ def test_shard_concatenation_equals_unsharded(ellipse, corridor):
     for i in range(2):
         assert np.array_equal(whole["best_idx"][i::2], halves[i]["best_idx"])
         assert np.array_equal(whole["costs"][i::2], halves[i]["costs"])
+
+
+@pytest.mark.parametrize("goal", [(1.0, 0.2, 0.1), (2.5, -0.8, -0.4), (3.5, 1.2, 0.9), (1.0, 1.0, 0.0),
+                                  (2.0, 0.0, 0.0), (0.5, -0.6, -1.2), (3.0, 0.5, -0.3)])
+def test_g1_clothoid_against_ode(goal):
+    """G1 Hermite clothoid (what lattice_planner.py:196 asks pyclothoids for): linear curvature,
+    reaches the goal pose, matches an independent ODE integration."""
+    kdl, st, ok = co.clothoid(goal, n_newton=10, m=100)
+    assert ok
+    k0, dk, L = kdl
+    np.testing.assert_allclose(st[-1, :3], goal, atol=5e-6)
+    np.testing.assert_allclose(st[:, 3], k0 + dk * np.linspace(0, L, 100), atol=1e-12)   # linear kappa
+    sol = solve_ivp(lambda s, z: [np.cos(z[2]), np.sin(z[2]), k0 + dk * s], [0, L], [0, 0, 0],
+                    t_eval=np.linspace(0, L, 100), rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(st[:, 0], sol.y[0], atol=1e-6)
+    np.testing.assert_allclose(st[:, 1], sol.y[1], atol=1e-6)
+    np.testing.assert_allclose(st[:, 2], sol.y[2], atol=1e-9)
+    # the reference's own example goal, G1Hermite(0,0,0,1,1,0) (test_pyclothoids.py:23): symmetric
+    if goal == (1.0, 1.0, 0.0):
+        np.testing.assert_allclose(st[:, 3], -st[::-1, 3], atol=1e-9)
