@@ -124,6 +124,11 @@ class LatticePlanner():
         if self._engine is not None:
             self._engine.set_grid(*self._map)
 
+    def load_map(self, yaml_path):
+        """ROS map_server yaml + image (examples/control/Spielberg_map.yaml) -> set_map"""
+        from . import io
+        self.set_map(*io.load_map(yaml_path))
+
     def configure(self, **config):
         self._config.update(config)
         if self._engine is not None:

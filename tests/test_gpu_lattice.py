@@ -233,3 +233,28 @@ def test_g1_clothoid_generator(ellipse, corridor):
     for g, stt in zip(goals, states):
         ref = co.clothoid(g, n_newton=cfg.n_newton, m=cfg.n_samples)[1]
         assert H.close(stt, ref, scale=H.traj_scale(ref)).all()
+
+
+def test_real_track_and_map_fixtures(golden_spielberg):
+    """Spielberg raceline + its ROS map and the Levine raceline + SLAM map (reference fixtures,
+    carried as tests/golden/maps.npz): plan parity against the oracle along the tracks."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "maps.npz"))
+
+    def unpack(name):
+        h, w = g[name + "_shape"]
+        return np.unpackbits(g[name + "_bits"], axis=1)[:, :w]
+    cases = [(golden_spielberg["waypoints"], unpack("spielberg"), tuple(g["spielberg_origin"]),
+              float(g["spielberg_res"]), np.linspace(0.8, 3.5, 10), np.linspace(-1.5, 1.5, 13)),
+             (g["levine_raceline"], unpack("levine"), tuple(g["levine_origin"]), float(g["levine_res"]),
+              np.linspace(0.5, 2.0, 8), np.linspace(-0.8, 0.8, 9))]
+    for wp, occ, origin, res, la, wd in cases:
+        eng, cfg, world = H.make_pair(wp, la, wd, grid=(occ, origin, res), kappa_max=2.5)
+        rng = np.random.default_rng(4)
+        n_map = 0
+        for k in rng.integers(0, wp.shape[0] - 1, 6):
+            pose = np.array([wp[k, 0], wp[k, 1], wp[k, 3] + rng.normal(0, 0.05), 4.0])
+            d, o, st = _run(eng, cfg, world, pose, None)
+            n_map += st["collide_map_count"]
+            assert st["n_both_valid"] > 10
+        assert n_map > 0
