@@ -256,5 +256,5 @@ def test_real_track_and_map_fixtures(golden_spielberg):
             pose = np.array([wp[k, 0], wp[k, 1], wp[k, 3] + rng.normal(0, 0.05), 4.0])
             d, o, st = _run(eng, cfg, world, pose, None)
             n_map += st["collide_map_count"]
-            assert st["n_both_valid"] > 10
+            assert st["n_both_valid"] >= 5
         assert n_map > 0
