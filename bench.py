@@ -69,7 +69,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -281,6 +281,44 @@ def extras(track, grid, device):
     return out
 
 
+def sharded_dense_query(track, grid, device, rank, world_size, dev):
+    """config 5 across ranks: every rank evaluates a contiguous block of the 65536 candidates of
+    ONE query (f1l_plan_shard), then an 8-byte-per-rank gather of (cost, idx) picks the winner
+    (SURVEY 8e).  Latency = barrier-to-result on the slowest rank."""
+    import torch
+    import torch.distributed as dist
+    from f1tenth_planning_b200 import sharding
+    from f1tenth_planning_b200.engine import Engine
+    la, wd = synth.goal_grid(5)
+    eng = Engine(device=device, n_samples=200, window=128)
+    eng.set_track(track)
+    eng.set_grid(*grid)
+    eng.set_goal_grid(la, wd)
+    C = eng.n_candidates
+    lo, hi = sharding.block(C, rank, world_size)
+    poses, opp, n_opp = synth.scenario_batch(track, 16, 8, 1005)   # same on every rank
+    ts = []
+    best = None
+    for i in range(3 + 30):
+        s = i % 16
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        d = eng.plan(poses[s], opp[s], update_prev=False, detail=False, shard=(lo, hi))
+        best = sharding.reduce_best(d.best_cost, d.best_idx)
+        dt = time.perf_counter() - t0
+        if i >= 3:
+            ts.append(dt)
+    t = torch.tensor(ts, dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    eng.close()
+    ts = t.cpu().numpy()
+    return {"c5_sharded_plan_p50_us": 1e6 * float(np.percentile(ts, 50)),
+            "c5_sharded_plan_p99_us": 1e6 * float(np.percentile(ts, 99)),
+            "c5_sharded_candidates_per_s": C / float(np.percentile(ts, 50)),
+            "c5_candidates_per_rank": hi - lo, "c5_last_best": list(best)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -389,6 +427,10 @@ def run_ours(args):
     h2d = h_poses.nbytes + h_opp.nbytes + h_nopp.nbytes
     d2h = sum(v.nbytes for v in h_out.values())
 
+    sharded = None
+    if world_size > 1 and not args.no_extras:
+        sharded = sharded_dense_query(track, grid, local, rank, world_size, dev)
+
     if rank != 0:
         if world_size > 1:
             dist.destroy_process_group()
@@ -445,6 +487,8 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": th, "kind": "port",
                                 "sample": "%d of the %d scenarios (x%d candidates), %.1f s, C oracle "
                                           "(oracle/c/f1o.c) with OpenMP over scenarios" % (n, S, C, dt)}
+    if sharded is not None:
+        line["extra"] = sharded
     if world_size == 1 and not args.no_extras:
         try:
             line["extra"] = extras(track, grid, local)
