@@ -297,7 +297,7 @@ def sharded_dense_query(track, grid, device, rank, world_size, dev):
     C = eng.n_candidates
     lo, hi = sharding.block(C, rank, world_size)
     poses, opp, n_opp = synth.scenario_batch(track, 16, 8, 1005)   # same on every rank
-    ts = []
+    ts, tp = [], []
     best = None
     for i in range(3 + 30):
         s = i % 16
@@ -305,10 +305,12 @@ def sharded_dense_query(track, grid, device, rank, world_size, dev):
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         d = eng.plan(poses[s], opp[s], update_prev=False, detail=False, shard=(lo, hi))
+        t1 = time.perf_counter()
         best = sharding.reduce_best(d.best_cost, d.best_idx)
         dt = time.perf_counter() - t0
         if i >= 3:
             ts.append(dt)
+            tp.append(t1 - t0)
     t = torch.tensor(ts, dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     eng.close()
@@ -316,6 +318,7 @@ def sharded_dense_query(track, grid, device, rank, world_size, dev):
     return {"c5_sharded_plan_p50_us": 1e6 * float(np.percentile(ts, 50)),
             "c5_sharded_plan_p99_us": 1e6 * float(np.percentile(ts, 99)),
             "c5_sharded_candidates_per_s": C / float(np.percentile(ts, 50)),
+            "c5_sharded_local_plan_p50_us": 1e6 * float(np.percentile(tp, 50)),
             "c5_candidates_per_rank": hi - lo, "c5_last_best": list(best)}
 
 
@@ -337,7 +340,18 @@ def run_ours(args):
         # NCCL prints its version banner on stdout at VERSION level; keep stdout to the JSON line
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # ... and whatever NCCL still writes to fd 1 while the communicator comes up goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     S = args.scenarios
     track, grid, la, wd, poses, opp, n_opp = workload(rank, S)
