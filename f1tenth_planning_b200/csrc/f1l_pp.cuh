@@ -13,9 +13,12 @@
 #pragma once
 #include "f1l_common.cuh"
 
-#define PP_CHUNK 2048          // segments staged per shared-memory chunk
-#define PP_THREADS 128
+#define PP_CHUNK 512           // segments staged per shared-memory chunk (multiple of 32)
+#define PP_THREADS 64
 #define PP_SMEM_BYTES (PP_CHUNK * (sizeof(float4) + sizeof(float2)) + (PP_CHUNK / 32) * sizeof(double2))
+// Launch shape: 64-thread CTAs with a 12.5 KB table chunk keep ~13 CTAs resident per SM, so the
+// 1563 CTAs of 10^5 poses run as ONE balanced wave (21 warps per SM +-5 %); 128-thread CTAs with a
+// 48 KB chunk fit 4 per SM and needed 1.3 waves (measured: issue slots busy 48 % of the time).
 
 struct PPOut {
     double* nearest;      // [B,4] proj_x, proj_y, dist, t
@@ -34,6 +37,15 @@ __device__ __forceinline__ double pi_2_pi64(double a) {
     if (a > pi) return a - 2.0 * pi;
     if (a < -pi) return a + 2.0 * pi;
     return a;
+}
+
+// FP32 squared distance of a block-relative point to a segment in line form
+__device__ __forceinline__ float pp_seg_d2(float prx, float pry, float4 A, float2 Bv) {
+    const float q = fmaf(prx, A.x, fmaf(pry, A.y, -A.z));
+    const float nn = fmaf(pry, A.x, fmaf(-prx, A.y, -A.w));
+    const float t = __saturatef(q * Bv.y);
+    const float ex = fmaf(-t, Bv.x, q);
+    return fmaf(ex, ex, nn * nn);
 }
 
 __global__ void __launch_bounds__(PP_THREADS)
@@ -55,51 +67,51 @@ pp_batch_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride,
         qy = xadd(qy, xmul(wb, sin(qth)));
     }
 
+    // The scan keeps only the running minimum of each 32-segment block (one FMNMX per segment
+    // instead of compare + two selects) and remembers the best block; the exact index is
+    // recovered afterwards by re-scanning that one block (1.6 % extra work).
     float best = CUDART_INF_F;
-    int bk = 0;
+    int bblk = 0;
     for (int c0 = 0; c0 < nseg; c0 += PP_CHUNK) {
         const int cn = min(PP_CHUNK, nseg - c0);
-        for (int q = threadIdx.x; q < cn; q += blockDim.x) {
-            sA[q] = __ldg(tr.segA + c0 + q);
-            sB[q] = __ldg(tr.segB + c0 + q);
-        }
         const int nblk = (cn + 31) >> 5;
+        for (int q = threadIdx.x; q < (nblk << 5); q += blockDim.x) {
+            float4 A = make_float4(1.0f, 0.0f, 1e15f, 1e15f);   // padding: far away, finite
+            float2 Bv = make_float2(1.0f, 1.0f);
+            if (q < cn) {
+                A = __ldg(tr.segA + c0 + q);
+                Bv = __ldg(tr.segB + c0 + q);
+            }
+            sA[q] = A;
+            sB[q] = Bv;
+        }
         for (int b = threadIdx.x; b < nblk; b += blockDim.x) sO[b] = tr.blk_origin[(c0 >> 5) + b];
         __syncthreads();
         for (int blk = 0; blk < nblk; ++blk) {
             const double2 o = sO[blk];
             const float prx = (float)(qx - o.x), pry = (float)(qy - o.y);
             const int j0 = blk << 5;
-            const int jn = min(32, cn - j0);
-            if (jn == 32) {
+            float m = CUDART_INF_F;
 #pragma unroll 8
-                for (int j = 0; j < 32; ++j) {
-                    const float4 A = sA[j0 + j];
-                    const float2 Bv = sB[j0 + j];
-                    const float q = fmaf(prx, A.x, fmaf(pry, A.y, -A.z));
-                    const float nn = fmaf(pry, A.x, fmaf(-prx, A.y, -A.w));
-                    const float t = __saturatef(q * Bv.y);
-                    const float ex = fmaf(-t, Bv.x, q);
-                    const float d2 = fmaf(ex, ex, nn * nn);
-                    if (d2 < best) { best = d2; bk = c0 + j0 + j; }
-                }
-            } else {
-                for (int j = 0; j < jn; ++j) {
-                    const float4 A = sA[j0 + j];
-                    const float2 Bv = sB[j0 + j];
-                    const float q = fmaf(prx, A.x, fmaf(pry, A.y, -A.z));
-                    const float nn = fmaf(pry, A.x, fmaf(-prx, A.y, -A.w));
-                    const float t = __saturatef(q * Bv.y);
-                    const float ex = fmaf(-t, Bv.x, q);
-                    const float d2 = fmaf(ex, ex, nn * nn);
-                    if (d2 < best) { best = d2; bk = c0 + j0 + j; }
-                }
-            }
+            for (int j = 0; j < 32; ++j) m = fminf(m, pp_seg_d2(prx, pry, sA[j0 + j], sB[j0 + j]));
+            if (m < best) { best = m; bblk = (c0 >> 5) + blk; }
         }
         __syncthreads();
     }
     if (!active) return;
 
+    // first segment of the best block that attains the block minimum (same FP32 arithmetic)
+    int bk = bblk << 5;
+    {
+        const double2 o = tr.blk_origin[bblk];
+        const float prx = (float)(qx - o.x), pry = (float)(qy - o.y);
+        float m = CUDART_INF_F;
+        const int k1 = min((bblk << 5) + 32, nseg);
+        for (int k = bblk << 5; k < k1; ++k) {
+            const float d2 = pp_seg_d2(prx, pry, __ldg(tr.segA + k), __ldg(tr.segB + k));
+            if (d2 < m) { m = d2; bk = k; }
+        }
+    }
     // float64 epilogue: exact nearest among the neighbours, then pure_pursuit.py:69-83
     const Nearest64 nr = refine_nearest64(tr.xy, nseg, qx, qy, bk);
     if (front_axle) {

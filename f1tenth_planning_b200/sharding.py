@@ -11,21 +11,42 @@ def block(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class _Workspace:
+    """preallocated buffers of reduce_best (one per group / backend): a pinned host pair, its
+    device copy and the gathered [world, 2] result, so a call is one H2D, one all-gather and
+    one D2H instead of a dozen small allocations and synchronising reads"""
+
+    def __init__(self, group):
+        import torch
+        import torch.distributed as dist
+        self.world = dist.get_world_size(group)
+        self.nccl = dist.get_backend(group) == "nccl"
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.nccl else torch.device("cpu")
+        self.host = torch.zeros(2, dtype=torch.float64, pin_memory=self.nccl)
+        self.mine = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.all = torch.zeros(self.world * 2, dtype=torch.float64, device=dev)   # flat: gloo too
+        self.all_host = torch.zeros(self.world * 2, dtype=torch.float64, pin_memory=self.nccl)
+
+
+_workspaces = {}
+
+
 def reduce_best(cost, idx, group=None):
     """lexicographic (cost, idx) minimum over ranks == np.argmin's first-minimum rule on the
     concatenated cost vector.  Works on any torch.distributed backend (gloo on CPU, nccl)."""
-    import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         return float(cost), int(idx)
-    world = dist.get_world_size(group)
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" \
-        else torch.device("cpu")
-    mine = torch.tensor([float(cost), float(idx)], dtype=torch.float64, device=dev)
-    allp = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)]
-    dist.all_gather(allp, mine, group=group)
-    pairs = [(float(p[0]), int(p[1])) for p in allp]
-    return min(pairs)
+    ws = _workspaces.get(group)
+    if ws is None:
+        ws = _workspaces[group] = _Workspace(group)
+    ws.host[0] = float(cost)
+    ws.host[1] = float(idx)
+    ws.mine.copy_(ws.host, non_blocking=True)
+    dist.all_gather_into_tensor(ws.all, ws.mine, group=group)
+    ws.all_host.copy_(ws.all)          # synchronises
+    flat = ws.all_host.tolist()
+    return min((flat[2 * r], int(flat[2 * r + 1])) for r in range(ws.world))
 
 
 def gather_stats(values, group=None):
