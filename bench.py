@@ -81,10 +81,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def mark(self):
+        """rows seen so far (call at the start of the timed region; the sampler itself is started
+        earlier because nvidia-smi needs ~0.2 s before its first row)"""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.06)
+        last = len(self.rows)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -92,7 +98,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = self.rows[getattr(self, "first", 0):last] or self.rows[-3:]
+        for r in rows:
             p = [x.strip() for x in r.split(",")]
             if len(p) < 8:
                 continue
@@ -377,15 +384,16 @@ def run_ours(args):
         eng.plan_batch_dev(tp, to, tn, best_idx=o_idx, best_cost=o_cost, best_traj=o_traj,
                            costs=o_costs, flags=o_flags, steer_speed=o_ss)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize(dev)
     eng.set_timing(True)
-    sampler = ClockSampler(local)
     if world_size > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    sampler.start()
+    sampler.mark()
     l0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
