@@ -83,6 +83,7 @@ SIGNATURES = {
                                             _ip]),
     "f1l_get_actuation_batch": (C.c_int, [_vp, _dp, C.c_int, C.c_double, _dp]),
     "f1l_launch_count": (C.c_int64, [_vp]),
+    "f1l_set_graph": (C.c_int, [_vp, C.c_int]),
     "f1l_set_timing": (C.c_int, [_vp, C.c_int]),
     "f1l_last_kernel_ms": (C.c_int, [_vp, _fp, _fp, _fp]),
     "f1l_mean_kernel_ms": (C.c_int, [_vp, _fp, _fp, _fp, C.POINTER(C.c_int)]),

@@ -37,6 +37,11 @@ struct f1l_ctx {
     char err[512] = {0};
     int64_t launches = 0;
     int timing = 0;
+    // CUDA graph of the single-query chain (H2D, sampler, eval, select, D2H)
+    int use_graph = 1;
+    unsigned long long epoch = 0;   // bumped by every upload / config change
+    cudaGraphExec_t gexec = nullptr;
+    unsigned long long gkey[2] = {~0ull, ~0ull};
     int timed = 0;  // events of the last pipeline launch are valid
 #define F1L_EV_SLOTS 64
     cudaEvent_t ev[4 * F1L_EV_SLOTS] = {nullptr};
@@ -455,6 +460,14 @@ struct QHeader {
 };
 static_assert(sizeof(QHeader) == 48, "QHeader layout");
 
+// pinned-host / device input block of a single query (fixed size, so that the copy is a constant
+// node of the CUDA graph): the opponent count travels in the block, not as a kernel argument
+struct QInput {
+    double pose[4];
+    int32_t n_opp, pad;
+    double opp[3 * F1L_MAX_OPP];
+};
+
 }  // namespace
 
 extern "C" {
@@ -501,6 +514,12 @@ const char* f1l_strerror(int code) {
 const char* f1l_last_cuda_error(f1l_handle h) { return h ? h->err : ""; }
 int f1l_device(f1l_handle h) { return h ? h->device : -1; }
 int64_t f1l_launch_count(f1l_handle h) { return h ? h->launches : 0; }
+
+int f1l_set_graph(f1l_handle h, int on) {
+    if (!h) return F1L_ERR_INVALID_ARG;
+    h->use_graph = on;
+    return F1L_OK;
+}
 
 int f1l_set_timing(f1l_handle h, int on) {
     if (!h) return F1L_ERR_INVALID_ARG;
@@ -557,6 +576,7 @@ int f1l_set_config(f1l_handle h, const f1l_config* cfg) {
     if (r != F1L_OK) return r;
     if (cfg->n_samples != h->cfg.n_samples) h->has_prev = 0;
     h->cfg = *cfg;
+    h->epoch++;
     return F1L_OK;
 }
 
@@ -657,6 +677,7 @@ int f1l_destroy(f1l_handle h) {
         if (p.done) cudaEventDestroy(p.done);
         if (p.stream) cudaStreamDestroy(p.stream);
     }
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
     for (int i = 0; i < 4 * F1L_EV_SLOTS; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->h_in) cudaFreeHost(h->h_in);
@@ -713,6 +734,7 @@ int f1l_set_track(f1l_handle h, const double* wpts, int n, int ncols) {
     CK(cudaMemcpy(h->segA.p, segA.data(), segA.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->segB.p, segB.data(), segB.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->blk.p, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice));
+    h->epoch++;
     h->n = n;
     h->ncols = ncols;
     return F1L_OK;
@@ -741,6 +763,7 @@ int f1l_set_grid(f1l_handle h, const uint8_t* occ, int height, int width, double
     h->gw = width;
     h->gox = ox;
     h->goy = oy;
+    h->epoch++;
     h->gres = res;
     return F1L_OK;
 }
@@ -752,6 +775,7 @@ int f1l_clear_grid(f1l_handle h) {
     release(h->grid);
     release(h->clear);
     release(h->clear_tmp);
+    h->epoch++;
     h->gh = h->gw = 0;
     return F1L_OK;
 }
@@ -768,6 +792,7 @@ int f1l_set_goal_grid(f1l_handle h, const double* lookaheads, int nL, const doub
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(h->lookaheads.p, lookaheads, (size_t)nL * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->widths.p, wf.data(), (size_t)nW * 4, cudaMemcpyHostToDevice));
+    h->epoch++;
     h->nL = nL;
     h->nW = nW;
     return F1L_OK;
@@ -798,6 +823,7 @@ int f1l_set_lut(f1l_handle h, const float* lut, const int32_t dims[3], const dou
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(h->lut.p, lut, bytes, cudaMemcpyHostToDevice));
     for (int i = 0; i < 3; ++i) h->ldims[i] = dims[i];
+    h->epoch++;
     for (int i = 0; i < 6; ++i) h->lranges[i] = ranges[i];
     return F1L_OK;
 }
@@ -832,11 +858,13 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     const int M = h->cfg.n_samples;
     cudaStream_t st = h->stream;
 
-    // stage inputs (pinned) -> device
-    double* hin = (double*)h->h_in;
-    memcpy(hin, pose, 4 * sizeof(double));
-    if (n_opp) memcpy(hin + 4, opp, (size_t)n_opp * 3 * sizeof(double));
-    ENS(h->q_in, (4 + 3 * F1L_MAX_OPP) * sizeof(double));
+    // stage inputs (pinned)
+    QInput* hin = (QInput*)h->h_in;
+    memcpy(hin->pose, pose, 4 * sizeof(double));
+    hin->n_opp = n_opp;
+    hin->pad = 0;
+    if (n_opp) memcpy(hin->opp, opp, (size_t)n_opp * 3 * sizeof(double));
+    ENS(h->q_in, sizeof(QInput));
     ENS(h->q_ctx, sizeof(QueryCtx));
     ENS(h->q_centres, sizeof(Centre) * (size_t)(h->nL > 0 ? h->nL : 1));
     ENS(h->q_best, 8);
@@ -853,8 +881,6 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     if (out->params) ENS(h->q_params, (size_t)C * 16);
     if (out->states) ENS(h->q_states, (size_t)C * M * 16);
     if (out->headings) ENS(h->q_headings, (size_t)C * M * 8);
-    CK(cudaMemcpyAsync(h->q_in.p, hin, (4 + 3 * (size_t)n_opp) * sizeof(double),
-                       cudaMemcpyHostToDevice, st));
     const float4* d_goals = nullptr;
     if (goals) {
         std::vector<float> g4(4 * (size_t)C);
@@ -886,26 +912,60 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     o.states = out->states ? (float4*)h->q_states.p : nullptr;
     o.headings = out->headings ? (float2*)h->q_headings.p : nullptr;
     o.prev_out = update_prev ? (float*)h->prev.p : nullptr;
-    if (c_begin != 0 || (c_end > 0 && c_end < C)) {
-        // sharded evaluation: untouched candidates keep +inf / zero flags
-        fill_f32_kernel<<<(C + 255) / 256, 256, 0, st>>>((float*)h->q_costs.p, (size_t)C, INFINITY);
-        h->launches += 1;
-        if (o.flags) CK(cudaMemsetAsync(h->q_flags.p, 0, (size_t)C, st));
-    }
-    // the similarity term must read the previous path while select overwrites it: eval reads
-    // prev before select runs (stream order), so one buffer suffices.
-    int r = launch_pipeline(h, st, (const double*)h->q_in.p,
-                            n_opp ? (const double*)h->q_in.p + 4 : nullptr, nullptr, 1, n_opp,
-                            d_goals, C, c_begin, c_end, (QueryCtx*)h->q_ctx.p,
-                            (Centre*)h->q_centres.p, (unsigned long long*)h->q_best.p, nullptr,
-                            nullptr, h->has_prev ? (const float*)h->prev.p : nullptr, o,
-                            h->timing != 0);
-    if (r != F1L_OK) return r;
-
-    // results -> pinned staging -> caller
+    const bool sharded = c_begin != 0 || (c_end > 0 && c_end < C);
     QHeader* hd = (QHeader*)h->h_out;
     float* htraj = (float*)((char*)h->h_out + sizeof(QHeader));
-    CK(cudaMemcpyAsync(hd, h->q_res.p, sizeof(QHeader) + (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+    const QInput* din = (const QInput*)h->q_in.p;
+    // H2D of the input block, the three kernels, D2H of header + best trajectory.  The
+    // similarity term reads the previous path while select overwrites it: eval reads it before
+    // select runs (stream order), so one buffer suffices.
+    auto enqueue = [&](bool time_it) -> int {
+        CK(cudaMemcpyAsync(h->q_in.p, hin, sizeof(QInput), cudaMemcpyHostToDevice, st));
+        if (sharded) {
+            // sharded evaluation: untouched candidates keep +inf / zero flags
+            fill_f32_kernel<<<(C + 255) / 256, 256, 0, st>>>((float*)h->q_costs.p, (size_t)C, INFINITY);
+            h->launches += 1;
+            if (o.flags) CK(cudaMemsetAsync(h->q_flags.p, 0, (size_t)C, st));
+        }
+        int r = launch_pipeline(h, st, din->pose, din->opp, &din->n_opp, 1, F1L_MAX_OPP, d_goals, C,
+                                c_begin, c_end, (QueryCtx*)h->q_ctx.p, (Centre*)h->q_centres.p,
+                                (unsigned long long*)h->q_best.p, nullptr, nullptr,
+                                h->has_prev ? (const float*)h->prev.p : nullptr, o, time_it);
+        if (r != F1L_OK) return r;
+        CK(cudaMemcpyAsync(hd, h->q_res.p, sizeof(QHeader) + (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+        return F1L_OK;
+    };
+    if (h->use_graph && !goals && !sharded && !h->timing) {
+        // the whole chain as one CUDA graph, re-captured only when an upload / config change or
+        // the set of requested outputs alters a kernel argument
+        const unsigned long long mask = (out->terms ? 1u : 0u) | (out->flags ? 2u : 0u) |
+                                        (out->goals ? 4u : 0u) | (out->params ? 8u : 0u) |
+                                        (out->states ? 16u : 0u) | (out->headings ? 32u : 0u) |
+                                        (update_prev ? 64u : 0u) | (h->has_prev ? 128u : 0u);
+        if (!h->gexec || h->gkey[0] != h->epoch || h->gkey[1] != mask) {
+            if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+            const int64_t launches0 = h->launches;
+            cudaGraph_t graph = nullptr;
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            int r = enqueue(false);
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            h->launches = launches0;
+            if (r != F1L_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+            if (ce != cudaSuccess) return fail(h, ce, "cudaStreamEndCapture");
+            ce = cudaGraphInstantiate(&h->gexec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ce != cudaSuccess) { h->gexec = nullptr; return fail(h, ce, "cudaGraphInstantiate"); }
+            h->gkey[0] = h->epoch;
+            h->gkey[1] = mask;
+        }
+        CK(cudaGraphLaunch(h->gexec, st));
+        h->launches += 3;
+    } else {
+        int r = enqueue(h->timing != 0);
+        if (r != F1L_OK) return r;
+    }
+
+    // optional per-candidate arrays straight into the caller's buffers
     if (out->costs) CK(cudaMemcpyAsync(out->costs, h->q_costs.p, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
     if (out->terms) CK(cudaMemcpyAsync(out->terms, h->q_terms.p, (size_t)C * F1L_N_TERMS * 4, cudaMemcpyDeviceToHost, st));
     if (out->flags) CK(cudaMemcpyAsync(out->flags, h->q_flags.p, (size_t)C, cudaMemcpyDeviceToHost, st));

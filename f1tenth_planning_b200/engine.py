@@ -341,6 +341,10 @@ class Engine:
     def launch_count(self):
         return int(self._L.f1l_launch_count(self._h))
 
+    def set_graph(self, on):
+        """replay the single-query chain as a CUDA graph (default on)"""
+        self._ck(self._L.f1l_set_graph(self._h, int(bool(on))))
+
     def set_timing(self, on):
         self._ck(self._L.f1l_set_timing(self._h, int(bool(on))))
 

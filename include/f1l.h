@@ -249,6 +249,10 @@ int f1l_get_actuation_batch(f1l_handle h, const double* in, int n, double wheelb
 /* Timing / evidence helpers: number of kernels launched by this handle so far, and the device
  * time (ms, CUDA events on the handle's stream) of the kernels of the last host-pointer call. */
 int64_t f1l_launch_count(f1l_handle h);
+/* The single-query chain (input copy, sampler, eval, select, result copy) is replayed as one CUDA
+ * graph, re-captured when an upload / configuration change or the requested outputs change a
+ * kernel argument.  on = 0 falls back to plain stream launches (default: on). */
+int f1l_set_graph(f1l_handle h, int on);
 /* on != 0: f1l_plan* record CUDA events around their three kernels (read with
  * f1l_last_kernel_ms); off by default to keep the single-query latency minimal. */
 int f1l_set_timing(f1l_handle h, int on);

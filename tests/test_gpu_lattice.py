@@ -258,3 +258,33 @@ def test_real_track_and_map_fixtures(golden_spielberg):
             n_map += st["collide_map_count"]
             assert st["n_both_valid"] >= 5
         assert n_map > 0
+
+
+def test_cuda_graph_replay_matches_stream_launches(ellipse, corridor):
+    """the graph of the single-query chain gives bit-identical results, survives changes of pose,
+    opponent count, requested outputs, previous path and configuration"""
+    la, wd = synth.goal_grid(3)
+    eng, cfg, world = H.make_pair(ellipse, la[::2], wd[::2], grid=corridor)
+    poses, opp, n_opp = synth.scenario_batch(ellipse, 6, 8, 9)
+    outs = {}
+    for mode in (True, False):
+        eng.set_graph(mode)
+        eng.set_prev_path(None)
+        res = []
+        for s in range(6):
+            k = int(n_opp[s]) if s % 2 else 0
+            d = eng.plan(poses[s], opp[s, :k] if k else None, update_prev=(s != 3), detail=(s % 3 != 0),
+                         want_states=(s == 4))
+            res.append(d)
+        eng.configure(kappa_max=2.0)
+        res.append(eng.plan(poses[0], opp[0], update_prev=False))
+        eng.configure(kappa_max=cfg.kappa_max)
+        outs[mode] = res
+    for a, b in zip(outs[True], outs[False]):
+        assert a.best_idx == b.best_idx and a.best_cost == b.best_cost
+        assert a.steer == b.steer and a.speed == b.speed
+        assert np.array_equal(a.best_traj, b.best_traj)
+        if a.costs is not None:
+            assert np.array_equal(a.costs, b.costs) and np.array_equal(a.flags, b.flags)
+        if a.states is not None:
+            assert np.array_equal(a.states, b.states)
