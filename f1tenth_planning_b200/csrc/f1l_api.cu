@@ -67,7 +67,7 @@ struct f1l_ctx {
     DevBuf prev;
     int has_prev = 0, prev_m = 0;
     // single-query device buffers
-    DevBuf q_res, q_in, q_goals, q_ctx, q_centres, q_best, q_idx, q_cost, q_status, q_ss, q_traj, q_costs,
+    DevBuf q_res, q_in, q_goals, q_ctx, q_centres, q_best, q_costs,
         q_terms, q_flags, q_gout, q_params, q_states, q_headings;
     // pinned staging for the single query
     void* h_in = nullptr;   // pose + opponents
@@ -663,8 +663,7 @@ int f1l_destroy(f1l_handle h) {
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->xy, &h->v, &h->psi, &h->kappa, &h->segA, &h->segB, &h->blk, &h->grid, &h->clear, &h->clear_tmp,
                       &h->lut, &h->lookaheads, &h->widths, &h->prev, &h->q_res, &h->q_in, &h->q_goals,
-                      &h->q_ctx, &h->q_centres, &h->q_best, &h->q_idx, &h->q_cost, &h->q_status,
-                      &h->q_ss, &h->q_traj, &h->q_costs, &h->q_terms, &h->q_flags, &h->q_gout,
+                      &h->q_ctx, &h->q_centres, &h->q_best, &h->q_costs, &h->q_terms, &h->q_flags, &h->q_gout,
                       &h->q_params, &h->q_states, &h->q_headings, &h->b_ctx, &h->b_centres,
                       &h->b_best, &h->b_near_i, &h->b_near4, &h->m_in, &h->m_in2, &h->m_o0, &h->m_o1, &h->m_o2, &h->m_o3,
                       &h->m_o4, &h->m_o5};
@@ -868,11 +867,6 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     ENS(h->q_ctx, sizeof(QueryCtx));
     ENS(h->q_centres, sizeof(Centre) * (size_t)(h->nL > 0 ? h->nL : 1));
     ENS(h->q_best, 8);
-    ENS(h->q_idx, 4);
-    ENS(h->q_cost, 4);
-    ENS(h->q_status, 8);
-    ENS(h->q_ss, 16);
-    ENS(h->q_traj, F1L_MAX_M * sizeof(float4));
     ENS(h->q_costs, (size_t)C * 4);
     ENS(h->prev, F1L_MAX_M * sizeof(float));
     if (out->terms) ENS(h->q_terms, (size_t)C * F1L_N_TERMS * 4);
