@@ -131,10 +131,11 @@ __device__ __forceinline__ bool nearest_better(double d, int i, double bd, int b
     return d < bd || (d == bd && i < bi);
 }
 
-// python-style modulo
+// python-style modulo for the index range the scans use (-n <= a < 2n): no integer division
 __device__ __forceinline__ int pymod(int a, int n) {
-    int r = a % n;
-    return r < 0 ? r + n : r;
+    if (a < 0) a += n;
+    else if (a >= n) a -= n;
+    return a;
 }
 
 // accessor concept: P(i) returns double2 waypoint i
@@ -184,7 +185,7 @@ __device__ inline Intersect64 intersect_point64(const P& pts, int n, double qx, 
     Intersect64 o;
     o.px = 0.0; o.py = 0.0; o.t = 0.0; o.i = 0; o.found = 0;
     const int start_i = (int)t;                 // :78
-    const double start_t = fmod(t, 1.0);        // :79
+    const double start_t = t - (double)start_i;  // == t % 1.0 for t >= 0, exactly        // :79
     double t1, t2, vx, vy;
     for (int i = start_i; i < n - 1; ++i) {     // :84
         const double2 s = pts(i);
@@ -231,7 +232,7 @@ __device__ inline Intersect64 intersect_point_warp(const P& pts, int n, double q
     Intersect64 o;
     o.px = 0.0; o.py = 0.0; o.t = 0.0; o.i = 0; o.found = 0;
     const int start_i = (int)t;                 // :78
-    const double start_t = fmod(t, 1.0);        // :79
+    const double start_t = t - (double)start_i;  // == t % 1.0 for t >= 0, exactly        // :79
     for (int phase = 0; phase < (wrap ? 2 : 1); ++phase) {
         const int lo = phase == 0 ? start_i : -1;          // :84 / :125
         const int hi = phase == 0 ? n - 1 : start_i;       // exclusive

@@ -351,11 +351,14 @@ __device__ __forceinline__ void candidate_goal(const Centre* __restrict__ centre
 #define SAMPLE_THREADS 256        // batches of a few queries
 #define SAMPLE_THREADS_MAX 1024   // a single query gets one warp per ~2 lookahead rows
 
+// a wrapped into [-pi, pi): (a + pi) mod 2 pi - pi without the iterative fmod
 __device__ __forceinline__ double wrap_to_pi64(double a) {
-    const double two_pi = 6.283185307179586476925286766559;
-    a = fmod(a + 3.14159265358979323846, two_pi);
-    if (a < 0.0) a += two_pi;
-    return a - 3.14159265358979323846;
+    const double two_pi = 6.283185307179586476925286766559, pi = 3.14159265358979323846;
+    const double b = a + pi;
+    double r = b - two_pi * floor(b * (1.0 / two_pi));
+    if (r < 0.0) r += two_pi;
+    if (r >= two_pi) r -= two_pi;
+    return r - pi;
 }
 
 // everything after the nearest-point search, shared by the two sampler kernels.  `lt` / `nt`:
@@ -365,7 +368,8 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
     const double px = a.poses[4 * (size_t)s], py = a.poses[4 * (size_t)s + 1];
     const double pth = a.poses[4 * (size_t)s + 2], pv = a.poses[4 * (size_t)s + 3];
     const int nseg = a.tr.n - 1;
-    const double cth = cos(pth), sth = sin(pth);
+    double cth, sth;
+    sincos(pth, &sth, &cth);
 
     // one intersect_point per lookahead row (lattice_planner.py:249-251); a warp per row
     XYTrack acc{a.tr.xy};
@@ -387,8 +391,10 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
             ce.cy = ip.found ? (float)(-sth * dx + cth * dy) : 0.0f;
             ce.psi_rel = ip.found ? (float)prel : 0.0f;
             ce.kappa_g = (float)a.tr.kappa[r];
-            ce.nx = ip.found ? (float)(-sin(prel)) : 0.0f;
-            ce.ny = ip.found ? (float)cos(prel) : 0.0f;
+            double sp_, cp_;
+            sincos(prel, &sp_, &cp_);
+            ce.nx = ip.found ? (float)(-sp_) : 0.0f;
+            ce.ny = ip.found ? (float)cp_ : 0.0f;
             ce.v = (float)a.tr.v[r];
             ce.ok = ip.found ? 1.0f : 0.0f;
             a.centres[(size_t)s * a.nL + j] = ce;
@@ -402,8 +408,10 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
         if (k < n_opp) {
             const double* op = a.opp + 3 * ((size_t)s * a.max_opp + k);
             const double dx = op[0] - px, dy = op[1] - py, ph = op[2] - pth;
-            o = make_float4((float)(cth * dx + sth * dy), (float)(-sth * dx + cth * dy),
-                            (float)cos(ph), (float)sin(ph));
+            double so_, co_;
+            sincos(ph, &so_, &co_);
+            o = make_float4((float)(cth * dx + sth * dy), (float)(-sth * dx + cth * dy), (float)co_,
+                            (float)so_);
         }
         q->opp[k] = o;
     }
