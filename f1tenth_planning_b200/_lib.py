@@ -12,7 +12,8 @@ MAX_M = 256
 FLAG_VALID, FLAG_COLLIDE_OPP, FLAG_COLLIDE_MAP, FLAG_NO_CENTRE = 1, 2, 4, 8
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libf1l.so")
+# F1L_LIB selects another build of the same library (A/B builds of kernel variants)
+LIB_PATH = os.environ.get("F1L_LIB") or os.path.join(HERE, "lib", "libf1l.so")
 
 _dp = C.POINTER(C.c_double)
 _fp = C.POINTER(C.c_float)

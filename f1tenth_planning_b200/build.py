@@ -26,14 +26,19 @@ def is_stale():
     return any(os.path.getmtime(os.path.join(SRC_DIR, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    if not force and not is_stale():
+def build(force=False, verbose=False, out=None, defs=()):
+    """`out` / `defs`: an A/B build of a kernel variant (-D switches) next to the product library."""
+    if out is None and not force and not is_stale():
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
+    return _compile(out or OUT, verbose, defs)
+
+
+def _compile(OUT, verbose, defs):
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
            "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "177",
            "-o", OUT] + [os.path.join(SRC_DIR, s) for s in SOURCES]
-    for d in os.environ.get("F1L_NVCC_DEFS", "").split():
+    for d in list(defs) + os.environ.get("F1L_NVCC_DEFS", "").split():
         cmd.insert(1, "-D" + d)   # e.g. F1L_NVCC_DEFS="EVAL_MIN_BLOCKS=4" for build-time experiments
     if verbose:
         cmd.insert(1, "-Xptxas")

@@ -205,10 +205,15 @@ struct EvalShape {
     int ipl, s, sg;
 };
 
+// deviation-pass shape of the M <= 104 kernels: S samples per lane x SG sample groups (A/B switch)
+#ifndef EVAL_S104
+#define EVAL_S104 13
+#define EVAL_SG104 8
+#endif
 EvalShape eval_shape(int M) {
     if (M <= 32) return {1, 4, 8};
     if (M <= 64) return {2, 8, 8};
-    if (M <= 104) return {4, 13, 8};
+    if (M <= 104) return {4, EVAL_S104, EVAL_SG104};
     if (M <= 128) return {4, 16, 8};
     if (M <= 208) return {7, 13, 16};
     return {8, 16, 16};
@@ -230,14 +235,14 @@ eval_fn eval_entry(int M, int nw) {
     if (nw == 7) {
         if (M <= 32) return eval_kernel<1, 4, 8, 7, EVAL_MINB7>;
         if (M <= 64) return eval_kernel<2, 8, 8, 7, EVAL_MINB7>;
-        if (M <= 104) return eval_kernel<4, 13, 8, 7, EVAL_MINB7>;
+        if (M <= 104) return eval_kernel<4, EVAL_S104, EVAL_SG104, 7, EVAL_MINB7>;
         if (M <= 128) return eval_kernel<4, 16, 8, 7, EVAL_MINB7>;
         if (M <= 208) return eval_kernel<7, 13, 16, 7, EVAL_MINB7>;
         return eval_kernel<8, 16, 16, 7, EVAL_MINB7>;
     }
     if (M <= 32) return eval_kernel<1, 4, 8, 8, EVAL_MINB8>;
     if (M <= 64) return eval_kernel<2, 8, 8, 8, EVAL_MINB8>;
-    if (M <= 104) return eval_kernel<4, 13, 8, 8, EVAL_MINB8>;
+    if (M <= 104) return eval_kernel<4, EVAL_S104, EVAL_SG104, 8, EVAL_MINB8>;
     if (M <= 128) return eval_kernel<4, 16, 8, 8, EVAL_MINB8>;
     if (M <= 208) return eval_kernel<7, 13, 16, 8, EVAL_MINB8>;
     return eval_kernel<8, 16, 16, 8, EVAL_MINB8>;

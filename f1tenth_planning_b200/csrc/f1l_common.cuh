@@ -330,6 +330,18 @@ __device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b) {
     return d;
 }
 
+// three-input max / min (sm_100 FMNMX3, one ALU-pipe instruction)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // warp helpers
 // ---------------------------------------------------------------------------------------------

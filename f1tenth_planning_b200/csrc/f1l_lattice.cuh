@@ -78,8 +78,9 @@ __device__ __forceinline__ void warp_allreduce8(float (&v)[8], int lane) {
 
 // Up to `iters` Newton steps q <- q - J^-1 r, whole warp, lane = Simpson node (lane+1)/32 (node 0
 // is analytic: cos 0 = 1 and every other integrand vanishes there).  The loop leaves as soon as
-// the residual of the current iterate is at the FP32 noise floor (warp-uniform: the whole warp
-// works on one candidate), so a LUT-seeded candidate typically spends 3-4 passes, not `iters`.
+// the residual of the current iterate is at the FP32 noise floor, or right after a step taken
+// from a residual small enough that the step itself reaches it (warp-uniform: the whole warp
+// works on one candidate), so a LUT-seeded candidate typically spends 2-3 passes, not `iters`.
 // Returns the number of quadrature passes done.
 __device__ __forceinline__ int spiral_newton(SpiralF& sp, float gx, float gy, float gth,
                                              int iters, int lane) {
@@ -88,7 +89,11 @@ __device__ __forceinline__ int spiral_newton(SpiralF& sp, float gx, float gy, fl
     const float u2 = u * u;
     const float d1 = u2 * fmaf(u, fmaf(u, 3.375f, -7.5f), 4.5f);
     const float d2 = u2 * fmaf(u, fmaf(u, -3.375f, 6.0f), -2.25f);
-    const float eps = 1.5e-6f * fmaxf(1.0f, fmaxf(fabsf(gx), fmaxf(fabsf(gy), fabsf(gth))));
+    const float gmax = fmaxf(1.0f, fmaxf(fabsf(gx), fmaxf(fabsf(gy), fabsf(gth))));
+    const float eps = 1.5e-6f * gmax;
+    // Newton converges quadratically: a step taken from a residual below eps_step lands below
+    // the noise floor, so its result is accepted without another quadrature pass to confirm it
+    const float eps_step = 2e-4f * gmax;
     int it = 0;
     for (; it < iters; ++it) {
         spiral_set(sp);
@@ -103,7 +108,8 @@ __device__ __forceinline__ int spiral_newton(SpiralF& sp, float gx, float gy, fl
         const float sf = sp.sf, sf2 = sf * sf;
         const float g1 = 0.125f * (sp.p0 + 3.0f * sp.p1 + 3.0f * sp.p2 + sp.p3);
         const float r0 = fmaf(sf, C0, -gx), r1 = fmaf(sf, S0, -gy), r2 = fmaf(sf, g1, -gth);
-        if (fmaxf(fabsf(r0), fmaxf(fabsf(r1), fabsf(r2))) < eps) { ++it; break; }
+        const float rmax = fmaxf(fabsf(r0), fmaxf(fabsf(r1), fabsf(r2)));
+        if (rmax < eps) { ++it; break; }
         const float J00 = -sf2 * S1, J01 = -sf2 * S2, J02 = fmaf(-sf, Sg, C0);
         const float J10 = sf2 * C1, J11 = sf2 * C2, J12 = fmaf(sf, Cg, S0);
         const float J20 = 0.375f * sf, J21 = J20, J22 = g1;
@@ -117,12 +123,13 @@ __device__ __forceinline__ int spiral_newton(SpiralF& sp, float gx, float gy, fl
         sp.p1 -= dq0;
         sp.p2 -= dq1;
         sp.sf -= dq2;
+        if (rmax < eps_step) { ++it; break; }
     }
     spiral_set(sp);
     return it;
 }
 
-// nearest-cell LUT seed
+// nearest-cell LUT seed (the seed the oracle starts from)
 __device__ __forceinline__ float4 lut_lookup(const LutView& lut, float gx, float gy, float gth) {
     int ix = __float2int_rd(fmaf(gx - lut.x0, lut.sx, 0.5f));
     int iy = __float2int_rd(fmaf(gy - lut.y0, lut.sy, 0.5f));
@@ -131,6 +138,36 @@ __device__ __forceinline__ float4 lut_lookup(const LutView& lut, float gx, float
     iy = min(max(iy, 0), lut.ny - 1);
     it = min(max(it, 0), lut.nt - 1);
     return __ldg(lut.cells + ((size_t)ix * lut.ny + iy) * lut.nt + it);
+}
+
+// Trilinear LUT seed, whole warp: lane & 7 owns one corner of the goal's cell, three xor steps sum
+// the weighted corners on every lane.  The converged cells are samples of one smooth solution
+// family, so the interpolated seed lies in the same Newton basin as the nearest cell (the
+// oracle's seed) but an order closer to the root: one quadrature pass fewer.  Goals outside the
+// table or next to a non-converged cell fall back to the nearest cell.
+__device__ __forceinline__ float4 lut_seed(const LutView& lut, float gx, float gy, float gth,
+                                           int lane) {
+    const float fx = (gx - lut.x0) * lut.sx, fy = (gy - lut.y0) * lut.sy, ft = (gth - lut.t0) * lut.st;
+    const bool inside = lut.nx > 1 && lut.ny > 1 && lut.nt > 1 && fx >= 0.0f && fy >= 0.0f &&
+                        ft >= 0.0f && fx <= (float)(lut.nx - 1) && fy <= (float)(lut.ny - 1) &&
+                        ft <= (float)(lut.nt - 1);
+    if (inside) {   // warp-uniform: the warp works on one goal
+        const int ix = min(__float2int_rd(fx), lut.nx - 2), iy = min(__float2int_rd(fy), lut.ny - 2);
+        const int it = min(__float2int_rd(ft), lut.nt - 2);
+        const float wx = fx - (float)ix, wy = fy - (float)iy, wt = ft - (float)it;
+        const int cx = lane & 1, cy = (lane >> 1) & 1, ct = (lane >> 2) & 1;
+        const float4 cell = __ldg(lut.cells + ((size_t)(ix + cx) * lut.ny + (iy + cy)) * lut.nt + (it + ct));
+        const float w = (cx ? wx : 1.0f - wx) * (cy ? wy : 1.0f - wy) * (ct ? wt : 1.0f - wt);
+        float a = w * cell.x, b = w * cell.y, c = w * cell.z;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            a += __shfl_xor_sync(F1L_FULL, a, o);
+            b += __shfl_xor_sync(F1L_FULL, b, o);
+            c += __shfl_xor_sync(F1L_FULL, c, o);
+        }
+        if (__all_sync(F1L_FULL, cell.w != 0.0f)) return make_float4(a, b, c, 1.0f);
+    }
+    return lut_lookup(lut, gx, gy, gth);
 }
 
 // G1 Hermite clothoid from (0,0,0) to the goal -- the generator the reference calls
@@ -195,7 +232,7 @@ __device__ __forceinline__ int generate_spiral(SpiralF& sp, const LutView& lut, 
     if (ep.generator == 1) return clothoid_g1(sp, gx, gy, gth, ep.n_newton, lane);
     sp.p0 = 0.0f;
     sp.p3 = p3;
-    const float4 seed = lut_lookup(lut, gx, gy, gth);
+    const float4 seed = lut_seed(lut, gx, gy, gth, lane);
     sp.p1 = seed.x; sp.p2 = seed.y; sp.sf = seed.z;
     return spiral_newton(sp, gx, gy, gth, ep.n_newton, lane);
 }
@@ -538,13 +575,117 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     return r;
 }
 
-#ifndef EVAL_CLAMP_ALU
-#define EVAL_CLAMP_ALU 0
+// deviation-loop variant: how |e| = |q - clamp(q, 0, len)| is formed
+//   0  e = q - sat(q / len) * len        FMUL.SAT + FFMA2: 8 FMA-pipe cycles per sample x segment
+//   1  e = q - min(max(q, 0), len)       two FMNMX + FADD2: 7 FMA-pipe, 3 ALU instructions
+//   2  e = max(-q, q - len, 0)           FADD2 + one three-input FMNMX3 (sm_100): 7 FMA-pipe, 2 ALU
+//   3  e = sat(|q - h| - h), h = len/2   one FADD.SAT with an |.| operand modifier: 7 FMA-pipe, no
+//                                        ALU instruction and the fewest register-operand reads.
+//                                        The table holds q's constant with h folded in, and all
+//                                        lengths in units of EVAL_DEV_UNIT metres so that the
+//                                        saturation (clamp to [0, 1]) only ever acts at 0.
+// The loop is bound by register-file operand bandwidth (about two 32-bit operands per lane per
+// clock, measured: tools/microbench/rf_bench.cu), not by the FMA pipe, so operand reads count.
+#ifndef EVAL_DEV_MODE
+#define EVAL_DEV_MODE 3
+#endif
+// order of the packed instructions of one segment step: 0 = sample pair after sample pair,
+// 1 = operation-major over groups of three pairs (consecutive instructions share their segment
+// constants, which then come from the operand reuse cache instead of the register file)
+#ifndef EVAL_DEV_ORDER
+#define EVAL_DEV_ORDER 1
+#endif
+#define EVAL_DEV_UNIT 16384.0f   // metres per table unit (a power of two: the scaling is exact)
+#if EVAL_DEV_MODE == 3
+#define EVAL_DEV_SCALE (1.0f / EVAL_DEV_UNIT)
+#else
+#define EVAL_DEV_SCALE 1.0f
+#endif
+#ifndef EVAL_DEV_MIN3
+#define EVAL_DEV_MIN3 0
 #endif
 #ifndef EVAL_SEG_UNROLL
 #define EVAL_SEG_UNROLL 2
 #endif
 #define EVAL_SEG_PAD 32   // readable slack behind the window tables (software-pipelined loads)
+
+// |e| of a packed pair from its q (see the mode table above)
+__device__ __forceinline__ f32x2 seg_axis_excess(f32x2 q2, const float4& T0, const float4& T1) {
+    float qa, qb;
+    unpack2(q2, qa, qb);
+#if EVAL_DEV_MODE == 3
+    return pack2(__saturatef(fabsf(qa) + T1.z), __saturatef(fabsf(qb) + T1.z));
+#elif EVAL_DEV_MODE == 2
+    float ra, rb;
+    unpack2(fadd2(q2, pack2(T1.z, T1.z)), ra, rb);
+    return pack2(fmax3(-qa, ra, 0.0f), fmax3(-qb, rb, 0.0f));
+#elif EVAL_DEV_MODE == 1
+    return fadd2(q2, pack2(-fminf(fmaxf(qa, 0.0f), -T1.z), -fminf(fmaxf(qb, 0.0f), -T1.z)));
+#else
+    return ffma2(pack2(__saturatef(qa * T0.w), __saturatef(qb * T0.w)), pack2(T1.z, T1.z), q2);
+#endif
+}
+
+// squared distance of a packed pair of samples (sx, sy) to one window segment in line form
+// T0 = (ux, uy, -uy, 1/len), T1 = (-a.u, -a.n, -len, 0):  q = p.u - a.u, n = p.n - a.n,
+// e = distance of q to [0, len], d^2 = e^2 + n^2  (nearest_point, utils.py:53-65, without the
+// division and the square root).  Segment constants enter FFMA2 as scalar-broadcast operands.
+// Mode 3: T1 = (-(a.u + h), -a.n, -h, 0) with h = len / 2, samples and T1 in table units.
+__device__ __forceinline__ f32x2 seg_dist2_pair(f32x2 sx, f32x2 sy, const float4& T0,
+                                                const float4& T1) {
+    const f32x2 ux = pack2(T0.x, T0.x), uy = pack2(T0.y, T0.y);
+    const f32x2 nuy = pack2(T0.z, T0.z), nc = pack2(T1.x, T1.x);
+    const f32x2 ne = pack2(T1.y, T1.y);
+    const f32x2 q2 = ffma2(sx, ux, ffma2(sy, uy, nc));
+    const f32x2 n2 = ffma2(sy, ux, ffma2(sx, nuy, ne));
+    const f32x2 e2 = seg_axis_excess(q2, T0, T1);
+    return ffma2(e2, e2, fmul2(n2, n2));
+}
+__device__ __forceinline__ float seg_dist2(float sx, float sy, const float4& T0, const float4& T1) {
+    const float qq = fmaf(sx, T0.x, fmaf(sy, T0.y, T1.x));
+    const float nn = fmaf(sy, T0.x, fmaf(sx, T0.z, T1.y));
+#if EVAL_DEV_MODE == 3
+    const float e = __saturatef(fabsf(qq) + T1.z);
+#elif EVAL_DEV_MODE == 2
+    const float e = fmax3(-qq, qq + T1.z, 0.0f);
+#elif EVAL_DEV_MODE == 1
+    const float e = qq - fminf(fmaxf(qq, 0.0f), -T1.z);
+#else
+    const float e = fmaf(__saturatef(qq * T0.w), T1.z, qq);
+#endif
+    return fmaf(e, e, nn * nn);
+}
+
+// squared distances of all SP sample pairs of a lane to one segment
+template <int SP>
+__device__ __forceinline__ void seg_step(const f32x2 (&sx2)[SP], const f32x2 (&sy2)[SP],
+                                         const float4& T0, const float4& T1, f32x2 (&d)[SP]) {
+#if EVAL_DEV_ORDER == 1
+    const f32x2 ux = pack2(T0.x, T0.x), uy = pack2(T0.y, T0.y);
+    const f32x2 nuy = pack2(T0.z, T0.z), nc = pack2(T1.x, T1.x), ne = pack2(T1.y, T1.y);
+#pragma unroll
+    for (int j0 = 0; j0 < SP; j0 += 3) {
+        f32x2 q[3], n[3], e[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) if (j0 + j < SP) q[j] = ffma2(sy2[j0 + j], uy, nc);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) if (j0 + j < SP) n[j] = ffma2(sx2[j0 + j], nuy, ne);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) if (j0 + j < SP) q[j] = ffma2(sx2[j0 + j], ux, q[j]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) if (j0 + j < SP) n[j] = ffma2(sy2[j0 + j], ux, n[j]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) if (j0 + j < SP) e[j] = seg_axis_excess(q[j], T0, T1);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) if (j0 + j < SP) n[j] = fmul2(n[j], n[j]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) if (j0 + j < SP) d[j0 + j] = ffma2(e[j], e[j], n[j]);
+    }
+#else
+#pragma unroll
+    for (int j = 0; j < SP; ++j) d[j] = seg_dist2_pair(sx2[j], sy2[j], T0, T1);
+#endif
+}
 
 // One CTA per (scenario, candidate chunk).  The CTA builds the scenario's raceline window once,
 // then its NW warps pull candidates of the chunk from a shared counter until it is exhausted
@@ -586,7 +727,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
         const int seg0 = q->seg0, nseg = q->nseg, ns = a.tr.n - 1;
         for (int k = tid; k < ntab; k += NW * 32) {
             float4 T0 = make_float4(1.0f, 0.0f, -0.0f, 1.0f);      // padding: far away, finite
+#if EVAL_DEV_MODE == 3
+            float4 T1 = make_float4(-1e9f, -1e9f, -1.0f, 0.0f);    // (table units) d^2 = 1e18
+#else
             float4 T1 = make_float4(-1e15f, -1e15f, -1.0f, 0.0f);
+#endif
             if (k < nseg) {
                 int sg = seg0 + k;
                 if (sg >= ns) sg -= ns;
@@ -599,7 +744,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 const float il = rsqrtf(l2);
                 const float ux = dx * il, uy = dy * il;
                 T0 = make_float4(ux, uy, -uy, il);
+#if EVAL_DEV_MODE == 3
+                const float hh = 0.5f * (l2 * il);
+                T1 = make_float4(-(fmaf(avx, ux, avy * uy) + hh) * EVAL_DEV_SCALE,
+                                 -fmaf(avy, ux, -avx * uy) * EVAL_DEV_SCALE, -hh * EVAL_DEV_SCALE, 0.0f);
+#else
                 T1 = make_float4(-fmaf(avx, ux, avy * uy), -fmaf(avy, ux, -avx * uy), -(l2 * il), 0.0f);
+#endif
             }
             sT[2 * k] = T0;
             sT[2 * k + 1] = T1;
@@ -668,8 +819,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 {
                     const int r = i / SG, g = i - r * SG;
                     const int at = ((r >> 1) * SG + g) * 2 + (r & 1);
-                    slab_x[at] = x[j];
-                    slab_y[at] = y[j];
+                    slab_x[at] = x[j] * EVAL_DEV_SCALE;
+                    slab_y[at] = y[j] * EVAL_DEV_SCALE;
                 }
                 if (i == M - 1) { ex = x[j]; ey = y[j]; eth = th[j]; }
             }
@@ -816,44 +967,54 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 }
                 const int nq = a.nseg_pad;
                 float4 T0 = sT[2 * ggi], T1 = sT[2 * ggi + 1];
+#if EVAL_DEV_MIN3
+                // two segments per trip: the running minimum takes both distances in one
+                // three-input FMNMX3 (nseg_pad / GG is a multiple of 8)
+                for (int k = ggi; k < nq; k += 2 * GG) {
+                    const float4 B0 = sT[2 * (k + GG)], B1 = sT[2 * (k + GG) + 1];
+#if EVAL_DEV_MIN3 == 1
+                    const float4 N0 = sT[2 * (k + 2 * GG)];   // EVAL_SEG_PAD entries of slack
+                    const float4 N1 = sT[2 * (k + 2 * GG) + 1];
+#endif
+                    f32x2 dA[SP > 0 ? SP : 1], dB[SP > 0 ? SP : 1];
+                    seg_step<SP>(sx2, sy2, T0, T1, dA);
+                    seg_step<SP>(sx2, sy2, B0, B1, dB);
+#pragma unroll
+                    for (int j = 0; j < SP; ++j) {
+                        float da, db, ea, eb;
+                        unpack2(dA[j], da, db);
+                        unpack2(dB[j], ea, eb);
+                        bdx[j] = fmin3(bdx[j], da, ea);
+                        bdy[j] = fmin3(bdy[j], db, eb);
+                    }
+                    if (ODD) bdl = fmin3(bdl, seg_dist2(sxl, syl, T0, T1), seg_dist2(sxl, syl, B0, B1));
+#if EVAL_DEV_MIN3 == 1
+                    T0 = N0;
+                    T1 = N1;
+#else
+                    T0 = sT[2 * (k + 2 * GG)];   // EVAL_SEG_PAD entries of slack
+                    T1 = sT[2 * (k + 2 * GG) + 1];
+#endif
+                }
+#else
 #pragma unroll kSegUnroll
                 for (int k = ggi; k < nq; k += GG) {
                     const float4 N0 = sT[2 * (k + GG)];       // EVAL_SEG_PAD entries of slack
                     const float4 N1 = sT[2 * (k + GG) + 1];
-                    const f32x2 ux = pack2(T0.x, T0.x), uy = pack2(T0.y, T0.y);
-                    const f32x2 nuy = pack2(T0.z, T0.z), nc = pack2(T1.x, T1.x);
-                    const f32x2 ne = pack2(T1.y, T1.y), nlen = pack2(T1.z, T1.z);
+                    f32x2 dA[SP > 0 ? SP : 1];
+                    seg_step<SP>(sx2, sy2, T0, T1, dA);
 #pragma unroll
                     for (int j = 0; j < SP; ++j) {
-                        const f32x2 q2 = ffma2(sx2[j], ux, ffma2(sy2[j], uy, nc));
-                        const f32x2 n2 = ffma2(sy2[j], ux, ffma2(sx2[j], nuy, ne));
-                        float qa, qb;
-                        unpack2(q2, qa, qb);
-#if EVAL_CLAMP_ALU
-                        // e = q - clamp(q, 0, len): the clamp on the ALU pipe (FMNMX), one packed
-                        // add on the FMA pipe -- 7 instead of 8 FMA-pipe cycles per sample
-                        const f32x2 m2 = pack2(-fminf(fmaxf(qa, 0.0f), -T1.z), -fminf(fmaxf(qb, 0.0f), -T1.z));
-                        const f32x2 e2 = fadd2(q2, m2);
-#else
-                        const f32x2 t2 = pack2(__saturatef(qa * T0.w), __saturatef(qb * T0.w));
-                        const f32x2 e2 = ffma2(t2, nlen, q2);
-#endif
-                        const f32x2 d2 = ffma2(e2, e2, fmul2(n2, n2));
                         float da, db;
-                        unpack2(d2, da, db);
+                        unpack2(dA[j], da, db);
                         bdx[j] = fminf(bdx[j], da);
                         bdy[j] = fminf(bdy[j], db);
                     }
-                    if (ODD) {
-                        const float qq = fmaf(sxl, T0.x, fmaf(syl, T0.y, T1.x));
-                        const float nn = fmaf(syl, T0.x, fmaf(sxl, T0.z, T1.y));
-                        const float t = __saturatef(qq * T0.w);
-                        const float e = fmaf(t, T1.z, qq);
-                        bdl = fminf(bdl, fmaf(e, e, nn * nn));
-                    }
+                    if (ODD) bdl = fminf(bdl, seg_dist2(sxl, syl, T0, T1));
                     T0 = N0;
                     T1 = N1;
                 }
+#endif
 #pragma unroll
                 for (int o = 1; o < GG; o <<= 1) {
 #pragma unroll
@@ -873,7 +1034,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                     dsum += (ib < M) ? fast_sqrt(bdy[j]) : 0.0f;
                 }
                 if (ODD) dsum += ((S - 1) * SG + sgi < M) ? fast_sqrt(bdl) : 0.0f;
-                t_dev = warp_sum(dsum) * (1.0f / (float)GG) / (float)M;
+                t_dev = warp_sum(dsum) * ((1.0f / EVAL_DEV_SCALE) / (float)GG) / (float)M;
             }
 
             if (!(flags & (F1L_FLAG_COLLIDE_OPP | F1L_FLAG_COLLIDE_MAP))) {
