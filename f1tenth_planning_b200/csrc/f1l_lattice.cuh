@@ -601,8 +601,11 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 #else
 #define EVAL_DEV_SCALE 1.0f
 #endif
+// segments per trip of the deviation loop: 0 = one (FMNMX per sample), 1 / 2 = two, the running
+// minimum taking both distances in one FMNMX3 (1: next trip's table entries prefetched into
+// registers, 2: loaded at the end of the trip -- fewer live registers, measured faster)
 #ifndef EVAL_DEV_MIN3
-#define EVAL_DEV_MIN3 0
+#define EVAL_DEV_MIN3 2
 #endif
 #ifndef EVAL_SEG_UNROLL
 #define EVAL_SEG_UNROLL 2
@@ -656,35 +659,76 @@ __device__ __forceinline__ float seg_dist2(float sx, float sy, const float4& T0,
     return fmaf(e, e, nn * nn);
 }
 
-// squared distances of all SP sample pairs of a lane to one segment
-template <int SP>
-__device__ __forceinline__ void seg_step(const f32x2 (&sx2)[SP], const f32x2 (&sy2)[SP],
-                                         const float4& T0, const float4& T1, f32x2 (&d)[SP]) {
+// squared distances of the sample pairs [J0, J0 + 3) of a lane to one segment
+#define EVAL_DEV_GROUP 3
+template <int SP, int J0>
+__device__ __forceinline__ void seg_group(const f32x2 (&sx2)[SP], const f32x2 (&sy2)[SP],
+                                          const float4& T0, const float4& T1,
+                                          f32x2 (&d)[EVAL_DEV_GROUP]) {
 #if EVAL_DEV_ORDER == 1
     const f32x2 ux = pack2(T0.x, T0.x), uy = pack2(T0.y, T0.y);
     const f32x2 nuy = pack2(T0.z, T0.z), nc = pack2(T1.x, T1.x), ne = pack2(T1.y, T1.y);
+    f32x2 q[EVAL_DEV_GROUP], n[EVAL_DEV_GROUP], e[EVAL_DEV_GROUP];
 #pragma unroll
-    for (int j0 = 0; j0 < SP; j0 += 3) {
-        f32x2 q[3], n[3], e[3];
+    for (int j = 0; j < EVAL_DEV_GROUP; ++j) if (J0 + j < SP) q[j] = ffma2(sy2[J0 + j], uy, nc);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) if (j0 + j < SP) q[j] = ffma2(sy2[j0 + j], uy, nc);
+    for (int j = 0; j < EVAL_DEV_GROUP; ++j) if (J0 + j < SP) n[j] = ffma2(sx2[J0 + j], nuy, ne);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) if (j0 + j < SP) n[j] = ffma2(sx2[j0 + j], nuy, ne);
+    for (int j = 0; j < EVAL_DEV_GROUP; ++j) if (J0 + j < SP) q[j] = ffma2(sx2[J0 + j], ux, q[j]);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) if (j0 + j < SP) q[j] = ffma2(sx2[j0 + j], ux, q[j]);
+    for (int j = 0; j < EVAL_DEV_GROUP; ++j) if (J0 + j < SP) n[j] = ffma2(sy2[J0 + j], ux, n[j]);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) if (j0 + j < SP) n[j] = ffma2(sy2[j0 + j], ux, n[j]);
+    for (int j = 0; j < EVAL_DEV_GROUP; ++j) if (J0 + j < SP) e[j] = seg_axis_excess(q[j], T0, T1);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) if (j0 + j < SP) e[j] = seg_axis_excess(q[j], T0, T1);
+    for (int j = 0; j < EVAL_DEV_GROUP; ++j) if (J0 + j < SP) n[j] = fmul2(n[j], n[j]);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) if (j0 + j < SP) n[j] = fmul2(n[j], n[j]);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) if (j0 + j < SP) d[j0 + j] = ffma2(e[j], e[j], n[j]);
-    }
+    for (int j = 0; j < EVAL_DEV_GROUP; ++j) if (J0 + j < SP) d[j] = ffma2(e[j], e[j], n[j]);
 #else
 #pragma unroll
-    for (int j = 0; j < SP; ++j) d[j] = seg_dist2_pair(sx2[j], sy2[j], T0, T1);
+    for (int j = 0; j < EVAL_DEV_GROUP; ++j)
+        if (J0 + j < SP) d[j] = seg_dist2_pair(sx2[J0 + j], sy2[J0 + j], T0, T1);
 #endif
+}
+
+// running minima of all SP sample pairs of a lane over one segment (A) or two (A and B: the
+// minimum takes both distances in one three-input FMNMX3)
+template <int SP, int J0 = 0>
+__device__ __forceinline__ void seg_min1(const f32x2 (&sx2)[SP], const f32x2 (&sy2)[SP],
+                                         const float4& A0, const float4& A1, float (&bdx)[SP],
+                                         float (&bdy)[SP]) {
+    if constexpr (J0 < SP) {
+        f32x2 dA[EVAL_DEV_GROUP];
+        seg_group<SP, J0>(sx2, sy2, A0, A1, dA);
+#pragma unroll
+        for (int j = 0; j < EVAL_DEV_GROUP; ++j)
+            if (J0 + j < SP) {
+                float da, db;
+                unpack2(dA[j], da, db);
+                bdx[J0 + j] = fminf(bdx[J0 + j], da);
+                bdy[J0 + j] = fminf(bdy[J0 + j], db);
+            }
+        seg_min1<SP, J0 + EVAL_DEV_GROUP>(sx2, sy2, A0, A1, bdx, bdy);
+    }
+}
+template <int SP, int J0 = 0>
+__device__ __forceinline__ void seg_min2(const f32x2 (&sx2)[SP], const f32x2 (&sy2)[SP],
+                                         const float4& A0, const float4& A1, const float4& B0,
+                                         const float4& B1, float (&bdx)[SP], float (&bdy)[SP]) {
+    if constexpr (J0 < SP) {
+        f32x2 dA[EVAL_DEV_GROUP], dB[EVAL_DEV_GROUP];
+        seg_group<SP, J0>(sx2, sy2, A0, A1, dA);
+        seg_group<SP, J0>(sx2, sy2, B0, B1, dB);
+#pragma unroll
+        for (int j = 0; j < EVAL_DEV_GROUP; ++j)
+            if (J0 + j < SP) {
+                float da, db, ea, eb;
+                unpack2(dA[j], da, db);
+                unpack2(dB[j], ea, eb);
+                bdx[J0 + j] = fmin3(bdx[J0 + j], da, ea);
+                bdy[J0 + j] = fmin3(bdy[J0 + j], db, eb);
+            }
+        seg_min2<SP, J0 + EVAL_DEV_GROUP>(sx2, sy2, A0, A1, B0, B1, bdx, bdy);
+    }
 }
 
 // One CTA per (scenario, candidate chunk).  The CTA builds the scenario's raceline window once,
@@ -841,13 +885,26 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
         unsigned flags = valid ? F1L_FLAG_VALID : 0u;
         if (!have_centre) flags |= F1L_FLAG_NO_CENTRE;
         flags |= (unsigned)min(n_pass, 15) << F1L_FLAG_PASS_SHIFT;
-        float t_len = 0.0f, t_maxk = 0.0f, t_meank = 0.0f, t_sim = 0.0f, t_dev = 0.0f;
+        // everything the deviation pass does not need leaves the registers before it starts:
+        // goal / parameter outputs now, the first four cost terms as one partial sum
+        if (lane == 0) {
+            if (a.goals_out) {
+                float* g = a.goals_out + cand * 3;
+                g[0] = gx; g[1] = gy; g[2] = gth;
+            }
+            if (a.params)   // cubic: (p1, p2, s_f, p3); clothoid: (kappa0, dkappa, L, kappa_end)
+                a.params[cand] = a.ep.generator == 1
+                                     ? make_float4(sp.p0, __fdividef(sp.b1, sp.sf), sp.sf, sp.p3)
+                                     : make_float4(sp.p1, sp.p2, sp.sf, sp.p3);
+        }
+        float t_dev = 0.0f, partial = 0.0f;
         float cost = CUDART_INF_F;
 
         if (valid) {  // warp-uniform
-            t_len = __fdividef(1.0f, sp.sf);       // lattice_planner.py:271
-            t_maxk = maxk;                         // :277
-            t_meank = sumk / (float)M;             // :284
+            const float t_len = __fdividef(1.0f, sp.sf);       // lattice_planner.py:271
+            const float t_maxk = maxk;                         // :277
+            const float t_meank = sumk / (float)M;             // :284
+            float t_sim = 0.0f;
 
             // ---- similarity (lattice_planner.py:287-296), collision ----
             float sim = 0.0f;
@@ -938,6 +995,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             hit_map = __any_sync(F1L_FULL, hit_map);
             if (hit_opp) flags |= F1L_FLAG_COLLIDE_OPP;
             if (hit_map) flags |= F1L_FLAG_COLLIDE_MAP;
+            partial = a.ep.w[0] * t_len + a.ep.w[1] * t_maxk + a.ep.w[2] * t_meank + a.ep.w[3] * t_sim;
+            if (lane == 0 && a.terms) {
+                float* t = a.terms + cand * F1L_N_TERMS;
+                t[0] = t_len; t[1] = t_maxk; t[2] = t_meank; t[3] = t_sim;
+            }
 
             // ---- raceline deviation: mean over samples of the nearest distance to the window
             //      (nearest_point semantics, utils.py:53-66).  Lane = (sample group sg, segment
@@ -976,17 +1038,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                     const float4 N0 = sT[2 * (k + 2 * GG)];   // EVAL_SEG_PAD entries of slack
                     const float4 N1 = sT[2 * (k + 2 * GG) + 1];
 #endif
-                    f32x2 dA[SP > 0 ? SP : 1], dB[SP > 0 ? SP : 1];
-                    seg_step<SP>(sx2, sy2, T0, T1, dA);
-                    seg_step<SP>(sx2, sy2, B0, B1, dB);
-#pragma unroll
-                    for (int j = 0; j < SP; ++j) {
-                        float da, db, ea, eb;
-                        unpack2(dA[j], da, db);
-                        unpack2(dB[j], ea, eb);
-                        bdx[j] = fmin3(bdx[j], da, ea);
-                        bdy[j] = fmin3(bdy[j], db, eb);
-                    }
+                    seg_min2<SP>(sx2, sy2, T0, T1, B0, B1, bdx, bdy);
                     if (ODD) bdl = fmin3(bdl, seg_dist2(sxl, syl, T0, T1), seg_dist2(sxl, syl, B0, B1));
 #if EVAL_DEV_MIN3 == 1
                     T0 = N0;
@@ -1001,15 +1053,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 for (int k = ggi; k < nq; k += GG) {
                     const float4 N0 = sT[2 * (k + GG)];       // EVAL_SEG_PAD entries of slack
                     const float4 N1 = sT[2 * (k + GG) + 1];
-                    f32x2 dA[SP > 0 ? SP : 1];
-                    seg_step<SP>(sx2, sy2, T0, T1, dA);
-#pragma unroll
-                    for (int j = 0; j < SP; ++j) {
-                        float da, db;
-                        unpack2(dA[j], da, db);
-                        bdx[j] = fminf(bdx[j], da);
-                        bdy[j] = fminf(bdy[j], db);
-                    }
+                    seg_min1<SP>(sx2, sy2, T0, T1, bdx, bdy);
                     if (ODD) bdl = fminf(bdl, seg_dist2(sxl, syl, T0, T1));
                     T0 = N0;
                     T1 = N1;
@@ -1038,8 +1082,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             }
 
             if (!(flags & (F1L_FLAG_COLLIDE_OPP | F1L_FLAG_COLLIDE_MAP))) {
-                cost = a.ep.w[0] * t_len + a.ep.w[1] * t_maxk + a.ep.w[2] * t_meank +
-                       a.ep.w[3] * t_sim + a.ep.w[4] * t_dev;
+                cost = partial + a.ep.w[4] * t_dev;
                 if (!isfinite(cost)) cost = CUDART_INF_F;
             }
         }
@@ -1050,16 +1093,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             if (a.flags) a.flags[cand] = (uint8_t)flags;
             if (a.terms) {
                 float* t = a.terms + cand * F1L_N_TERMS;
-                t[0] = t_len; t[1] = t_maxk; t[2] = t_meank; t[3] = t_sim; t[4] = t_dev;
+                if (!(flags & F1L_FLAG_VALID)) { t[0] = 0.0f; t[1] = 0.0f; t[2] = 0.0f; t[3] = 0.0f; }
+                t[4] = t_dev;
             }
-            if (a.goals_out) {
-                float* g = a.goals_out + cand * 3;
-                g[0] = gx; g[1] = gy; g[2] = gth;
-            }
-            if (a.params)   // cubic: (p1, p2, s_f, p3); clothoid: (kappa0, dkappa, L, kappa_end)
-                a.params[cand] = a.ep.generator == 1
-                                     ? make_float4(sp.p0, __fdividef(sp.b1, sp.sf), sp.sf, sp.p3)
-                                     : make_float4(sp.p1, sp.p2, sp.sf, sp.p3);
             const unsigned long long key =
                 ((unsigned long long)float_orderable(cost) << 32) | (unsigned)c;
             atomicMin(a.best + s, key);
