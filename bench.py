@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=["c4"])
     ap.add_argument("--scenarios", type=int, default=S_PER_GPU, help="scenarios per GPU per step")
+    ap.add_argument("--prune", type=int, default=0, choices=[0, 1],
+                    help="prune_window of the headline run (0: every sample against all W window "
+                         "segments, the SURVEY FLOP model; 1: provably-far segments skipped)")
     ap.add_argument("--no-extras", action="store_true", help="skip the C2/C3/C5 side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -362,7 +365,7 @@ def run_ours(args):
 
     S = args.scenarios
     track, grid, la, wd, poses, opp, n_opp = workload(rank, S)
-    eng = Engine(device=local, **PLAN_CFG)
+    eng = Engine(device=local, prune_window=args.prune, **PLAN_CFG)
     eng.set_track(track)
     eng.set_grid(*grid)
     eng.set_goal_grid(la, wd)
@@ -415,8 +418,40 @@ def run_ours(args):
     value = world_size * S * C * args.steps / (ms_total * 1e-3)
 
     flags = o_flags.cpu().numpy()
-    step_flops, valid_frac, mean_passes = work_flops(flags, M, PLAN_CFG["window"], float(n_opp.mean()))
+    seg_steps, seg_cands = eng.stats()
+    # window segments each valid candidate was tested against (= W unless --prune 1)
+    w_eff = seg_steps / seg_cands if seg_cands else float(PLAN_CFG["window"])
+    step_flops, valid_frac, mean_passes = work_flops(flags, M, w_eff, float(n_opp.mean()))
     achieved_tflops = step_flops / (k_eval * 1e-3) / 1e12 if k_eval > 0 else None
+
+    # ---- side measurement: the same step with prune_window = 1 (bit-identical costs) ------------
+    pruned = None
+    if world_size == 1 and not args.no_extras and not args.prune:
+        costs_full = o_costs.clone()
+        eng.configure(prune_window=1)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize(dev)
+        eng.stats()
+        eng.set_timing(True)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(args.steps):
+            step()
+        p1.record()
+        torch.cuda.synchronize(dev)
+        _, pk_eval, _, _ = eng.mean_kernel_ms()
+        eng.set_timing(False)
+        ps, pc = eng.stats()
+        p_ms = p0.elapsed_time(p1) / args.steps
+        p_flops, _, _ = work_flops(flags, M, ps / max(pc, 1), float(n_opp.mean()))
+        pruned = {"candidates_per_s": S * C / (p_ms * 1e-3), "ms_per_step": p_ms, "eval_kernel_ms": pk_eval,
+                  "window_segments_tested_mean": ps / max(pc, 1),
+                  "executed_tflops": p_flops / (pk_eval * 1e-3) / 1e12,
+                  "costs_bit_identical_to_full_scan": bool(torch.equal(o_costs, costs_full))}
+        eng.configure(prune_window=0)
+        step()
+        torch.cuda.synchronize(dev)
     hbm_bytes = S * C * F.candidate_hbm_bytes() + S * (M * 16 + 32 + 4 + 4 + 16) + S * (32 + K_OPP * 24 + 4)
 
     # ---- end-to-end arm: public API, pinned host buffers, H2D + D2H inside the timed region ------
@@ -465,9 +500,10 @@ def run_ours(args):
         "data": "synthetic",
         "config": {
             "workload": "c4: %d independent scenarios per GPU x 4x7 goal grid (%d candidates/step/GPU), "
-                        "M=%d arc samples, raceline window W=%d, 1..%d opponents, occupancy grid on, "
+                        "M=%d arc samples, raceline window W=%d (prune_window=%d: %.1f segments tested per "
+                        "sample), 1..%d opponents, occupancy grid on, "
                         "kappa_max off (every converged candidate does the full cost+collision work)"
-                        % (S, S * C, M, PLAN_CFG["window"], K_OPP),
+                        % (S, S * C, M, PLAN_CFG["window"], args.prune, w_eff, K_OPP),
             "track": "ellipse N=2000 a=80 b=40", "grid": "3400x1800 @0.05 m",
             "valid_frac": valid_frac, "newton_passes_mean": mean_passes, "feasible_frac": float(np.isfinite(o_costs.cpu().numpy()).mean()),
             "l2": "per-step working set %.0f MB > 126 MB L2 (outputs rewritten every step); no explicit flush"
@@ -516,6 +552,8 @@ def run_ours(args):
             line["extra"] = extras(track, grid, local)
         except Exception as ex:  # side measurements must not lose the headline
             line["extra"] = {"error": repr(ex)}
+        if pruned is not None:
+            line["extra"]["prune_window_1"] = pruned
     print(json.dumps(line), flush=True)
     if world_size > 1:
         dist.destroy_process_group()

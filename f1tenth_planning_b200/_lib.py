@@ -31,6 +31,7 @@ class Config(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("n_newton", C.c_int32), ("window", C.c_int32),
                 ("n_shift", C.c_int32), ("n_cull", C.c_int32), ("literal_tracker", C.c_int32),
                 ("use_goal_kappa", C.c_int32), ("generator", C.c_int32),
+                ("prune_window", C.c_int32),
                 ("weights", C.c_double * N_TERMS), ("kappa_max", C.c_double),
                 ("car_length", C.c_double), ("car_width", C.c_double),
                 ("converge_tol", C.c_double), ("tracker_lookahead", C.c_double),
@@ -83,6 +84,7 @@ SIGNATURES = {
     "f1l_intersect_point_batch": (C.c_int, [_vp, _dp, _dp, C.c_int, C.c_double, C.c_int, _dp,
                                             _ip]),
     "f1l_get_actuation_batch": (C.c_int, [_vp, _dp, C.c_int, C.c_double, _dp]),
+    "f1l_get_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
     "f1l_launch_count": (C.c_int64, [_vp]),
     "f1l_set_graph": (C.c_int, [_vp, C.c_int]),
     "f1l_set_timing": (C.c_int, [_vp, C.c_int]),

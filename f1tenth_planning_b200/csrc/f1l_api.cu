@@ -73,6 +73,8 @@ struct f1l_ctx {
     void* h_in = nullptr;   // pose + opponents
     void* h_out = nullptr;  // header + best trajectory
     size_t h_out_cap = 0;
+    // deviation-pass work counters (f1l_get_stats)
+    DevBuf stats;
     // batch (device-pointer API) scratch
     DevBuf b_ctx, b_centres, b_best, b_near_i, b_near4;
     // batch pipeline (host-pointer API)
@@ -177,6 +179,7 @@ EvalParams eval_params(f1l_handle h) {
     e.literal_tracker = c.literal_tracker;
     e.use_goal_kappa = c.use_goal_kappa;
     e.generator = c.generator;
+    e.prune = c.prune_window != 0;
     for (int i = 0; i < F1L_N_TERMS; ++i) e.w[i] = (float)c.weights[i];
     e.kappa_max = (float)c.kappa_max;
     e.half_l = (float)(0.5 * c.car_length);
@@ -415,6 +418,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     ea.states = o.states;
     ea.headings = o.headings;
     ea.best = best;
+    ea.stats = (unsigned long long*)h->stats.p;
     const long long n_ctas = (long long)S * ea.ctas_per_scn;
     if (n_ctas > 0x7fffffffLL) return F1L_ERR_TOO_LARGE;
     eval_entry(M, wpc)<<<(unsigned)n_ctas, wpc * 32, smem, stream>>>(ea);
@@ -519,6 +523,18 @@ const char* f1l_strerror(int code) {
 const char* f1l_last_cuda_error(f1l_handle h) { return h ? h->err : ""; }
 int f1l_device(f1l_handle h) { return h ? h->device : -1; }
 int64_t f1l_launch_count(f1l_handle h) { return h ? h->launches : 0; }
+
+int f1l_get_stats(f1l_handle h, uint64_t* out, int n) {
+    if (!h || !out || n < 2) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());   // batch pipelines run on their own streams
+    unsigned long long v[2] = {0, 0};
+    CK(cudaMemcpy(v, h->stats.p, sizeof(v), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(h->stats.p, 0, sizeof(v)));
+    out[0] = v[0];
+    out[1] = v[1];
+    return F1L_OK;
+}
 
 int f1l_set_graph(f1l_handle h, int on) {
     if (!h) return F1L_ERR_INVALID_ARG;
@@ -654,6 +670,9 @@ int f1l_create(f1l_handle* out, int device, const f1l_config* cfg) {
         return F1L_ERR_CUDA;
     }
     r = build_lut(h);
+    if (r == F1L_OK) r = ensure(h, h->stats, 2 * sizeof(unsigned long long));
+    if (r == F1L_OK && cudaMemsetAsync(h->stats.p, 0, 2 * sizeof(unsigned long long), h->stream) != cudaSuccess)
+        r = F1L_ERR_CUDA;
     if (r != F1L_OK) {
         f1l_destroy(h);
         return r;
@@ -670,7 +689,7 @@ int f1l_destroy(f1l_handle h) {
                       &h->lut, &h->lookaheads, &h->widths, &h->prev, &h->q_res, &h->q_in, &h->q_goals,
                       &h->q_ctx, &h->q_centres, &h->q_best, &h->q_costs, &h->q_terms, &h->q_flags, &h->q_gout,
                       &h->q_params, &h->q_states, &h->q_headings, &h->b_ctx, &h->b_centres,
-                      &h->b_best, &h->b_near_i, &h->b_near4, &h->m_in, &h->m_in2, &h->m_o0, &h->m_o1, &h->m_o2, &h->m_o3,
+                      &h->b_best, &h->b_near_i, &h->b_near4, &h->stats, &h->m_in, &h->m_in2, &h->m_o0, &h->m_o1, &h->m_o2, &h->m_o3,
                       &h->m_o4, &h->m_o5};
     for (DevBuf* b : bufs) release(*b);
     for (int i = 0; i < N_PIPE; ++i) {

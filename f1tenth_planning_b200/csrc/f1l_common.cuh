@@ -53,6 +53,7 @@ struct EvalParams {
     int n_shift, n_cull;
     int literal_tracker, use_goal_kappa;
     int generator;    // 0 cubic spiral, 1 G1 clothoid
+    int prune;        // deviation pass: skip window segments that cannot be nearest
     float w[F1L_N_TERMS];
     float kappa_max;  // <= 0: off
     float half_l, half_w;

@@ -330,6 +330,7 @@ struct EvalArgs {
     float4* states;          // [S,C,M]
     float2* headings;        // [S,C,M] (cos, sin) used by the footprint (teacher-forced tests)
     unsigned long long* best;  // [S]
+    unsigned long long* stats; // [2] deviation-pass work counters (segment steps, candidates) or null
 };
 
 struct SelectArgs {
@@ -569,6 +570,15 @@ __device__ __forceinline__ bool grid_hit(const uint8_t* __restrict__ occ, int gw
     return __ldg(occ + (size_t)row * gw + col) != 0;
 }
 
+// a[j] of a register array with a run-time j (selects, no local memory)
+template <int N>
+__device__ __forceinline__ float pick(const float (&a)[N], int j) {
+    float r = a[0];
+#pragma unroll
+    for (int k = 1; k < N; ++k) r = (j == k) ? a[k] : r;
+    return r;
+}
+
 __device__ __forceinline__ float fast_sqrt(float x) {
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -740,6 +750,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
     constexpr int kSegUnroll = EVAL_SEG_UNROLL;
     extern __shared__ __align__(16) unsigned char ev_smem[];
     __shared__ int s_next;
+    __shared__ unsigned long long s_work;   // deviation pass: candidates << 40 | (candidate, segment) pairs
     __shared__ float s_gf[6];
     __shared__ int s_gi[4];
     const int M = a.ep.M;
@@ -799,10 +810,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             sT[2 * k] = T0;
             sT[2 * k + 1] = T1;
         }
-        if (a.prev_theta)
+        if (a.prev_theta) {
+#pragma unroll 1
             for (int i = tid; i < M; i += NW * 32) sprev[i] = a.prev_theta[i];
+        }
         if (tid < F1L_MAX_OPP) sopp[tid] = q->opp[tid];
-        if (tid == 0) s_next = cb + NW;
+        if (tid == 0) { s_next = cb + NW; s_work = 0ull; }
         // per-scenario collision constants live in shared memory, not in registers, so that the
         // candidate loop does not carry them through the deviation pass
         if (tid == 32 % (NW * 32)) {
@@ -815,6 +828,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
 
     float* slab_x = slab_all + (size_t)wid * (2 * SLAB);
     float* slab_y = slab_x + SLAB;
+#pragma unroll 1
     for (int i = M + lane; i < S * SG; i += 32) {   // unused slots of the last rows: finite dummies
         const int r = i / SG, g = i - r * SG;
         slab_x[((r >> 1) * SG + g) * 2 + (r & 1)] = 0.0f;
@@ -964,30 +978,39 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 }
             }
             if (has_grid) {
+                // samples whose clearance does not prove the footprint free: nine probes each.
+                // One copy of the probe code serves all of a lane's samples (register arrays are
+                // read through selects), the probes run as a rolled loop over a sign table --
+                // the unrolled form was 750 instructions of instruction-cache footprint.
+                unsigned need = 0;
 #pragma unroll
-                for (int j = 0; j < IPL; ++j) {
-                    const int i = lane * IPL + j;
-                    if (i < M && clr[j] <= a.grid.probe_reach) {
-                        // footprint centre and half-axes in grid-cell coordinates
-                        const float ccx = fa(fa(fm(A00, x[j]), fm(A01, y[j])), gfx);
-                        const float ccy = fa(fa(fm(A10, x[j]), fm(A11, y[j])), gfy);
-                        const float lx = fm(cs[j], hl), ly = fm(sn[j], hl);    // body x axis * hl
-                        const float wx = fm(-sn[j], hw), wy = fm(cs[j], hw);   // body y axis * hw
-                        const float elx = fa(fm(A00, lx), fm(A01, ly)), ely = fa(fm(A10, lx), fm(A11, ly));
-                        const float ewx = fa(fm(A00, wx), fm(A01, wy)), ewy = fa(fm(A10, wx), fm(A11, wy));
-                        bool h = false;
-                        // 4 corners, 4 edge mid-points, centre (SURVEY B.6, P = 9)
-                        h |= grid_hit(occ, gw, gh, gix, giy, fa(fa(ccx, elx), ewx), fa(fa(ccy, ely), ewy));
-                        h |= grid_hit(occ, gw, gh, gix, giy, fs(fa(ccx, elx), ewx), fs(fa(ccy, ely), ewy));
-                        h |= grid_hit(occ, gw, gh, gix, giy, fa(fs(ccx, elx), ewx), fa(fs(ccy, ely), ewy));
-                        h |= grid_hit(occ, gw, gh, gix, giy, fs(fs(ccx, elx), ewx), fs(fs(ccy, ely), ewy));
-                        h |= grid_hit(occ, gw, gh, gix, giy, fa(ccx, elx), fa(ccy, ely));
-                        h |= grid_hit(occ, gw, gh, gix, giy, fs(ccx, elx), fs(ccy, ely));
-                        h |= grid_hit(occ, gw, gh, gix, giy, fa(ccx, ewx), fa(ccy, ewy));
-                        h |= grid_hit(occ, gw, gh, gix, giy, fs(ccx, ewx), fs(ccy, ewy));
-                        h |= grid_hit(occ, gw, gh, gix, giy, ccx, ccy);
-                        hit_map |= h;
+                for (int j = 0; j < IPL; ++j)
+                    if (lane * IPL + j < M && clr[j] <= a.grid.probe_reach) need |= 1u << j;
+                while (need) {
+                    const int j = __ffs(need) - 1;
+                    need &= need - 1;
+                    const float xj = pick<IPL>(x, j), yj = pick<IPL>(y, j);
+                    const float cj = pick<IPL>(cs, j), sj = pick<IPL>(sn, j);
+                    // footprint centre and half-axes in grid-cell coordinates
+                    const float ccx = fa(fa(fm(A00, xj), fm(A01, yj)), gfx);
+                    const float ccy = fa(fa(fm(A10, xj), fm(A11, yj)), gfy);
+                    const float lx = fm(cj, hl), ly = fm(sj, hl);      // body x axis * hl
+                    const float wx = fm(-sj, hw), wy = fm(cj, hw);     // body y axis * hw
+                    const float elx = fa(fm(A00, lx), fm(A01, ly)), ely = fa(fm(A10, lx), fm(A11, ly));
+                    const float ewx = fa(fm(A00, wx), fm(A01, wy)), ewy = fa(fm(A10, wx), fm(A11, wy));
+                    // 4 corners, 4 edge mid-points, centre (SURVEY B.6, P = 9): probe p sits at
+                    // centre + sa * l-axis + sb * w-axis with (sa, sb) in {-1, 0, 1}, two bits each.
+                    // x + (+-1) * e and x + 0 * e round like x +- e and x, so the cells are the
+                    // ones the oracle's float32 mirror visits.
+                    bool h = false;
+#pragma unroll 1
+                    for (int p = 0; p < 9; ++p) {
+                        const float sa = (float)(int)((0x1520au >> (2 * p)) & 3u) - 1.0f;
+                        const float sb = (float)(int)((0x12522u >> (2 * p)) & 3u) - 1.0f;
+                        h |= grid_hit(occ, gw, gh, gix, giy, fa(fa(ccx, fm(sa, elx)), fm(sb, ewx)),
+                                      fa(fa(ccy, fm(sa, ely)), fm(sb, ewy)));
                     }
+                    hit_map |= h;
                 }
             }
             t_sim = warp_sum(sim);
@@ -1028,11 +1051,40 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                     syl = slab_y[(SP * SG + sgi) * 2];
                 }
                 const int nq = a.nseg_pad;
-                float4 T0 = sT[2 * ggi], T1 = sT[2 * ggi + 1];
+                // segment range [k_begin, k_end) of the window this candidate is tested against
+                int k_begin = 0, k_end = nq;
+                if (a.ep.prune) {
+                    // Every point of a curve of length s_f from the origin to (ex, ey) lies
+                    // within rho = s_f / 2 of the chord midpoint c.  With D = the distance of c
+                    // to the window, every sample's nearest distance is <= D + rho, and a
+                    // segment farther than D + 2 rho from c is farther than D + rho from every
+                    // sample: it cannot hold any sample's minimum.  Dropping it leaves every
+                    // per-sample minimum, hence the cost, bit-identical.  The kept segments are
+                    // covered by one index range (the raceline is a curve: normally one run).
+                    const float cmx = 0.5f * ex * EVAL_DEV_SCALE, cmy = 0.5f * ey * EVAL_DEV_SCALE;
+                    float dmin = CUDART_INF_F;
+                    for (int k = lane; k < nq; k += 32)
+                        dmin = fminf(dmin, seg_dist2(cmx, cmy, sT[2 * k], sT[2 * k + 1]));
+                    dmin = __uint_as_float(__reduce_min_sync(F1L_FULL, __float_as_uint(dmin)));
+                    // 1 mm + 0.1 % of slack over the rounding of the FP32 distances and samples
+                    const float thr = (fast_sqrt(dmin) + sp.sf * EVAL_DEV_SCALE) * 1.001f + 1e-3f * EVAL_DEV_SCALE;
+                    const float thr2 = thr * thr;
+                    int lo = nq, hi = -1;
+                    for (int k = lane; k < nq; k += 32)
+                        if (seg_dist2(cmx, cmy, sT[2 * k], sT[2 * k + 1]) <= thr2) { lo = min(lo, k); hi = max(hi, k); }
+                    lo = __reduce_min_sync(F1L_FULL, lo);
+                    hi = __reduce_max_sync(F1L_FULL, hi);
+                    if (hi >= lo) {   // (always: the nearest segment itself passes)
+                        k_begin = lo & ~(2 * GG - 1);
+                        k_end = min(nq, (hi + 2 * GG) & ~(2 * GG - 1));
+                    }
+                }
+                if (lane == 0) atomicAdd(&s_work, (1ull << 40) + (unsigned long long)(k_end - k_begin));
+                float4 T0 = sT[2 * (k_begin + ggi)], T1 = sT[2 * (k_begin + ggi) + 1];
 #if EVAL_DEV_MIN3
                 // two segments per trip: the running minimum takes both distances in one
                 // three-input FMNMX3 (nseg_pad / GG is a multiple of 8)
-                for (int k = ggi; k < nq; k += 2 * GG) {
+                for (int k = k_begin + ggi; k < k_end; k += 2 * GG) {
                     const float4 B0 = sT[2 * (k + GG)], B1 = sT[2 * (k + GG) + 1];
 #if EVAL_DEV_MIN3 == 1
                     const float4 N0 = sT[2 * (k + 2 * GG)];   // EVAL_SEG_PAD entries of slack
@@ -1050,7 +1102,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 }
 #else
 #pragma unroll kSegUnroll
-                for (int k = ggi; k < nq; k += GG) {
+                for (int k = k_begin + ggi; k < k_end; k += GG) {
                     const float4 N0 = sT[2 * (k + GG)];       // EVAL_SEG_PAD entries of slack
                     const float4 N1 = sT[2 * (k + GG) + 1];
                     seg_min1<SP>(sx2, sy2, T0, T1, bdx, bdy);
@@ -1102,6 +1154,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             c_next = atomicAdd(&s_next, 1);
         }
         c = __shfl_sync(F1L_FULL, c_next, 0);
+    }
+    if (a.stats) {   // one pair of global atomics per CTA
+        __syncthreads();
+        if (tid == 0) {
+            atomicAdd(a.stats, s_work & ((1ull << 40) - 1));
+            atomicAdd(a.stats + 1, s_work >> 40);
+        }
     }
 }
 

@@ -341,6 +341,14 @@ class Engine:
     def launch_count(self):
         return int(self._L.f1l_launch_count(self._h))
 
+    def stats(self):
+        """(segment_steps, candidates) of the raceline-deviation pass since the last call: the
+        (candidate, window segment) pairs evaluated and the valid candidates that reached the
+        pass.  Resets the counters (f1l_get_stats)."""
+        out = (C.c_uint64 * 2)()
+        self._ck(self._L.f1l_get_stats(self._h, out, 2))
+        return int(out[0]), int(out[1])
+
     def set_graph(self, on):
         """replay the single-query chain as a CUDA graph (default on)"""
         self._ck(self._L.f1l_set_graph(self._h, int(bool(on))))

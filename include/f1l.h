@@ -71,6 +71,10 @@ typedef struct {
     int32_t generator;       /* 0: cubic spiral (LUT seed + Newton on p1, p2, s_f); 1: G1 clothoid as
                                 the reference's Clothoid.G1Hermite(0,0,0,gx,gy,gtheta)
                                 (lattice_planner.py:196), 1-D Newton */
+    int32_t prune_window;    /* raceline deviation: 0 = every sample against every window segment
+                                (default); 1 = skip the window segments that provably cannot be
+                                nearest to any sample of the candidate (chord-midpoint bound).
+                                Same minima, hence bit-identical costs, fewer segment tests. */
     double weights[F1L_N_TERMS]; /* cost weights (lattice_planner.py:130-156) */
     double kappa_max;        /* candidates with max|kappa| above it are invalid; <=0 disables */
     double car_length;       /* 0.58 */
@@ -245,6 +249,12 @@ int f1l_intersect_point_batch(f1l_handle h, const double* points, const double* 
  * return order. */
 int f1l_get_actuation_batch(f1l_handle h, const double* in, int n, double wheelbase,
                             double* out);
+
+/* Work counters of the deviation pass since the last call (synchronises the handle's stream and
+ * resets them): out[0] = (candidate, window segment) pairs evaluated, out[1] = candidates that
+ * reached the pass (valid trajectories).  With prune_window = 0, out[0] / out[1] is the padded
+ * window length.  n >= 2. */
+int f1l_get_stats(f1l_handle h, uint64_t* out, int n);
 
 /* Timing / evidence helpers: number of kernels launched by this handle so far, and the device
  * time (ms, CUDA events on the handle's stream) of the kernels of the last host-pointer call. */

@@ -37,6 +37,7 @@ extern "C" {
 
 typedef struct {
     int32_t n_samples, n_newton, window, n_shift, n_cull, literal_tracker, use_goal_kappa, generator;
+    int32_t prune_window; /* layout parity with f1l_config only: the oracle always scans the whole window */
     double weights[F1O_N_TERMS];
     double kappa_max, car_length, car_width, converge_tol, tracker_lookahead, wheelbase,
         max_reacquire;

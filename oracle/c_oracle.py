@@ -22,6 +22,7 @@ class Config(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("n_newton", C.c_int32), ("window", C.c_int32),
                 ("n_shift", C.c_int32), ("n_cull", C.c_int32), ("literal_tracker", C.c_int32),
                 ("use_goal_kappa", C.c_int32), ("generator", C.c_int32),
+                ("prune_window", C.c_int32),
                 ("weights", C.c_double * N_TERMS), ("kappa_max", C.c_double),
                 ("car_length", C.c_double), ("car_width", C.c_double),
                 ("converge_tol", C.c_double), ("tracker_lookahead", C.c_double),

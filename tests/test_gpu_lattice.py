@@ -288,3 +288,47 @@ def test_cuda_graph_replay_matches_stream_launches(ellipse, corridor):
             assert np.array_equal(a.costs, b.costs) and np.array_equal(a.flags, b.flags)
         if a.states is not None:
             assert np.array_equal(a.states, b.states)
+
+
+@pytest.mark.parametrize("config,window", [(1, 128), (1, 0), (3, 128), (3, 512)])
+def test_pruned_window_is_bit_identical(ellipse, corridor, config, window):
+    """prune_window = 1 drops window segments that provably cannot be nearest to any sample of a
+    candidate: every cost term, flag, cost and the argmin must be bit-identical to the full scan,
+    with fewer (candidate, segment) pairs evaluated."""
+    la, wd = synth.goal_grid(config)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, grid=corridor, window=window, kappa_max=0.0)
+    seeds = (21, 22, 23, 24) if config == 1 else (25,)
+    full, work_full = [], None
+    for seed in seeds:
+        pose, opp = H.scenario(ellipse, seed, 4)
+        full.append(eng.plan(pose, opp, update_prev=False))
+    work_full = eng.stats()
+    eng.configure(prune_window=1)
+    for seed, f in zip(seeds, full):
+        pose, opp = H.scenario(ellipse, seed, 4)
+        p = eng.plan(pose, opp, update_prev=False)
+        assert np.array_equal(p.flags, f.flags)
+        assert np.array_equal(p.terms, f.terms)
+        assert np.array_equal(p.costs, f.costs)
+        assert p.best_idx == f.best_idx and p.best_cost == f.best_cost
+    work_pruned = eng.stats()
+    assert work_full[1] == work_pruned[1] > 0
+    assert work_pruned[0] < 0.6 * work_full[0], (work_full, work_pruned)
+
+
+def test_pruned_window_batch_and_hairpin(golden_spielberg):
+    """pruned vs full scan on the Spielberg raceline (hairpins: the kept segments may form two
+    runs that one index range must cover) in batch mode."""
+    wp = golden_spielberg["waypoints"]
+    la, wd = np.linspace(0.5, 3.0, 6), np.linspace(-1.0, 1.0, 9)
+    from f1tenth_planning_b200.engine import Engine
+    eng = Engine(window=256, kappa_max=0.0)
+    eng.set_track(wp)
+    eng.set_goal_grid(la, wd)
+    poses, opp, n_opp = synth.scenario_batch(wp, 512, 4, 5)
+    a = eng.plan_batch(poses, opp, n_opp, want_flags=True)
+    eng.configure(prune_window=1)
+    b = eng.plan_batch(poses, opp, n_opp, want_flags=True)
+    assert np.isfinite(a.costs).sum() > 1000
+    assert np.array_equal(a.costs, b.costs) and np.array_equal(a.flags, b.flags)
+    assert np.array_equal(a.best_idx, b.best_idx) and np.array_equal(a.best_traj, b.best_traj)
