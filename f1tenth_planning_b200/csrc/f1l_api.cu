@@ -80,7 +80,7 @@ struct f1l_ctx {
     // batch pipeline (host-pointer API)
     PipeSlot pipe[N_PIPE];
     // misc scratch for the pure-pursuit / intersect host APIs
-    DevBuf m_in, m_in2, m_o0, m_o1, m_o2, m_o3, m_o4, m_o5;
+    DevBuf m_in, m_in2, m_o0, m_o1, m_o2, m_o3, m_o4, m_o5, pp_bk;
 };
 
 namespace {
@@ -234,7 +234,18 @@ typedef void (*generate_fn)(LutView, EvalParams, const float4*, int, float4*, fl
 #ifndef EVAL_MINB7
 #define EVAL_MINB7 4
 #endif
+#ifndef EVAL_MINB4
+#define EVAL_MINB4 7
+#endif
 eval_fn eval_entry(int M, int nw) {
+    if (nw == 4) {
+        if (M <= 32) return eval_kernel<1, 4, 8, 4, EVAL_MINB4>;
+        if (M <= 64) return eval_kernel<2, 8, 8, 4, EVAL_MINB4>;
+        if (M <= 104) return eval_kernel<4, EVAL_S104, EVAL_SG104, 4, EVAL_MINB4>;
+        if (M <= 128) return eval_kernel<4, 16, 8, 4, EVAL_MINB4>;
+        if (M <= 208) return eval_kernel<7, 13, 16, 4, EVAL_MINB4>;
+        return eval_kernel<8, 16, 16, 4, EVAL_MINB4>;
+    }
     if (nw == 7) {
         if (M <= 32) return eval_kernel<1, 4, 8, 7, EVAL_MINB7>;
         if (M <= 64) return eval_kernel<2, 8, 8, 7, EVAL_MINB7>;
@@ -276,9 +287,13 @@ struct CtaPlan {
 CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count) {
     CtaPlan best{8, 8, 1};
     double best_cost = 1e300;
-    for (int nw = 7; nw <= 8; ++nw) {
-        if (nw == 7 && M > 128) continue;   // the 7-warp build of the M = 200 shape spills
-        const int resident = (nw == 7 ? 4 : 3) * sm_count;
+    const int nws[3] = {4, 7, 8};
+    for (int nw : nws) {
+#ifdef F1L_FORCE_NW
+        if (nw != F1L_FORCE_NW) continue;
+#endif
+        if (nw != 8 && M > 128) continue;   // the 72-register builds of the M = 200 shapes spill
+        const int resident = (nw == 4 ? EVAL_MINB4 : nw == 7 ? EVAL_MINB7 : EVAL_MINB8) * sm_count;
         // enough CTAs for ~8 waves; batches of small queries get one CTA per scenario
         long long per = (8LL * resident + S - 1) / S;
         const long long max_per = (n_cand + nw - 1) / nw;
@@ -292,10 +307,22 @@ CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count) {
         const double rounds = std::ceil((double)chunk / nw);        // candidates per warp
         // time ~ waves x rounds, in units of one candidate per warp; slightly favour the
         // configuration with more resident warps on ties
-        const double cost = waves * rounds * (nw == 7 ? 0.999 : 1.0);
+        // the CTA holds its registers until its last warp finishes: about half a candidate of
+        // idle tail per CTA, which weighs more the fewer candidates each warp runs
+        const double cost = waves * (rounds + 0.5) * (nw == 7 ? 0.999 : 1.0);
         if (cost < best_cost) { best_cost = cost; best = {nw, chunk, cps}; }
     }
     return best;
+}
+
+// K1 = scan + finish on one stream.  best_k: int32 scratch per pose (may alias o.nearest_i)
+void launch_pp(const TrackView& tv, cudaStream_t stream, const double* poses, int pose_stride,
+               int n_poses, double L, double wb, double max_reacquire, int front_axle, double k_path,
+               int32_t* best_k, const PPOut& o) {
+    pp_scan_kernel<<<(n_poses + PP_CTA_POSES - 1) / PP_CTA_POSES, PP_SCAN_THREADS, 0, stream>>>(
+        tv, poses, pose_stride, n_poses, front_axle, wb, best_k);
+    pp_finish_kernel<<<(n_poses + PP_THREADS - 1) / PP_THREADS, PP_THREADS, 0, stream>>>(
+        tv, poses, pose_stride, n_poses, L, wb, max_reacquire, front_axle, k_path, best_k, o);
 }
 
 size_t eval_smem_bytes(int nseg_pad, int warps, int M) {
@@ -374,11 +401,10 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
         po.actuation = nullptr;
         po.status = nullptr;
         po.front = nullptr;
-        pp_batch_kernel<<<(S + PP_THREADS - 1) / PP_THREADS, PP_THREADS, PP_SMEM_BYTES, stream>>>(
-            sa.tr, poses, 4, S, -1.0, 0.33, 0.0, 0, 0.0, po);
+        launch_pp(sa.tr, stream, poses, 4, S, -1.0, 0.33, 0.0, 0, 0.0, near_i, po);
         sample_warp_kernel<<<(S + SAMPLE_WARPS - 1) / SAMPLE_WARPS, SAMPLE_WARPS * 32, 0, stream>>>(
             sa, near_i, near4, S);
-        h->launches += 1;
+        h->launches += 2;
     } else {
         // a lone dense query: one warp per ~2 lookahead rows; small batches: 8 warps each
         int st_threads = SAMPLE_THREADS;
@@ -652,7 +678,8 @@ int f1l_create(f1l_handle* out, int device, const f1l_config* cfg) {
         if (sm > 0) h->sm_count = sm;
         // opt in to large dynamic shared memory for every eval instantiation + the scan kernel
         const int big = 226 * 1024;  // opt-in maximum is 227 KB per block INCLUDING static shared memory
-        for (int nw = 7; nw <= 8; ++nw) {
+        const int nws[3] = {4, 7, 8};
+        for (int nw : nws) {
             const int ms[] = {32, 64, 100, 128, 200, 256};
             for (int m : ms) {
                 cudaError_t e2 = cudaFuncSetAttribute(
@@ -660,9 +687,6 @@ int f1l_create(f1l_handle* out, int device, const f1l_config* cfg) {
                 if (e2 != cudaSuccess && e == cudaSuccess) e = e2;
             }
         }
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(pp_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)PP_SMEM_BYTES);
     }
     if (e != cudaSuccess) {
         fail(h, e, "f1l_create");
@@ -690,7 +714,7 @@ int f1l_destroy(f1l_handle h) {
                       &h->q_ctx, &h->q_centres, &h->q_best, &h->q_costs, &h->q_terms, &h->q_flags, &h->q_gout,
                       &h->q_params, &h->q_states, &h->q_headings, &h->b_ctx, &h->b_centres,
                       &h->b_best, &h->b_near_i, &h->b_near4, &h->stats, &h->m_in, &h->m_in2, &h->m_o0, &h->m_o1, &h->m_o2, &h->m_o3,
-                      &h->m_o4, &h->m_o5};
+                      &h->m_o4, &h->m_o5, &h->pp_bk};
     for (DevBuf* b : bufs) release(*b);
     for (int i = 0; i < N_PIPE; ++i) {
         PipeSlot& p = h->pipe[i];
@@ -735,12 +759,13 @@ int f1l_set_track(f1l_handle h, const double* wpts, int n, int ncols) {
         const double dx = xy[2 * k + 2] - xy[2 * k], dy = xy[2 * k + 3] - xy[2 * k + 1];
         const double len = std::sqrt(dx * dx + dy * dy);
         const double ux = dx / len, uy = dy / len;
+        const double sc = (double)TRACK_SCALE, hh = 0.5 * len;   // table units (track_seg_d2)
         segA[4 * k] = (float)ux;
         segA[4 * k + 1] = (float)uy;
-        segA[4 * k + 2] = (float)(ax * ux + ay * uy);
-        segA[4 * k + 3] = (float)(-ax * uy + ay * ux);
-        segB[2 * k] = (float)len;
-        segB[2 * k + 1] = (float)(1.0 / len);
+        segA[4 * k + 2] = (float)(-(ax * ux + ay * uy + hh) * sc);
+        segA[4 * k + 3] = (float)(-(-ax * uy + ay * ux) * sc);
+        segB[2 * k] = (float)(-hh * sc);
+        segB[2 * k + 1] = (float)(-uy);
     }
     ENS(h->xy, xy.size() * 8);
     ENS(h->v, v.size() * 8);
@@ -1163,10 +1188,14 @@ int f1l_pure_pursuit_batch_dev(f1l_handle h, const double* poses_dev, int n_pose
     o.actuation = actuation_dev;
     o.status = status_dev;
     o.front = nullptr;
-    const int blocks = (n_poses + PP_THREADS - 1) / PP_THREADS;
-    pp_batch_kernel<<<blocks, PP_THREADS, PP_SMEM_BYTES, (cudaStream_t)stream>>>(
-        track_view(h), poses_dev, 3, n_poses, L, h->cfg.wheelbase, h->cfg.max_reacquire, 0, 0.0, o);
-    h->launches += 1;
+    int32_t* bk = nearest_i_dev;
+    if (!bk) {   // scratch for the scan result (one call in flight per handle)
+        ENS(h->pp_bk, (size_t)n_poses * 4);
+        bk = (int32_t*)h->pp_bk.p;
+    }
+    launch_pp(track_view(h), (cudaStream_t)stream, poses_dev, 3, n_poses, L, h->cfg.wheelbase,
+              h->cfg.max_reacquire, 0, 0.0, bk, o);
+    h->launches += 2;
     CK(cudaGetLastError());
     return F1L_OK;
 }
@@ -1215,10 +1244,14 @@ int f1l_front_axle_batch_dev(f1l_handle h, const double* poses_dev, int n_poses,
     o.actuation = nullptr;
     o.status = nullptr;
     o.front = front_dev;
-    const int blocks = (n_poses + PP_THREADS - 1) / PP_THREADS;
-    pp_batch_kernel<<<blocks, PP_THREADS, PP_SMEM_BYTES, (cudaStream_t)stream>>>(
-        track_view(h), poses_dev, 4, n_poses, 0.0, wheelbase, 0.0, 1, k_path, o);
-    h->launches += 1;
+    int32_t* bk = nearest_i_dev;
+    if (!bk) {
+        ENS(h->pp_bk, (size_t)n_poses * 4);
+        bk = (int32_t*)h->pp_bk.p;
+    }
+    launch_pp(track_view(h), (cudaStream_t)stream, poses_dev, 4, n_poses, 0.0, wheelbase, 0.0, 1,
+              k_path, bk, o);
+    h->launches += 2;
     CK(cudaGetLastError());
     return F1L_OK;
 }

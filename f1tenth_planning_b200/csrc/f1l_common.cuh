@@ -22,9 +22,10 @@ struct TrackView {
     const double* v;       // [n] column 2 (speed) or zeros
     const double* psi;     // [n] column 3 or zeros
     const double* kappa;   // [n] column 4 or zeros
-    // float32 line form of the n-1 open segments in block-local frames (pure-pursuit scan):
-    //   segA[k] = (ux, uy, c, e): unit direction, c = a.u, e = a.n with a relative to the origin
-    //   of block k/32 and n = (-uy, ux);  segB[k] = (len, 1/len)
+    // float32 line form of the n-1 open segments in block-local frames (nearest-point scans), in
+    // table units of TRACK_UNIT metres (see track_seg_d2):
+    //   segA[k] = (ux, uy, -(a.u + h), -a.n): unit direction u, normal n = (-uy, ux), a = segment
+    //   start relative to the origin of block k/32, h = len / 2;  segB[k] = (-h, -uy)
     const float4* segA;
     const float2* segB;
     const double2* blk_origin;  // [ceil((n-1)/32)]
@@ -82,6 +83,20 @@ struct __align__(16) Centre {
     float cx, cy, psi_rel, kappa_g;  // centre xy, wrap(psi - theta), raceline curvature
     float nx, ny, v, ok;             // unit normal (-sin psi_rel, cos psi_rel), raceline speed, found
 };
+
+// FP32 squared distance (table units squared) of a block-relative point, already in table units,
+// to segment k of the uploaded line form: q_c = p.u - (a.u + h) is the coordinate along the
+// segment measured from its midpoint, so the excess beyond the segment is max(|q_c| - h, 0) =
+// sat(|q_c| - h) -- one FADD.SAT with an |.| operand modifier -- as long as it stays below one
+// table unit, which TRACK_UNIT = 16384 m guarantees for any real track.  7 FMA-pipe instructions.
+#define TRACK_UNIT 16384.0f
+#define TRACK_SCALE (1.0f / TRACK_UNIT)
+__device__ __forceinline__ float track_seg_d2(float prx, float pry, float4 A, float2 Bv) {
+    const float q = fmaf(prx, A.x, fmaf(pry, A.y, A.z));
+    const float nn = fmaf(pry, A.x, fmaf(-prx, A.y, A.w));
+    const float e = __saturatef(fabsf(q) + Bv.x);
+    return fmaf(e, e, nn * nn);
+}
 
 // ---------------------------------------------------------------------------------------------
 // float64 helpers that follow the reference operation by operation (no FMA contraction)
@@ -275,18 +290,13 @@ __device__ inline Intersect64 intersect_point_warp(const P& pts, int n, double q
 struct TrackPrefilter {
     const TrackView& tr;
     double qx, qy;
-    float rr2;
+    float rr2;   // (radius + 1 mm)^2 in metres^2
     __device__ __forceinline__ bool operator()(int i) const {
         if (i < 0) return true;
         const double2 o = tr.blk_origin[i >> 5];
-        const float prx = (float)(qx - o.x), pry = (float)(qy - o.y);
-        const float4 A = __ldg(tr.segA + i);
-        const float2 Bv = __ldg(tr.segB + i);
-        const float q = fmaf(prx, A.x, fmaf(pry, A.y, -A.z));
-        const float nn = fmaf(pry, A.x, fmaf(-prx, A.y, -A.w));
-        const float tc = __saturatef(q * Bv.y);
-        const float ex = fmaf(-tc, Bv.x, q);
-        return fmaf(ex, ex, nn * nn) <= rr2;
+        const float prx = (float)(qx - o.x) * TRACK_SCALE, pry = (float)(qy - o.y) * TRACK_SCALE;
+        return track_seg_d2(prx, pry, __ldg(tr.segA + i), __ldg(tr.segB + i)) <=
+               rr2 * (TRACK_SCALE * TRACK_SCALE);
     }
 };
 struct NoPrefilter {

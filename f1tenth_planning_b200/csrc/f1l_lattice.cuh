@@ -496,14 +496,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS_MAX) sample_kernel(SampleArgs a
     int bi = 0x7fffffff;
     for (int k = tid; k < nseg; k += nthreads) {
         const double2 o = a.tr.blk_origin[k >> 5];
-        const float prx = (float)(px - o.x), pry = (float)(py - o.y);
-        const float4 A = __ldg(a.tr.segA + k);
-        const float2 Bv = __ldg(a.tr.segB + k);
-        const float q = fmaf(prx, A.x, fmaf(pry, A.y, -A.z));
-        const float nn = fmaf(pry, A.x, fmaf(-prx, A.y, -A.w));
-        const float t = __saturatef(q * Bv.y);
-        const float ex = fmaf(-t, Bv.x, q);
-        const float d2 = fmaf(ex, ex, nn * nn);
+        const float prx = (float)(px - o.x) * TRACK_SCALE, pry = (float)(py - o.y) * TRACK_SCALE;
+        const float d2 = track_seg_d2(prx, pry, __ldg(a.tr.segA + k), __ldg(a.tr.segB + k));
         if (d2 < bd) { bd = d2; bi = k; }
     }
 #pragma unroll
@@ -526,7 +520,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS_MAX) sample_kernel(SampleArgs a
     sample_body(a, s, tid, nthreads, s_best, s_t);
 }
 
-// batches: the nearest-point search of all scenarios is done by pp_batch_kernel (thread per pose,
+// batches: the nearest-point search of all scenarios is done by pp_scan_kernel + pp_finish_kernel (K1, lane per pose,
 // track in shared memory); here one warp per scenario does the rest.
 #define SAMPLE_WARPS 4
 __global__ void __launch_bounds__(SAMPLE_WARPS * 32)

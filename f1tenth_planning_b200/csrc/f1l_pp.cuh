@@ -3,22 +3,35 @@
 // Replaces, for B poses at once, utils/utils.py:37-67 (nearest_point), :69-151
 // (intersect_point), :153-161 (get_actuation) and pure_pursuit.py:56-122.
 //
-// Design: one THREAD per pose.  The segment table streams through shared memory in chunks and
-// every lane of a warp reads the same segment (a broadcast: one wavefront per LDS), so the
-// inner loop is 8 FMA-pipe + 3 ALU instructions per (pose, segment) with no cross-lane traffic.
-// The scan runs in FP32 on a line-form of each segment expressed in the frame of its 32-segment
-// block (origin kept in float64), which keeps |coordinates| small where it matters; the winner
-// and its +-2 neighbours are then re-evaluated in float64 operation by operation like the
-// reference, so index / t / dist / projection agree with the numba path to rounding.
+// Two kernels:
+//   pp_scan_kernel    FP32 scan.  A CTA owns 128 poses -- four per lane, as two packed FP32x2
+//                     pairs -- and its PP_PARTS warps each scan their share of the track's
+//                     32-segment blocks for all of them.  Every lane of a warp reads the same
+//                     table entry (a broadcast load, L1-resident: 48 KB for a 2000-waypoint
+//                     track).  Why this shape: a broadcast LDS / LDG still writes 32 x 24 B back
+//                     to the register file and an SM moves 128 B per clock, so one pose per lane
+//                     is bound by that write-back at 24 cycles per (pose, segment) per warp
+//                     (measured: l1tex data pipe 87 % busy) -- four poses per lane cut it to 6
+//                     and the packed FFMA2 math (7 FMA-pipe + 1 ALU instruction per pose and
+//                     segment, the deviation loop of eval_kernel) becomes the bound.  Splitting
+//                     the TRACK over the warps of a CTA instead of the poses over more CTAs keeps
+//                     the machine full at BASELINE config 2, where 10^5 poses at four per lane
+//                     are only 782 warps.  The scan runs on a line form of each segment in the
+//                     frame of its 32-segment block (origin kept in float64), which keeps
+//                     |coordinates| small where it matters; it only has to find the right
+//                     neighbourhood.
+//   pp_finish_kernel  one thread per pose, float64: the winner and its +-2 neighbours are
+//                     re-evaluated operation by operation like the reference, so index / t / dist
+//                     / projection agree with the numba path to rounding; then the lookahead
+//                     search and get_actuation (or the Stanley / LQR front-axle errors).
 #pragma once
 #include "f1l_common.cuh"
 
-#define PP_CHUNK 512           // segments staged per shared-memory chunk (multiple of 32)
-#define PP_THREADS 64
-#define PP_SMEM_BYTES (PP_CHUNK * (sizeof(float4) + sizeof(float2)) + (PP_CHUNK / 32) * sizeof(double2))
-// Launch shape: 64-thread CTAs with a 12.5 KB table chunk keep ~13 CTAs resident per SM, so the
-// 1563 CTAs of 10^5 poses run as ONE balanced wave (21 warps per SM +-5 %); 128-thread CTAs with a
-// 48 KB chunk fit 4 per SM and needed 1.3 waves (measured: issue slots busy 48 % of the time).
+#define PP_PARTS 8             // warps of a scan CTA, each scanning 1/PP_PARTS of the track
+#define PP_LANE_POSES 4        // poses per lane (two packed pairs)
+#define PP_CTA_POSES (32 * PP_LANE_POSES)
+#define PP_SCAN_THREADS (32 * PP_PARTS)
+#define PP_THREADS 128         // finish kernel
 
 struct PPOut {
     double* nearest;      // [B,4] proj_x, proj_y, dist, t
@@ -39,79 +52,148 @@ __device__ __forceinline__ double pi_2_pi64(double a) {
     return a;
 }
 
-// FP32 squared distance of a block-relative point to a segment in line form
-__device__ __forceinline__ float pp_seg_d2(float prx, float pry, float4 A, float2 Bv) {
-    const float q = fmaf(prx, A.x, fmaf(pry, A.y, -A.z));
-    const float nn = fmaf(pry, A.x, fmaf(-prx, A.y, -A.w));
-    const float t = __saturatef(q * Bv.y);
-    const float ex = fmaf(-t, Bv.x, q);
-    return fmaf(ex, ex, nn * nn);
-}
-
-__global__ void __launch_bounds__(PP_THREADS)
-pp_batch_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, int n_poses, double L, double wb,
-                double max_reacquire, int front_axle, double k_path, PPOut out) {
-    extern __shared__ __align__(16) unsigned char pp_smem[];
-    float4* sA = reinterpret_cast<float4*>(pp_smem);
-    float2* sB = reinterpret_cast<float2*>(sA + PP_CHUNK);
-    double2* sO = reinterpret_cast<double2*>(sB + PP_CHUNK);
-
-    const int nseg = tr.n - 1;
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = gid < n_poses;
-    const int pid = active ? gid : n_poses - 1;
-    double qx = poses[(size_t)pose_stride * pid], qy = poses[(size_t)pose_stride * pid + 1];
-    const double qth = poses[(size_t)pose_stride * pid + 2];
-    if (front_axle) {   // query point = front axle centre (stanley.py:66-68, lqr.py:76-78)
+// query point of pose `pid`: the pose position, or the front-axle centre (stanley.py:66-68,
+// lqr.py:76-78)
+__device__ __forceinline__ void pp_query_point(const double* __restrict__ poses, int pose_stride,
+                                               int pid, int front_axle, double wb, double& qx,
+                                               double& qy, double& qth) {
+    qx = poses[(size_t)pose_stride * pid];
+    qy = poses[(size_t)pose_stride * pid + 1];
+    qth = poses[(size_t)pose_stride * pid + 2];
+    if (front_axle) {
         qx = xadd(qx, xmul(wb, cos(qth)));
         qy = xadd(qy, xmul(wb, sin(qth)));
     }
+}
 
-    // The scan keeps only the running minimum of each 32-segment block (one FMNMX per segment
-    // instead of compare + two selects) and remembers the best block; the exact index is
-    // recovered afterwards by re-scanning that one block (1.6 % extra work).
-    float best = CUDART_INF_F;
-    int bblk = 0;
-    for (int c0 = 0; c0 < nseg; c0 += PP_CHUNK) {
-        const int cn = min(PP_CHUNK, nseg - c0);
-        const int nblk = (cn + 31) >> 5;
-        for (int q = threadIdx.x; q < (nblk << 5); q += blockDim.x) {
-            float4 A = make_float4(1.0f, 0.0f, 1e15f, 1e15f);   // padding: far away, finite
-            float2 Bv = make_float2(1.0f, 1.0f);
-            if (q < cn) {
-                A = __ldg(tr.segA + c0 + q);
-                Bv = __ldg(tr.segB + c0 + q);
+// packed pair of track_seg_d2 (segB.y = -uy)
+__device__ __forceinline__ f32x2 track_seg_d2_pair(f32x2 px, f32x2 py, float4 A, float2 Bv) {
+    const f32x2 ux = pack2(A.x, A.x), uy = pack2(A.y, A.y), nuy = pack2(Bv.y, Bv.y);
+    const f32x2 q = ffma2(px, ux, ffma2(py, uy, pack2(A.z, A.z)));
+    const f32x2 n = ffma2(py, ux, ffma2(px, nuy, pack2(A.w, A.w)));
+    float qa, qb;
+    unpack2(q, qa, qb);
+    const f32x2 e = pack2(__saturatef(fabsf(qa) + Bv.x), __saturatef(fabsf(qb) + Bv.x));
+    return ffma2(e, e, fmul2(n, n));
+}
+
+__global__ void __launch_bounds__(PP_SCAN_THREADS)
+pp_scan_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, int n_poses,
+               int front_axle, double wb, int32_t* __restrict__ best_k) {
+    __shared__ float s_d[PP_PARTS][PP_CTA_POSES];
+    __shared__ int s_b[PP_PARTS][PP_CTA_POSES];
+    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
+    const int base = blockIdx.x * PP_CTA_POSES;
+    double qx[PP_LANE_POSES], qy[PP_LANE_POSES];
+#pragma unroll
+    for (int p = 0; p < PP_LANE_POSES; ++p) {
+        double qth;
+        pp_query_point(poses, pose_stride, min(base + p * 32 + lane, n_poses - 1), front_axle, wb,
+                       qx[p], qy[p], qth);
+    }
+    const int nseg = tr.n - 1, nblk = (nseg + 31) >> 5;
+    const int b0 = (int)((long long)nblk * part / PP_PARTS);
+    const int b1 = (int)((long long)nblk * (part + 1) / PP_PARTS);
+    // The scan keeps only the running minimum of each 32-segment block (no index bookkeeping
+    // in the inner loop) and remembers the best block; the exact index is recovered afterwards
+    // by re-scanning that one block.
+    float best[PP_LANE_POSES];
+    int bblk[PP_LANE_POSES];
+#pragma unroll
+    for (int p = 0; p < PP_LANE_POSES; ++p) { best[p] = CUDART_INF_F; bblk[p] = 0; }
+    for (int blk = b0; blk < b1; ++blk) {
+        const double2 o = tr.blk_origin[blk];
+        f32x2 px[PP_LANE_POSES / 2], py[PP_LANE_POSES / 2];
+#pragma unroll
+        for (int p = 0; p < PP_LANE_POSES / 2; ++p) {
+            px[p] = pack2((float)(qx[2 * p] - o.x) * TRACK_SCALE, (float)(qx[2 * p + 1] - o.x) * TRACK_SCALE);
+            py[p] = pack2((float)(qy[2 * p] - o.y) * TRACK_SCALE, (float)(qy[2 * p + 1] - o.y) * TRACK_SCALE);
+        }
+        const int k0 = blk << 5;
+        const int kn = min(32, nseg - k0);   // the track's last block may be partial
+        float m[PP_LANE_POSES];
+#pragma unroll
+        for (int p = 0; p < PP_LANE_POSES; ++p) m[p] = CUDART_INF_F;
+        if (kn == 32) {
+#pragma unroll 2
+            for (int j = 0; j < 32; j += 2) {   // two segments per trip, minima by FMNMX3
+                const float4 A0 = __ldg(tr.segA + k0 + j), A1 = __ldg(tr.segA + k0 + j + 1);
+                const float2 B0 = __ldg(tr.segB + k0 + j), B1 = __ldg(tr.segB + k0 + j + 1);
+#pragma unroll
+                for (int p = 0; p < PP_LANE_POSES / 2; ++p) {
+                    float a0, a1, c0, c1;
+                    unpack2(track_seg_d2_pair(px[p], py[p], A0, B0), a0, a1);
+                    unpack2(track_seg_d2_pair(px[p], py[p], A1, B1), c0, c1);
+                    m[2 * p] = fmin3(m[2 * p], a0, c0);
+                    m[2 * p + 1] = fmin3(m[2 * p + 1], a1, c1);
+                }
             }
-            sA[q] = A;
-            sB[q] = Bv;
+        } else {
+            for (int j = 0; j < kn; ++j) {
+                const float4 A0 = __ldg(tr.segA + k0 + j);
+                const float2 B0 = __ldg(tr.segB + k0 + j);
+#pragma unroll
+                for (int p = 0; p < PP_LANE_POSES / 2; ++p) {
+                    float a0, a1;
+                    unpack2(track_seg_d2_pair(px[p], py[p], A0, B0), a0, a1);
+                    m[2 * p] = fminf(m[2 * p], a0);
+                    m[2 * p + 1] = fminf(m[2 * p + 1], a1);
+                }
+            }
         }
-        for (int b = threadIdx.x; b < nblk; b += blockDim.x) sO[b] = tr.blk_origin[(c0 >> 5) + b];
-        __syncthreads();
-        for (int blk = 0; blk < nblk; ++blk) {
-            const double2 o = sO[blk];
-            const float prx = (float)(qx - o.x), pry = (float)(qy - o.y);
-            const int j0 = blk << 5;
-            float m = CUDART_INF_F;
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) m = fminf(m, pp_seg_d2(prx, pry, sA[j0 + j], sB[j0 + j]));
-            if (m < best) { best = m; bblk = (c0 >> 5) + blk; }
-        }
-        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < PP_LANE_POSES; ++p)
+            if (m[p] < best[p]) { best[p] = m[p]; bblk[p] = blk; }
     }
-    if (!active) return;
+#pragma unroll
+    for (int p = 0; p < PP_LANE_POSES; ++p) {
+        s_d[part][p * 32 + lane] = best[p];
+        s_b[part][p * 32 + lane] = bblk[p];
+    }
+    __syncthreads();
+    // Each warp finishes PP_CTA_POSES / PP_PARTS poses: lane i < 16 combines pose i's block
+    // minima over the parts (track order, strict <: the first minimum, utils.py:66); then, pose
+    // by pose, the 32 lanes evaluate the 32 segments of the winning block and the lowest lane
+    // that attains the block minimum gives the segment index.
+    constexpr int PER_WARP = PP_CTA_POSES / PP_PARTS;
+    int my_blk = 0;
+    if (lane < PER_WARP) {
+        const int pl = part * PER_WARP + lane;
+        float d = s_d[0][pl];
+        my_blk = s_b[0][pl];
+#pragma unroll
+        for (int q = 1; q < PP_PARTS; ++q)
+            if (s_d[q][pl] < d) { d = s_d[q][pl]; my_blk = s_b[q][pl]; }
+    }
+    for (int i = 0; i < PER_WARP; ++i) {
+        const int gid = base + part * PER_WARP + i;
+        if (gid >= n_poses) break;   // warp-uniform
+        const int blk = __shfl_sync(F1L_FULL, my_blk, i);
+        double x, y, th;
+        pp_query_point(poses, pose_stride, gid, front_axle, wb, x, y, th);
+        const double2 o = tr.blk_origin[blk];
+        const float prx = (float)(x - o.x) * TRACK_SCALE, pry = (float)(y - o.y) * TRACK_SCALE;
+        const int k = (blk << 5) + lane;
+        float d2 = CUDART_INF_F;
+        if (k < nseg) d2 = track_seg_d2(prx, pry, __ldg(tr.segA + k), __ldg(tr.segB + k));
+        const unsigned bits = __float_as_uint(d2);   // d2 >= 0: the bit pattern orders like the value
+        const unsigned mn = __reduce_min_sync(F1L_FULL, bits);
+        const unsigned hit = __ballot_sync(F1L_FULL, bits == mn);
+        if (lane == 0) best_k[gid] = (blk << 5) + __ffs(hit) - 1;
+    }
+}
 
-    // first segment of the best block that attains the block minimum (same FP32 arithmetic)
-    int bk = bblk << 5;
-    {
-        const double2 o = tr.blk_origin[bblk];
-        const float prx = (float)(qx - o.x), pry = (float)(qy - o.y);
-        float m = CUDART_INF_F;
-        const int k1 = min((bblk << 5) + 32, nseg);
-        for (int k = bblk << 5; k < k1; ++k) {
-            const float d2 = pp_seg_d2(prx, pry, __ldg(tr.segA + k), __ldg(tr.segB + k));
-            if (d2 < m) { m = d2; bk = k; }
-        }
-    }
+// `best_k` may alias out.nearest_i (each thread reads its element before writing it)
+__global__ void __launch_bounds__(PP_THREADS)
+pp_finish_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, int n_poses, double L, double wb,
+                 double max_reacquire, int front_axle, double k_path, const int32_t* best_k, PPOut out) {
+    const int nseg = tr.n - 1;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n_poses) return;
+    const int pid = gid;
+    double qx, qy, qth;
+    pp_query_point(poses, pose_stride, pid, front_axle, wb, qx, qy, qth);
+    const int bk = best_k[gid];
     // float64 epilogue: exact nearest among the neighbours, then pure_pursuit.py:69-83
     const Nearest64 nr = refine_nearest64(tr.xy, nseg, qx, qy, bk);
     if (front_axle) {

@@ -32,8 +32,8 @@ marks = [("prologue (window table)", k0),
          ("arc samples", find("// ---- arc samples", k0)),
          ("curvature / validity / slab", find("// ---- curvature terms", k0)),
          ("similarity + collision", find("// ---- similarity", k0)),
-         ("deviation: setup", find("// ---- raceline deviation", k0)),
-         ("deviation: segment loop", find("float4 T0 = sT[2 * ggi]", k0)),
+         ("deviation: setup + pruning bound", find("// ---- raceline deviation", k0)),
+         ("deviation: segment loop", find("float4 T0 = sT[2 * (k_begin + ggi)]", k0)),
          ("deviation: reduce", find("for (int o = 1; o < GG; o <<= 1)", k0) - 1),
          ("cost + output + next candidate", find("if (!(flags & (F1L_FLAG_COLLIDE_OPP", k0)),
          ("end", find("// K5: select", k0))]
