@@ -119,6 +119,22 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def profiled_dram_bytes(path=os.path.join(ROOT, "profiles", "r1_eval_kernel.md")):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one eval_kernel launch of the bench workload,
+    from the committed ncu --set full summary (bench.py cannot run under ncu itself)."""
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, seen = 0.0, 0
+    try:
+        for ln in open(path):
+            c = [x.strip() for x in ln.split("|")]
+            if len(c) > 3 and c[1] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(c[2]) * unit[c[3]]
+                seen += 1
+    except Exception:
+        return None
+    return int(tot) if seen == 2 else None
+
+
 def workload(seed_rank, S):
     track = synth.ellipse_track()
     grid = synth.corridor_grid()
@@ -520,7 +536,7 @@ def run_ours(args):
             "mufu_peak_gops": mufu_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one eval_kernel launch of this workload
             # (ncu --set full; profiles/r1_eval_kernel.md) -- bench.py cannot run under ncu itself
-            "traffic": 50935808 if S == S_PER_GPU else None,
+            "traffic": profiled_dram_bytes() if (S == S_PER_GPU and not args.prune) else None,
             "traffic_source": "profiles/r1_eval_kernel.md",
             "hbm": {"algorithmic_bytes_per_step": hbm_bytes,
                     "achieved_gbs": hbm_bytes / (ms_total / args.steps * 1e-3) / 1e9},

@@ -1,6 +1,7 @@
 """Writes the judged profile summaries under profiles/ from the scratch ncu outputs in gpurun_out/.
 
-    python tools/make_profile_summary.py <tag> <launches.csv> <eval.ncu-rep> [<pp.ncu-rep>]
+    python tools/make_profile_summary.py <tag> <launches.csv> <eval.ncu-rep> [<pp_scan.ncu-rep>
+                                         [<eval_prune.ncu-rep>]]
 """
 import csv
 import os
@@ -10,6 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag, launches, eval_rep = sys.argv[1], sys.argv[2], sys.argv[3]
 pp_rep = sys.argv[4] if len(sys.argv) > 4 else None
+prune_rep = sys.argv[5] if len(sys.argv) > 5 else None
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
@@ -42,12 +44,12 @@ lines = ["# ncu launch list, %s" % tag, "",
          "%d launches captured; the device-resident steps (eval grid = 100000 CTAs):" % len(seq), "",
          "| step | kernel | grid | ms | share of step |", "|---|---|---|---|---|"]
 for si, i in enumerate(big):
-    grp = seq[i - 2:i + 2]
+    grp = seq[i - 3:i + 2]   # pp_scan, pp_finish, sample_warp, eval, select
     tot = sum(v for _, _, v in grp)
     for n, g, v in grp:
         lines.append("| %d | %s | %s | %.4f | %.1f %% |" % (si, n, g, v, 100 * v / tot))
 lines += ["", "Other launches: LUT build, clearance map (2), peak microbenchmarks (6), and the chunked "
-          "end-to-end arm (8192-scenario chunks of the same four kernels)."]
+          "end-to-end arm (8192-scenario chunks of the same five kernels)."]
 open(os.path.join(out_dir, "%s_launches.md" % tag), "w").write("\n".join(lines) + "\n")
 
 
@@ -69,10 +71,21 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__thread_inst_executed_per_inst_executed.ratio",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.pct_of_peak_sustained_elapsed",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.max",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum"]
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio"]
 
 
-def kernel_summary(rep, title, kern_sub, name):
+def kernel_summary(rep, title, kern_sub, name, stages=False):
     m = raw_metrics(rep)
     src_csv = os.path.join(ROOT, "gpurun_out", name + "_src.csv")
     with open(src_csv, "w") as f:
@@ -89,14 +102,33 @@ def kernel_summary(rep, title, kern_sub, name):
     for k in WANT:
         if k in m:
             lines.append("| %s | %s | %s |" % (k, m[k][1], m[k][0]))
+    if stages:
+        reg = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_regions.py"), src_csv, kern_sub],
+                             capture_output=True, text=True).stdout
+        lines += ["", "## stages (tools/ncu_regions.py: outermost call site of every SASS instruction)", "",
+                  reg.strip()]
     lines += ["", "## instruction mix (warp-instructions executed)", "", "```", mix.strip(), "```", "",
               "## stall samples by CUDA source line", "", "```", by_line.strip(), "```"]
     open(os.path.join(out_dir, "%s.md" % name), "w").write("\n".join(lines) + "\n")
 
 
-kernel_summary(eval_rep, "eval_kernel<4,13,8,7,4> (K3+K4), bench workload, %s" % tag,
-               "eval_kernelILi4ELi13ELi8ELi7", "%s_eval_kernel" % tag)
+def kernel_of(rep):
+    """mangled-name substring of the (single) kernel in a report"""
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    name = rows[2][rows[0].index("Kernel Name")]
+    return name
+
+
+ek = kernel_of(eval_rep)
+targs = ek[ek.index("<") + 1:ek.index(">")].replace(" ", "").split(",")
+sub = "eval_kernelILi%sELi%sELi%sELi%sELi%s" % tuple(targs)
+kernel_summary(eval_rep, "%s (K3+K4), bench workload (every window segment tested), %s" % (ek.split("(")[0].replace("void ", ""), tag),
+               sub, "%s_eval_kernel" % tag, stages=True)
 if pp_rep:
-    kernel_summary(pp_rep, "pp_batch_kernel (K1), 10^5 poses x 1999 segments, %s" % tag, "pp_batch_kernel",
-                   "%s_pp_batch_kernel" % tag)
+    kernel_summary(pp_rep, "pp_scan_kernel (K1 scan), 10^5 poses x 1999 segments, %s" % tag, "pp_scan_kernel",
+                   "%s_pp_scan_kernel" % tag)
+if prune_rep:
+    kernel_summary(prune_rep, "%s (K3+K4), bench workload with prune_window = 1, %s" % (ek.split("(")[0].replace("void ", ""), tag),
+                   sub, "%s_eval_kernel_pruned" % tag, stages=True)
 print("written to", out_dir)
