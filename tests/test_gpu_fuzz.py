@@ -29,6 +29,7 @@ def _case(seed):
         car_length=float(rng.uniform(0.4, 0.7)), car_width=float(rng.uniform(0.2, 0.4)),
         use_goal_kappa=int(rng.integers(0, 2)), literal_tracker=int(rng.integers(0, 2)),
         tracker_lookahead=float(rng.uniform(0.4, 1.2)),
+        prune_window=int(rng.integers(0, 2)),
     )
     w = rng.uniform(0.05, 1.0, 5)
     cfg["weights"] = list(w / w.sum())

@@ -145,3 +145,29 @@ def test_stanley_front_axle_matches_reference(golden_spielberg):
         StanleyPlanner().plan(0.0, 0.0, 0.0, 1.0)
     with pytest.raises(ValueError):
         pl.plan(0.0, 0.0, 0.0, 1.0, waypoints=np.zeros((5, 3)))
+
+
+@pytest.mark.parametrize("n_wp", [2, 3, 9, 32, 33, 34, 65, 255, 257, 1025])
+@pytest.mark.parametrize("n_poses", [1, 31, 129, 300])
+def test_scan_shapes_small_tracks_and_ragged_batches(n_wp, n_poses):
+    """K1's scan splits the track's 32-segment blocks over the 8 warps of a CTA and packs four
+    poses per lane: tracks with fewer blocks than warps, partial last blocks and batches that are
+    not a multiple of 128 poses must give the oracle's answer."""
+    from f1tenth_planning_b200.engine import Engine
+    rng = np.random.default_rng(n_wp * 1000 + n_poses)
+    phi = np.sort(rng.uniform(0.0, 1.5 * np.pi, n_wp))     # open arc, irregular spacing
+    track = np.stack([12.0 * np.cos(phi), 7.0 * np.sin(phi), np.full(n_wp, 3.0),
+                      np.zeros(n_wp), np.zeros(n_wp)], axis=1)
+    eng = Engine()
+    eng.set_track(track)
+    poses = np.stack([rng.uniform(-14, 14, n_poses), rng.uniform(-9, 9, n_poses),
+                      rng.uniform(-np.pi, np.pi, n_poses)], axis=1)
+    r = eng.pure_pursuit_batch(poses, 0.9)
+    o = co.pure_pursuit_batch(track, poses, 0.9)
+    same = r.nearest_i == o["nearest_i"]
+    # an FP32 scan may pick a neighbour when two segments tie to ~1e-7 m; the distance still agrees
+    np.testing.assert_allclose(r.nearest[:, 2], o["nearest"][:, 2], rtol=1e-9, atol=1e-9)
+    assert same.mean() >= 0.97
+    np.testing.assert_allclose(r.nearest[same], o["nearest"][same], rtol=1e-9, atol=1e-9)
+    np.testing.assert_array_equal(r.status[same], o["status"][same])
+    np.testing.assert_allclose(r.actuation[same], o["actuation"][same], rtol=1e-9, atol=1e-9)
