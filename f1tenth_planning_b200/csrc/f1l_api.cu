@@ -329,6 +329,7 @@ size_t eval_smem_bytes(int nseg_pad, int warps, int M) {
     const EvalShape sh = eval_shape(M);
     size_t b = (size_t)(nseg_pad + EVAL_SEG_PAD) * (2 * sizeof(float4));
     b += (size_t)warps * 2 * (((sh.s + 1) / 2) * sh.sg * 2) * sizeof(float);   // pair-layout slabs
+    b += (size_t)warps * 2 * (sh.s * sh.sg) * sizeof(float4);                  // grid-probe lists
     b += (size_t)((M + 3) & ~3) * sizeof(float);
     b += F1L_MAX_OPP * sizeof(float4);
     return b;

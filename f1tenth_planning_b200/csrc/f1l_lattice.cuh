@@ -564,15 +564,6 @@ __device__ __forceinline__ bool grid_hit(const uint8_t* __restrict__ occ, int gw
     return __ldg(occ + (size_t)row * gw + col) != 0;
 }
 
-// a[j] of a register array with a run-time j (selects, no local memory)
-template <int N>
-__device__ __forceinline__ float pick(const float (&a)[N], int j) {
-    float r = a[0];
-#pragma unroll
-    for (int k = 1; k < N; ++k) r = (j == k) ? a[k] : r;
-    return r;
-}
-
 __device__ __forceinline__ float fast_sqrt(float x) {
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -758,6 +749,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
     constexpr int SROWS = (S + 1) / 2;
     constexpr int SLAB = SROWS * SG * 2;                                     // floats per coordinate
     float* slab_all = sprev + ((M + 3) & ~3);                                // [NW][2][SLAB]
+    // per-warp list of the footprints that need their nine grid probes: centre and half-axes
+    // in grid-cell coordinates, two float4 per entry
+    constexpr int PCAP = S * SG;
+    float4* plist_all = reinterpret_cast<float4*>(slab_all + (size_t)NW * 2 * SLAB);   // [NW][PCAP][2]
 
     int s, cta;
     if (a.ctas_per_scn == 1) { s = blockIdx.x; cta = 0; }
@@ -972,39 +967,53 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 }
             }
             if (has_grid) {
-                // samples whose clearance does not prove the footprint free: nine probes each.
-                // One copy of the probe code serves all of a lane's samples (register arrays are
-                // read through selects), the probes run as a rolled loop over a sign table --
-                // the unrolled form was 750 instructions of instruction-cache footprint.
-                unsigned need = 0;
+                // Samples whose clearance does not prove the footprint free get their nine probes.
+                // They are few and scattered over the lanes (walls are near the outer goals
+                // only), so the warp shares them: each owner lane writes the footprint of its
+                // needy samples into a per-warp list, then all 32 lanes take (footprint, probe)
+                // pairs from it -- ~6x fewer instructions than every lane probing its own
+                // samples while the others idle.
+                unsigned nm[IPL];
+                int total = 0;
 #pragma unroll
-                for (int j = 0; j < IPL; ++j)
-                    if (lane * IPL + j < M && clr[j] <= a.grid.probe_reach) need |= 1u << j;
-                while (need) {
-                    const int j = __ffs(need) - 1;
-                    need &= need - 1;
-                    const float xj = pick<IPL>(x, j), yj = pick<IPL>(y, j);
-                    const float cj = pick<IPL>(cs, j), sj = pick<IPL>(sn, j);
-                    // footprint centre and half-axes in grid-cell coordinates
-                    const float ccx = fa(fa(fm(A00, xj), fm(A01, yj)), gfx);
-                    const float ccy = fa(fa(fm(A10, xj), fm(A11, yj)), gfy);
-                    const float lx = fm(cj, hl), ly = fm(sj, hl);      // body x axis * hl
-                    const float wx = fm(-sj, hw), wy = fm(cj, hw);     // body y axis * hw
-                    const float elx = fa(fm(A00, lx), fm(A01, ly)), ely = fa(fm(A10, lx), fm(A11, ly));
-                    const float ewx = fa(fm(A00, wx), fm(A01, wy)), ewy = fa(fm(A10, wx), fm(A11, wy));
+                for (int j = 0; j < IPL; ++j) {
+                    nm[j] = __ballot_sync(F1L_FULL, lane * IPL + j < M && clr[j] <= a.grid.probe_reach);
+                    total += __popc(nm[j]);
+                }
+                if (total) {   // warp-uniform
+                    float4* pl = plist_all + (size_t)wid * (2 * PCAP);
+                    int rank0 = 0;
+#pragma unroll
+                    for (int j = 0; j < IPL; ++j) {
+                        if ((nm[j] >> lane) & 1u) {
+                            const int r = rank0 + __popc(nm[j] & ((1u << lane) - 1u));
+                            // footprint centre and half-axes in grid-cell coordinates
+                            const float ccx = fa(fa(fm(A00, x[j]), fm(A01, y[j])), gfx);
+                            const float ccy = fa(fa(fm(A10, x[j]), fm(A11, y[j])), gfy);
+                            const float lx = fm(cs[j], hl), ly = fm(sn[j], hl);    // body x axis * hl
+                            const float wx = fm(-sn[j], hw), wy = fm(cs[j], hw);   // body y axis * hw
+                            pl[2 * r] = make_float4(ccx, ccy, fa(fm(A00, lx), fm(A01, ly)),
+                                                    fa(fm(A10, lx), fm(A11, ly)));
+                            pl[2 * r + 1] = make_float4(fa(fm(A00, wx), fm(A01, wy)),
+                                                        fa(fm(A10, wx), fm(A11, wy)), 0.0f, 0.0f);
+                        }
+                        rank0 += __popc(nm[j]);
+                    }
+                    __syncwarp();
                     // 4 corners, 4 edge mid-points, centre (SURVEY B.6, P = 9): probe p sits at
                     // centre + sa * l-axis + sb * w-axis with (sa, sb) in {-1, 0, 1}, two bits each.
                     // x + (+-1) * e and x + 0 * e round like x +- e and x, so the cells are the
                     // ones the oracle's float32 mirror visits.
-                    bool h = false;
-#pragma unroll 1
-                    for (int p = 0; p < 9; ++p) {
+                    const int nwork = total * 9;
+                    for (int w = lane; w < nwork; w += 32) {
+                        const int fp = w / 9, p = w - 9 * fp;
+                        const float4 P0 = pl[2 * fp], P1 = pl[2 * fp + 1];
                         const float sa = (float)(int)((0x1520au >> (2 * p)) & 3u) - 1.0f;
                         const float sb = (float)(int)((0x12522u >> (2 * p)) & 3u) - 1.0f;
-                        h |= grid_hit(occ, gw, gh, gix, giy, fa(fa(ccx, fm(sa, elx)), fm(sb, ewx)),
-                                      fa(fa(ccy, fm(sa, ely)), fm(sb, ewy)));
+                        hit_map |= grid_hit(occ, gw, gh, gix, giy, fa(fa(P0.x, fm(sa, P0.z)), fm(sb, P1.x)),
+                                            fa(fa(P0.y, fm(sa, P0.w)), fm(sb, P1.y)));
                     }
-                    hit_map |= h;
+                    __syncwarp();
                 }
             }
             t_sim = warp_sum(sim);
