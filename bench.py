@@ -530,7 +530,7 @@ def run_ours(args):
             "frac": achieved_tflops / fp32_peak if achieved_tflops else None,
             "peak_source": "FFMA microbenchmark measured in this run (f1l_measure_peaks); "
                            "MEASURED_PEAKS.json has no FP32 entry; nominal 74.4",
-            "kernel": "eval_kernel<4,13,8>", "kernel_ms": k_eval, "kernel_launches_timed": n_timed,
+            "kernel": "eval_kernel<4,13,8,4,7>", "kernel_ms": k_eval, "kernel_launches_timed": n_timed,
             "kernel_share_of_step": k_eval / (ms_total / args.steps) if k_eval else None,
             "flops_per_launch": step_flops,
             "mufu_peak_gops": mufu_peak,
