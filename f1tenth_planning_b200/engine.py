@@ -229,6 +229,8 @@ class Engine:
         states = np.zeros((g.shape[0], M, 4), np.float32)
         params = np.zeros((g.shape[0], 4), np.float32)
         flags = np.zeros(g.shape[0], np.uint8)
+        if g.shape[0] == 0:
+            return states, params, flags != 0
         self._ck(self._L.f1l_generate(self._h, _ptr(g, _dp), g.shape[0], _ptr(states, _fp),
                                       _ptr(params, _fp), _ptr(flags, _bp)))
         return states, params, (flags & FLAG_VALID) != 0
@@ -263,6 +265,8 @@ class Engine:
         flags = o.get("flags") if want_flags else None
         if want_flags and flags is None:
             flags = np.zeros((S, Cn), np.uint8)
+        if S == 0:   # an empty batch is a valid (empty) answer, not an error
+            return BatchPlan(best_idx, best_cost, best_traj, costs, flags, steer_speed)
         self._ck(self._L.f1l_plan_batch(self._h, _vp(poses), _vp(opponents), _vp(n_opp), S, K,
                                         _vp(best_idx), _vp(best_cost), _vp(best_traj), _vp(costs),
                                         _vp(flags), _vp(steer_speed)))
@@ -293,6 +297,8 @@ class Engine:
         look_i = o.get("lookahead_i") if o.get("lookahead_i") is not None else np.zeros(B, np.int32)
         act = o.get("actuation") if o.get("actuation") is not None else np.zeros((B, 2))
         status = o.get("status") if o.get("status") is not None else np.zeros(B, np.int32)
+        if B == 0:
+            return PurePursuitBatch(nearest, nearest_i, look, look_i, act, status)
         self._ck(self._L.f1l_pure_pursuit_batch(self._h, _vp(poses), B, float(lookahead_distance),
                                                 _vp(nearest), _vp(nearest_i), _vp(look),
                                                 _vp(look_i), _vp(act), _vp(status)))
@@ -314,6 +320,8 @@ class Engine:
         st = _f64(states).reshape(-1, 4)
         front = np.zeros((st.shape[0], 6))
         idx = np.zeros(st.shape[0], np.int32)
+        if st.shape[0] == 0:
+            return front, idx
         self._ck(self._L.f1l_front_axle_batch(self._h, _vp(st), st.shape[0], float(wheelbase),
                                               float(k_path), _vp(front), _vp(idx)))
         return front, idx
@@ -324,6 +332,8 @@ class Engine:
         n = pts.shape[0]
         out = np.zeros((n, 4))
         out_i = np.zeros(n, np.int32)
+        if n == 0:
+            return out, out_i
         self._ck(self._L.f1l_intersect_point_batch(self._h, _ptr(pts, _dp), _ptr(t0, _dp), n,
                                                    float(radius), int(bool(wrap)), _ptr(out, _dp),
                                                    _ptr(out_i, _ip)))

@@ -332,3 +332,45 @@ def test_pruned_window_batch_and_hairpin(golden_spielberg):
     assert np.isfinite(a.costs).sum() > 1000
     assert np.array_equal(a.costs, b.costs) and np.array_equal(a.flags, b.flags)
     assert np.array_equal(a.best_idx, b.best_idx) and np.array_equal(a.best_traj, b.best_traj)
+
+
+def test_empty_ragged_and_extreme_inputs(ellipse, corridor):
+    """the edges of the input space: empty batches, no / the maximum number of opponents, one
+    candidate, a window longer than the track, a non-finite pose"""
+    la, wd = synth.goal_grid(1)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, grid=corridor, kappa_max=0.0)
+    # empty batches are empty answers
+    b = eng.plan_batch(np.zeros((0, 4)), np.zeros((0, 2, 3)), np.zeros(0, np.int32), want_flags=True)
+    assert b.best_idx.shape == (0,) and b.costs.shape == (0, 28) and b.best_traj.shape == (0, 100, 4)
+    r = eng.pure_pursuit_batch(np.zeros((0, 3)), 0.8)
+    assert r.nearest.shape == (0, 4) and r.status.shape == (0,)
+    assert eng.front_axle_batch(np.zeros((0, 4)), 0.33)[0].shape == (0, 6)
+    assert eng.generate(np.zeros((0, 3)))[0].shape == (0, 100, 4)
+    # ragged opponent counts, including zero, in one batch
+    poses, opp, n_opp = synth.scenario_batch(ellipse, 64, 16, 9)
+    n_opp = (np.arange(64) % 17).astype(np.int32)          # 0 .. 16 = F1L_MAX_OPP
+    bb = eng.plan_batch(poses, opp, n_opp, want_flags=True)
+    for s in (0, 5, 16, 33):
+        d = eng.plan(poses[s], opp[s, :n_opp[s]] if n_opp[s] else None, update_prev=False)
+        assert np.array_equal(d.costs, bb.costs[s]) and d.best_idx == bb.best_idx[s]
+        o = co.plan(cfg, world, poses[s], opp[s, :n_opp[s]] if n_opp[s] else None, want_states=True)
+        H.compare_plan(eng.plan(poses[s], opp[s, :n_opp[s]] if n_opp[s] else None,
+                                update_prev=False, want_states=True), o, cfg)
+    with pytest.raises(ValueError):
+        eng.plan(poses[0], np.zeros((17, 3)))
+    # one candidate
+    eng.set_goal_grid([0.8], [0.0])
+    d = eng.plan(poses[1], None, update_prev=False)
+    assert d.costs.shape == (1,) and d.best_idx == 0
+    eng.set_goal_grid(la, wd)
+    # a window longer than the track is the whole track
+    eng.configure(window=10 ** 6)
+    d_big = eng.plan(poses[2], opp[2, :2], update_prev=False)
+    eng.configure(window=0)
+    d_all = eng.plan(poses[2], opp[2, :2], update_prev=False)
+    assert np.array_equal(d_big.costs, d_all.costs)
+    # a non-finite pose yields "no feasible candidate", not a hang or a crash
+    bad = poses[3].copy()
+    bad[0] = np.nan
+    d = eng.plan(bad, None, update_prev=False)
+    assert d.no_feasible and not np.isfinite(d.costs).any()
