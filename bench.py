@@ -234,6 +234,31 @@ def extras(track, grid, device):
     import torch
     from f1tenth_planning_b200.engine import Engine
     out = {}
+    # C1: the reference's own case -- LatticePlanner.plan(), default 4x7 grid, one opponent --
+    # through the public class, next to the CPU oracle's plan() of the same queries
+    from f1tenth_planning_b200 import LatticePlanner
+    from oracle import c_oracle as co
+    la1, wd1 = synth.goal_grid(1)
+    pl = LatticePlanner(waypoints=track, device=device, n_samples=100, window=128)
+    pl.set_map(*grid)
+    p1, o1, _ = synth.scenario_batch(track, 64, 1, 1001)
+    for i in range(5):
+        pl.plan(*p1[i], opponent_poses=o1[i])
+    ts = []
+    for i in range(1000):
+        t = time.perf_counter()
+        pl.plan(*p1[i % 64], opponent_poses=o1[i % 64])
+        ts.append(time.perf_counter() - t)
+    out["c1_plan_p50_us"] = 1e6 * float(np.percentile(ts, 50))
+    out["c1_plan_p99_us"] = 1e6 * float(np.percentile(ts, 99))
+    ocfg = co.default_config(n_samples=100, window=128)
+    world = co.World_(track, la1, wd1, grid=grid[0], grid_origin=grid[1], grid_res=grid[2])
+    ts = []
+    for i in range(40):
+        t = time.perf_counter()
+        co.plan(ocfg, world, p1[i % 64], o1[i % 64])
+        ts.append(time.perf_counter() - t)
+    out["c1_cpu_oracle_plan_p50_us"] = 1e6 * float(np.percentile(ts, 50))
     # C3: single query, 4096 candidates
     la, wd = synth.goal_grid(3)
     eng = Engine(device=device, n_samples=100, window=128)

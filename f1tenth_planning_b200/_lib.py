@@ -43,8 +43,9 @@ class PlanResult(C.Structure):
     _fields_ = [("steer", C.c_double), ("speed", C.c_double), ("best_idx", C.c_int32),
                 ("no_feasible", C.c_int32), ("tracker_found", C.c_int32),
                 ("n_candidates", C.c_int32), ("best_cost", C.c_float), ("reserved", C.c_int32),
-                ("best_traj", _fp), ("costs", _fp), ("terms", _fp), ("flags", _bp),
-                ("goals", _fp), ("params", _fp), ("states", _fp), ("headings", _fp)]
+                # float* / uint8_t* in the header; void* here so that plain addresses can be stored
+                ("best_traj", _vp), ("costs", _vp), ("terms", _vp), ("flags", _vp),
+                ("goals", _vp), ("params", _vp), ("states", _vp), ("headings", _vp)]
 
 
 # name -> (restype, argtypes); must list every symbol include/f1l.h declares
@@ -66,9 +67,9 @@ SIGNATURES = {
     "f1l_set_lut": (C.c_int, [_vp, _fp, _ip, _dp]),
     "f1l_set_prev_path": (C.c_int, [_vp, _fp, C.c_int]),
     "f1l_clear_prev_path": (C.c_int, [_vp]),
-    "f1l_plan": (C.c_int, [_vp, _dp, _dp, C.c_int, C.c_int, C.POINTER(PlanResult)]),
-    "f1l_plan_shard": (C.c_int, [_vp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.POINTER(PlanResult)]),
-    "f1l_plan_goals": (C.c_int, [_vp, _dp, _dp, C.c_int, _dp, C.c_int, C.c_int,
+    "f1l_plan": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.POINTER(PlanResult)]),
+    "f1l_plan_shard": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(PlanResult)]),
+    "f1l_plan_goals": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int,
                                  C.POINTER(PlanResult)]),
     "f1l_generate": (C.c_int, [_vp, _dp, C.c_int, _fp, _fp, _bp]),
     "f1l_plan_batch_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp,

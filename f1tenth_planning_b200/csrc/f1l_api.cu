@@ -67,12 +67,16 @@ struct f1l_ctx {
     DevBuf prev;
     int has_prev = 0, prev_m = 0;
     // single-query device buffers
-    DevBuf q_res, q_in, q_goals, q_ctx, q_centres, q_best, q_costs,
-        q_terms, q_flags, q_gout, q_params, q_states, q_headings;
+    DevBuf q_res, q_in, q_goals, q_ctx, q_centres, q_best, q_states, q_headings, q_params, q_flags;
     // pinned staging for the single query
     void* h_in = nullptr;   // pose + opponents
     void* h_out = nullptr;  // header + best trajectory
     size_t h_out_cap = 0;
+    // per-candidate detail block of a single query (costs | terms | goals | params | flags): one
+    // device block, one D2H into pinned staging, then plain copies into the caller's arrays
+    DevBuf q_detail;
+    void* h_detail = nullptr;
+    size_t h_detail_cap = 0;
     // deviation-pass work counters (f1l_get_stats)
     DevBuf stats;
     // batch (device-pointer API) scratch
@@ -712,8 +716,7 @@ int f1l_destroy(f1l_handle h) {
     cudaDeviceSynchronize();
     DevBuf* bufs[] = {&h->xy, &h->v, &h->psi, &h->kappa, &h->segA, &h->segB, &h->blk, &h->grid, &h->clear, &h->clear_tmp,
                       &h->lut, &h->lookaheads, &h->widths, &h->prev, &h->q_res, &h->q_in, &h->q_goals,
-                      &h->q_ctx, &h->q_centres, &h->q_best, &h->q_costs, &h->q_terms, &h->q_flags, &h->q_gout,
-                      &h->q_params, &h->q_states, &h->q_headings, &h->b_ctx, &h->b_centres,
+                      &h->q_ctx, &h->q_centres, &h->q_best, &h->q_detail, &h->q_params, &h->q_flags, &h->q_states, &h->q_headings, &h->b_ctx, &h->b_centres,
                       &h->b_best, &h->b_near_i, &h->b_near4, &h->stats, &h->m_in, &h->m_in2, &h->m_o0, &h->m_o1, &h->m_o2, &h->m_o3,
                       &h->m_o4, &h->m_o5, &h->pp_bk};
     for (DevBuf* b : bufs) release(*b);
@@ -730,6 +733,7 @@ int f1l_destroy(f1l_handle h) {
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->h_in) cudaFreeHost(h->h_in);
     if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_detail) cudaFreeHost(h->h_detail);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return F1L_OK;
@@ -917,12 +921,24 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     ENS(h->q_ctx, sizeof(QueryCtx));
     ENS(h->q_centres, sizeof(Centre) * (size_t)(h->nL > 0 ? h->nL : 1));
     ENS(h->q_best, 8);
-    ENS(h->q_costs, (size_t)C * 4);
     ENS(h->prev, F1L_MAX_M * sizeof(float));
-    if (out->terms) ENS(h->q_terms, (size_t)C * F1L_N_TERMS * 4);
-    if (out->flags) ENS(h->q_flags, (size_t)C);
-    if (out->goals) ENS(h->q_gout, (size_t)C * 3 * 4);
-    if (out->params) ENS(h->q_params, (size_t)C * 16);
+    // detail block layout (every region 16-byte aligned)
+    const size_t c16 = ((size_t)C + 3) & ~(size_t)3;
+    const size_t off_costs = 0, off_terms = off_costs + c16 * 4, off_goals = off_terms + c16 * F1L_N_TERMS * 4;
+    const size_t off_params = off_goals + c16 * 12, off_flags = off_params + c16 * 16;
+    const size_t detail_bytes = off_flags + c16;
+    ENS(h->q_detail, detail_bytes);
+    const bool want_detail = out->costs || out->terms || out->flags || out->goals || out->params;
+    if (want_detail && h->h_detail_cap < detail_bytes) {
+        CK(cudaStreamSynchronize(st));
+        if (h->h_detail) cudaFreeHost(h->h_detail);
+        h->h_detail = nullptr;
+        h->h_detail_cap = 0;
+        CK(cudaHostAlloc(&h->h_detail, detail_bytes, cudaHostAllocDefault));
+        h->h_detail_cap = detail_bytes;
+        h->epoch++;   // the captured graph holds the old staging address
+    }
+    char* ddet = (char*)h->q_detail.p;
     if (out->states) ENS(h->q_states, (size_t)C * M * 16);
     if (out->headings) ENS(h->q_headings, (size_t)C * M * 8);
     const float4* d_goals = nullptr;
@@ -948,11 +964,11 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     o.status = (int32_t*)(dres + offsetof(QHeader, no_feasible));
     o.best_cost = (float*)(dres + offsetof(QHeader, best_cost));
     o.best_traj = (float4*)(dres + sizeof(QHeader));
-    o.costs = (float*)h->q_costs.p;
-    o.terms = out->terms ? (float*)h->q_terms.p : nullptr;
-    o.flags = out->flags ? (uint8_t*)h->q_flags.p : nullptr;
-    o.goals_out = out->goals ? (float*)h->q_gout.p : nullptr;
-    o.params = out->params ? (float4*)h->q_params.p : nullptr;
+    o.costs = (float*)(ddet + off_costs);
+    o.terms = out->terms ? (float*)(ddet + off_terms) : nullptr;
+    o.flags = out->flags ? (uint8_t*)(ddet + off_flags) : nullptr;
+    o.goals_out = out->goals ? (float*)(ddet + off_goals) : nullptr;
+    o.params = out->params ? (float4*)(ddet + off_params) : nullptr;
     o.states = out->states ? (float4*)h->q_states.p : nullptr;
     o.headings = out->headings ? (float2*)h->q_headings.p : nullptr;
     o.prev_out = update_prev ? (float*)h->prev.p : nullptr;
@@ -967,9 +983,9 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
         CK(cudaMemcpyAsync(h->q_in.p, hin, sizeof(QInput), cudaMemcpyHostToDevice, st));
         if (sharded) {
             // sharded evaluation: untouched candidates keep +inf / zero flags
-            fill_f32_kernel<<<(C + 255) / 256, 256, 0, st>>>((float*)h->q_costs.p, (size_t)C, INFINITY);
+            fill_f32_kernel<<<(C + 255) / 256, 256, 0, st>>>(o.costs, (size_t)C, INFINITY);
             h->launches += 1;
-            if (o.flags) CK(cudaMemsetAsync(h->q_flags.p, 0, (size_t)C, st));
+            if (o.flags) CK(cudaMemsetAsync(o.flags, 0, (size_t)C, st));
         }
         int r = launch_pipeline(h, st, din->pose, din->opp, &din->n_opp, 1, F1L_MAX_OPP, d_goals, C,
                                 c_begin, c_end, (QueryCtx*)h->q_ctx.p, (Centre*)h->q_centres.p,
@@ -977,12 +993,14 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
                                 h->has_prev ? (const float*)h->prev.p : nullptr, o, time_it);
         if (r != F1L_OK) return r;
         CK(cudaMemcpyAsync(hd, h->q_res.p, sizeof(QHeader) + (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+        if (want_detail)
+            CK(cudaMemcpyAsync(h->h_detail, ddet, detail_bytes, cudaMemcpyDeviceToHost, st));
         return F1L_OK;
     };
     if (h->use_graph && !goals && !sharded && !h->timing) {
         // the whole chain as one CUDA graph, re-captured only when an upload / config change or
         // the set of requested outputs alters a kernel argument
-        const unsigned long long mask = (out->terms ? 1u : 0u) | (out->flags ? 2u : 0u) |
+        const unsigned long long mask = (want_detail ? 256u : 0u) | (out->terms ? 1u : 0u) | (out->flags ? 2u : 0u) |
                                         (out->goals ? 4u : 0u) | (out->params ? 8u : 0u) |
                                         (out->states ? 16u : 0u) | (out->headings ? 32u : 0u) |
                                         (update_prev ? 64u : 0u) | (h->has_prev ? 128u : 0u);
@@ -1009,12 +1027,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
         if (r != F1L_OK) return r;
     }
 
-    // optional per-candidate arrays straight into the caller's buffers
-    if (out->costs) CK(cudaMemcpyAsync(out->costs, h->q_costs.p, (size_t)C * 4, cudaMemcpyDeviceToHost, st));
-    if (out->terms) CK(cudaMemcpyAsync(out->terms, h->q_terms.p, (size_t)C * F1L_N_TERMS * 4, cudaMemcpyDeviceToHost, st));
-    if (out->flags) CK(cudaMemcpyAsync(out->flags, h->q_flags.p, (size_t)C, cudaMemcpyDeviceToHost, st));
-    if (out->goals) CK(cudaMemcpyAsync(out->goals, h->q_gout.p, (size_t)C * 12, cudaMemcpyDeviceToHost, st));
-    if (out->params) CK(cudaMemcpyAsync(out->params, h->q_params.p, (size_t)C * 16, cudaMemcpyDeviceToHost, st));
+    // the big optional arrays go straight into the caller's buffers
     if (out->states) CK(cudaMemcpyAsync(out->states, h->q_states.p, (size_t)C * M * 16, cudaMemcpyDeviceToHost, st));
     if (out->headings) CK(cudaMemcpyAsync(out->headings, h->q_headings.p, (size_t)C * M * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1030,6 +1043,14 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     out->n_candidates = C;
     out->best_cost = hd->best_cost;
     if (out->best_traj) memcpy(out->best_traj, htraj, (size_t)M * 16);
+    if (want_detail) {
+        const char* hdet = (const char*)h->h_detail;
+        if (out->costs) memcpy(out->costs, hdet + off_costs, (size_t)C * 4);
+        if (out->terms) memcpy(out->terms, hdet + off_terms, (size_t)C * F1L_N_TERMS * 4);
+        if (out->flags) memcpy(out->flags, hdet + off_flags, (size_t)C);
+        if (out->goals) memcpy(out->goals, hdet + off_goals, (size_t)C * 12);
+        if (out->params) memcpy(out->params, hdet + off_params, (size_t)C * 16);
+    }
     return F1L_OK;
 }
 

@@ -58,6 +58,7 @@ class Engine:
         self._apply(cfg, config)
         dev = default_device() if device is None else int(device)
         _lib.check(self._L.f1l_create(C.byref(self._h), dev, C.byref(cfg)))
+        self._n_samples = int(cfg.n_samples)
         self.device = dev
         self.n_lookaheads = 0
         self.n_widths = 0
@@ -102,10 +103,7 @@ class Engine:
         cfg = self.config
         self._apply(cfg, kw)
         self._ck(self._L.f1l_set_config(self._h, C.byref(cfg)))
-
-    @property
-    def n_samples(self):
-        return self.config.n_samples
+        self._n_samples = int(cfg.n_samples)
 
     @property
     def n_candidates(self):
@@ -157,25 +155,25 @@ class Engine:
     def _result(self, C_, detail, want_states, want_headings=False):
         M = self.n_samples
         res = _lib.PlanResult()
-        bufs = {"best_traj": np.zeros((M, 4), np.float32)}
-        res.best_traj = _ptr(bufs["best_traj"], _fp)
+        bufs = {"best_traj": np.empty((M, 4), np.float32)}
+        res.best_traj = bufs["best_traj"].ctypes.data
         if detail:
-            bufs["costs"] = np.zeros(C_, np.float32)
-            bufs["terms"] = np.zeros((C_, N_TERMS), np.float32)
-            bufs["flags"] = np.zeros(C_, np.uint8)
-            bufs["goals"] = np.zeros((C_, 3), np.float32)
-            bufs["params"] = np.zeros((C_, 4), np.float32)
-            res.costs = _ptr(bufs["costs"], _fp)
-            res.terms = _ptr(bufs["terms"], _fp)
-            res.flags = _ptr(bufs["flags"], _bp)
-            res.goals = _ptr(bufs["goals"], _fp)
-            res.params = _ptr(bufs["params"], _fp)
+            bufs["costs"] = np.empty(C_, np.float32)
+            bufs["terms"] = np.empty((C_, N_TERMS), np.float32)
+            bufs["flags"] = np.empty(C_, np.uint8)
+            bufs["goals"] = np.empty((C_, 3), np.float32)
+            bufs["params"] = np.empty((C_, 4), np.float32)
+            res.costs = bufs["costs"].ctypes.data
+            res.terms = bufs["terms"].ctypes.data
+            res.flags = bufs["flags"].ctypes.data
+            res.goals = bufs["goals"].ctypes.data
+            res.params = bufs["params"].ctypes.data
         if want_states:
             bufs["states"] = np.zeros((C_, M, 4), np.float32)
-            res.states = _ptr(bufs["states"], _fp)
+            res.states = bufs["states"].ctypes.data
         if want_headings:
             bufs["headings"] = np.zeros((C_, M, 2), np.float32)
-            res.headings = _ptr(bufs["headings"], _fp)
+            res.headings = bufs["headings"].ctypes.data
         return res, bufs
 
     @staticmethod
@@ -194,6 +192,10 @@ class Engine:
             raise ValueError("at most %d opponents" % MAX_OPP)
         return (o, o.shape[0]) if o.shape[0] else (None, 0)
 
+    @property
+    def n_samples(self):
+        return self._n_samples
+
     def plan(self, pose, opponent_poses=None, update_prev=True, detail=True, want_states=False,
              shard=None, want_headings=False):
         """One query.  pose = (x, y, theta, velocity).  shard = (c_begin, c_end) evaluates a
@@ -204,11 +206,11 @@ class Engine:
         opp, k = self._opp(opponent_poses)
         res, bufs = self._result(self.n_candidates, detail, want_states, want_headings)
         if shard is None:
-            code = self._L.f1l_plan(self._h, _ptr(pose, _dp), _ptr(opp, _dp), k,
+            code = self._L.f1l_plan(self._h, pose.ctypes.data, opp.ctypes.data if k else None, k,
                                     int(bool(update_prev)), C.byref(res))
         else:
-            code = self._L.f1l_plan_shard(self._h, _ptr(pose, _dp), _ptr(opp, _dp), k,
-                                          int(shard[0]), int(shard[1]), C.byref(res))
+            code = self._L.f1l_plan_shard(self._h, pose.ctypes.data, opp.ctypes.data if k else None,
+                                          k, int(shard[0]), int(shard[1]), C.byref(res))
         self._ck(code)
         return self._detail(res, bufs)
 
@@ -218,8 +220,9 @@ class Engine:
         g = _f64(goals).reshape(-1, 3)
         opp, k = self._opp(opponent_poses)
         res, bufs = self._result(g.shape[0], detail, want_states)
-        self._ck(self._L.f1l_plan_goals(self._h, _ptr(pose, _dp), _ptr(g, _dp), g.shape[0],
-                                        _ptr(opp, _dp), k, int(bool(update_prev)), C.byref(res)))
+        self._ck(self._L.f1l_plan_goals(self._h, pose.ctypes.data, g.ctypes.data, g.shape[0],
+                                        opp.ctypes.data if k else None, k, int(bool(update_prev)),
+                                        C.byref(res)))
         return self._detail(res, bufs)
 
     def generate(self, goals):
