@@ -1140,6 +1140,7 @@ int f1l_plan_batch(f1l_handle h, const double* poses, const double* opp, const i
     const int M = h->cfg.n_samples;
     // chunked 3-stream pipeline: H2D(i+1) | kernels(i) | D2H(i-1)
     int chunk = 8192;
+    if (const char* e = getenv("F1L_PIPE_CHUNK")) { const int v = atoi(e); if (v > 0) chunk = v; }
     if (S < chunk * N_PIPE) chunk = (S + N_PIPE - 1) / N_PIPE;
     if (chunk < 1) chunk = 1;
     int slot = 0;

@@ -77,7 +77,10 @@ __device__ __forceinline__ f32x2 track_seg_d2_pair(f32x2 px, f32x2 py, float4 A,
     return ffma2(e, e, fmul2(n, n));
 }
 
-__global__ void __launch_bounds__(PP_SCAN_THREADS)
+#ifndef PP_SCAN_MINB
+#define PP_SCAN_MINB 1
+#endif
+__global__ void __launch_bounds__(PP_SCAN_THREADS, PP_SCAN_MINB)
 pp_scan_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, int n_poses,
                int front_axle, double wb, int32_t* __restrict__ best_k) {
     __shared__ float s_d[PP_PARTS][PP_CTA_POSES];
@@ -114,8 +117,12 @@ pp_scan_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, 
         float m[PP_LANE_POSES];
 #pragma unroll
         for (int p = 0; p < PP_LANE_POSES; ++p) m[p] = CUDART_INF_F;
+#ifndef PP_UNROLL
+#define PP_UNROLL 2
+#endif
+        constexpr int kUnroll = PP_UNROLL;
         if (kn == 32) {
-#pragma unroll 2
+#pragma unroll kUnroll
             for (int j = 0; j < 32; j += 2) {   // two segments per trip, minima by FMNMX3
                 const float4 A0 = __ldg(tr.segA + k0 + j), A1 = __ldg(tr.segA + k0 + j + 1);
                 const float2 B0 = __ldg(tr.segB + k0 + j), B1 = __ldg(tr.segB + k0 + j + 1);
