@@ -284,11 +284,14 @@ generate_fn generate_entry(int M) {
 // resident CTAs per SM (72 registers, 28 warps), NW = 8 three (80 registers, 24 warps); besides
 // exact divisibility (no idle warp in the last round of a CTA) the choice minimises the number
 // of CTA waves, which is what decides the latency of one dense query.
+#ifndef EVAL_ITEM
+#define EVAL_ITEM 4
+#endif
 struct CtaPlan {
     int nw, chunk, ctas_per_scn;
 };
 
-CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count) {
+CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count, bool cubic) {
     CtaPlan best{8, 8, 1};
     double best_cost = 1e300;
     const int nws[3] = {4, 7, 8};
@@ -308,7 +311,10 @@ CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count) {
         const int cps = (n_cand + chunk - 1) / chunk;
         const double ctas = (double)S * cps;
         const double waves = std::ceil(ctas / resident);
-        const double rounds = std::ceil((double)chunk / nw);        // candidates per warp
+        // candidates a warp runs one after the other; with the cubic generator and at least four
+        // candidates per warp they are taken four at a time (shared Newton solve)
+        const int item = (cubic && chunk >= 4 * nw) ? EVAL_ITEM : 1;
+        const double rounds = std::ceil(std::ceil((double)chunk / item) / nw) * item;
         // time ~ waves x rounds, in units of one candidate per warp; slightly favour the
         // configuration with more resident warps on ties
         // the CTA holds its registers until its last warp finishes: about half a candidate of
@@ -334,6 +340,7 @@ size_t eval_smem_bytes(int nseg_pad, int warps, int M) {
     size_t b = (size_t)(nseg_pad + EVAL_SEG_PAD) * (2 * sizeof(float4));
     b += (size_t)warps * 2 * (((sh.s + 1) / 2) * sh.sg * 2) * sizeof(float);   // pair-layout slabs
     b += (size_t)warps * 2 * (sh.s * sh.sg) * sizeof(float4);                  // grid-probe lists
+    b += (size_t)warps * 8 * sizeof(float4);                                   // item solutions
     b += (size_t)((M + 3) & ~3) * sizeof(float);
     b += F1L_MAX_OPP * sizeof(float4);
     return b;
@@ -375,7 +382,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     if (nseg <= 0 || nseg > nsegs) nseg = nsegs;
     const int nseg_pad = (nseg + 31) & ~31;
     const int n_cand = c_end - c_begin;
-    const CtaPlan cp = plan_ctas(n_cand, S, M, h->sm_count);
+    const CtaPlan cp = plan_ctas(n_cand, S, M, h->sm_count, ep.generator == 0);
     const int wpc = cp.nw;
     const size_t smem = eval_smem_bytes(nseg_pad, wpc, M);
     if (smem > 226 * 1024) return F1L_ERR_TOO_LARGE;
@@ -439,6 +446,8 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     ea.c_end = c_end;
     ea.chunk = cp.chunk;
     ea.ctas_per_scn = cp.ctas_per_scn;
+    // four candidates per warp at a time (shared Newton) when every warp has at least four
+    ea.item = (ep.generator == 0 && cp.chunk >= 4 * cp.nw) ? EVAL_ITEM : 1;
     ea.inv_nW = 1.0f / (float)(h->nW > 0 ? h->nW : 1);
     ea.nseg_pad = nseg_pad;
     ea.costs = o.costs;

@@ -42,88 +42,100 @@ __device__ __forceinline__ float spiral_kappa(const SpiralF& s, float u) {
     return fmaf(u, fmaf(u, fmaf(u, s.b3, s.b2), s.b1), s.p0);
 }
 
-// all-reduce (sum) of 8 values per lane with 9 + 8 shuffles instead of 40: three halving steps
-// leave each lane with one partial column, two full steps finish it, then 8 broadcasts.
-__device__ __forceinline__ void warp_allreduce8(float (&v)[8], int lane) {
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+// all-reduce (sum) of 8 values per lane over each 8-lane group with 7 + 8 shuffles instead of 24:
+// three halving steps leave each lane with one column total, then 8 broadcasts in the group.
+__device__ __forceinline__ void group8_allreduce8(float (&v)[8], int lane) {
+    const bool h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
     float a[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float keep = h16 ? v[j + 4] : v[j];
-        const float send = h16 ? v[j] : v[j + 4];
-        a[j] = keep + __shfl_xor_sync(F1L_FULL, send, 16);
+        const float keep = h4 ? v[j + 4] : v[j];
+        const float send = h4 ? v[j] : v[j + 4];
+        a[j] = keep + __shfl_xor_sync(F1L_FULL, send, 4);
     }
     float b[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-        const float keep = h8 ? a[j + 2] : a[j];
-        const float send = h8 ? a[j] : a[j + 2];
-        b[j] = keep + __shfl_xor_sync(F1L_FULL, send, 8);
+        const float keep = h2 ? a[j + 2] : a[j];
+        const float send = h2 ? a[j] : a[j + 2];
+        b[j] = keep + __shfl_xor_sync(F1L_FULL, send, 2);
     }
-    float c;
-    {
-        const float keep = h4 ? b[1] : b[0];
-        const float send = h4 ? b[0] : b[1];
-        c = keep + __shfl_xor_sync(F1L_FULL, send, 4);
-    }
-    c += __shfl_xor_sync(F1L_FULL, c, 2);
-    c += __shfl_xor_sync(F1L_FULL, c, 1);
-    // lane l now holds the total of column ((l>>4)&1)*4 + ((l>>3)&1)*2 + ((l>>2)&1)
+    const float keep = h1 ? b[1] : b[0];
+    const float send = h1 ? b[0] : b[1];
+    const float c = keep + __shfl_xor_sync(F1L_FULL, send, 1);
+    // lane l of a group now holds the total of column l & 7
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int src = ((j & 4) ? 16 : 0) + ((j & 2) ? 8 : 0) + ((j & 1) ? 4 : 0);
-        v[j] = __shfl_sync(F1L_FULL, c, src);
-    }
+    for (int j = 0; j < 8; ++j) v[j] = __shfl_sync(F1L_FULL, c, j, 8);
 }
 
-// Up to `iters` Newton steps q <- q - J^-1 r, whole warp, lane = Simpson node (lane+1)/32 (node 0
-// is analytic: cos 0 = 1 and every other integrand vanishes there).  The loop leaves as soon as
-// the residual of the current iterate is at the FP32 noise floor, or right after a step taken
-// from a residual small enough that the step itself reaches it (warp-uniform: the whole warp
-// works on one candidate), so a LUT-seeded candidate typically spends 2-3 passes, not `iters`.
-// Returns the number of quadrature passes done.
-__device__ __forceinline__ int spiral_newton(SpiralF& sp, float gx, float gy, float gth,
-                                             int iters, int lane) {
-    const float u = (float)(lane + 1) * (1.0f / 32.0f);
-    const float w = (lane == 31) ? (1.0f / 96.0f) : (((lane + 1) & 1) ? (4.0f / 96.0f) : (2.0f / 96.0f));
-    const float u2 = u * u;
-    const float d1 = u2 * fmaf(u, fmaf(u, 3.375f, -7.5f), 4.5f);
-    const float d2 = u2 * fmaf(u, fmaf(u, -3.375f, 6.0f), -2.25f);
+// Up to `iters` Newton steps q <- q - J^-1 r on FOUR candidates per warp: each 8-lane group owns
+// one candidate (its lanes hold the same goal and iterate), each lane four consecutive Simpson
+// nodes (lane & 7) * 4 + m + 1 of 32 (node 0 is analytic: cos 0 = 1 and every other integrand
+// vanishes there).  A quadrature pass costs about the same instructions as one candidate on 32
+// lanes did, but serves four.  A group leaves when its residual reaches the FP32 noise floor, or
+// right after a step taken from a residual small enough that the step itself reaches it
+// (Newton is quadratic); the warp leaves when all groups have, so a LUT-seeded candidate
+// typically spends 2-3 passes, not `iters`.  Callers with one candidate give all groups the
+// same goal (same arithmetic, hence bit-identical parameters, as a batch).  `active` = this
+// group has a candidate.  Returns the number of quadrature passes this group used.
+__device__ __forceinline__ int spiral_newton_g8(SpiralF& sp, float gx, float gy, float gth,
+                                                int iters, int lane, bool active) {
+    const int l8 = lane & 7;
+    float u[4], w[4], d1[4], d2[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int j = l8 * 4 + m + 1;
+        u[m] = (float)j * (1.0f / 32.0f);
+        w[m] = (j == 32) ? (1.0f / 96.0f) : ((j & 1) ? (4.0f / 96.0f) : (2.0f / 96.0f));
+        const float u2 = u[m] * u[m];
+        d1[m] = u2 * fmaf(u[m], fmaf(u[m], 3.375f, -7.5f), 4.5f);
+        d2[m] = u2 * fmaf(u[m], fmaf(u[m], -3.375f, 6.0f), -2.25f);
+    }
     const float gmax = fmaxf(1.0f, fmaxf(fabsf(gx), fmaxf(fabsf(gy), fabsf(gth))));
     const float eps = 1.5e-6f * gmax;
-    // Newton converges quadratically: a step taken from a residual below eps_step lands below
-    // the noise floor, so its result is accepted without another quadrature pass to confirm it
     const float eps_step = 2e-4f * gmax;
+    bool done = !active;
     int it = 0;
-    for (; it < iters; ++it) {
+    for (int pass = 0; pass < iters; ++pass) {
+        if (__all_sync(F1L_FULL, done)) break;
         spiral_set(sp);
-        const float g = spiral_g(sp, u);
-        float s, c;
-        __sincosf(sp.sf * g, &s, &c);
-        const float wc = w * c, ws = w * s;
-        float v[8] = {wc, ws, wc * g, ws * g, wc * d1, ws * d1, wc * d2, ws * d2};
-        warp_allreduce8(v, lane);
+        float v[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const float g = spiral_g(sp, u[m]);
+            float s, c;
+            __sincosf(sp.sf * g, &s, &c);
+            const float wc = w[m] * c, ws = w[m] * s;
+            v[0] += wc; v[1] += ws;
+            v[2] = fmaf(wc, g, v[2]); v[3] = fmaf(ws, g, v[3]);
+            v[4] = fmaf(wc, d1[m], v[4]); v[5] = fmaf(ws, d1[m], v[5]);
+            v[6] = fmaf(wc, d2[m], v[6]); v[7] = fmaf(ws, d2[m], v[7]);
+        }
+        group8_allreduce8(v, lane);
         const float C0 = v[0] + (1.0f / 96.0f), S0 = v[1], Cg = v[2], Sg = v[3];
         const float C1 = v[4], S1 = v[5], C2 = v[6], S2 = v[7];
         const float sf = sp.sf, sf2 = sf * sf;
         const float g1 = 0.125f * (sp.p0 + 3.0f * sp.p1 + 3.0f * sp.p2 + sp.p3);
         const float r0 = fmaf(sf, C0, -gx), r1 = fmaf(sf, S0, -gy), r2 = fmaf(sf, g1, -gth);
         const float rmax = fmaxf(fabsf(r0), fmaxf(fabsf(r1), fabsf(r2)));
-        if (rmax < eps) { ++it; break; }
-        const float J00 = -sf2 * S1, J01 = -sf2 * S2, J02 = fmaf(-sf, Sg, C0);
-        const float J10 = sf2 * C1, J11 = sf2 * C2, J12 = fmaf(sf, Cg, S0);
-        const float J20 = 0.375f * sf, J21 = J20, J22 = g1;
-        const float m0 = J11 * J22 - J12 * J21, m1 = J10 * J22 - J12 * J20, m2 = J10 * J21 - J11 * J20;
-        const float det = J00 * m0 - J01 * m1 + J02 * m2;
-        const float inv = __fdividef(1.0f, det);
-        const float n0 = r1 * J22 - J12 * r2, n1 = r1 * J21 - J11 * r2, n2 = J10 * r2 - r1 * J20;
-        const float dq0 = (r0 * m0 - J01 * n0 + J02 * n1) * inv;
-        const float dq1 = (J00 * n0 - r0 * m1 + J02 * n2) * inv;
-        const float dq2 = (-J00 * n1 - J01 * n2 + r0 * m2) * inv;
-        sp.p1 -= dq0;
-        sp.p2 -= dq1;
-        sp.sf -= dq2;
-        if (rmax < eps_step) { ++it; break; }
+        if (!done) {
+            ++it;
+            if (rmax < eps) {
+                done = true;
+            } else {
+                const float J00 = -sf2 * S1, J01 = -sf2 * S2, J02 = fmaf(-sf, Sg, C0);
+                const float J10 = sf2 * C1, J11 = sf2 * C2, J12 = fmaf(sf, Cg, S0);
+                const float J20 = 0.375f * sf, J21 = J20, J22 = g1;
+                const float m0 = J11 * J22 - J12 * J21, m1 = J10 * J22 - J12 * J20, m2 = J10 * J21 - J11 * J20;
+                const float det = J00 * m0 - J01 * m1 + J02 * m2;
+                const float inv = __fdividef(1.0f, det);
+                const float n0 = r1 * J22 - J12 * r2, n1 = r1 * J21 - J11 * r2, n2 = J10 * r2 - r1 * J20;
+                sp.p1 -= (r0 * m0 - J01 * n0 + J02 * n1) * inv;
+                sp.p2 -= (J00 * n0 - r0 * m1 + J02 * n2) * inv;
+                sp.sf -= (-J00 * n1 - J01 * n2 + r0 * m2) * inv;
+                if (rmax < eps_step) done = true;
+            }
+        }
     }
     spiral_set(sp);
     return it;
@@ -140,34 +152,36 @@ __device__ __forceinline__ float4 lut_lookup(const LutView& lut, float gx, float
     return __ldg(lut.cells + ((size_t)ix * lut.ny + iy) * lut.nt + it);
 }
 
-// Trilinear LUT seed, whole warp: lane & 7 owns one corner of the goal's cell, three xor steps sum
-// the weighted corners on every lane.  The converged cells are samples of one smooth solution
-// family, so the interpolated seed lies in the same Newton basin as the nearest cell (the
-// oracle's seed) but an order closer to the root: one quadrature pass fewer.  Goals outside the
-// table or next to a non-converged cell fall back to the nearest cell.
+// Trilinear LUT seed per 8-lane group: lane & 7 owns one corner of the goal's cell, three xor
+// steps sum the weighted corners on every lane of the group.  The converged cells are samples of
+// one smooth solution family, so the interpolated seed lies in the same Newton basin as the nearest
+// cell (the oracle's seed) but an order closer to the root: one quadrature pass fewer.  Goals
+// outside the table or next to a non-converged cell take the nearest cell.  Branch-free: the four
+// groups of a warp may hold different goals.
 __device__ __forceinline__ float4 lut_seed(const LutView& lut, float gx, float gy, float gth,
                                            int lane) {
     const float fx = (gx - lut.x0) * lut.sx, fy = (gy - lut.y0) * lut.sy, ft = (gth - lut.t0) * lut.st;
     const bool inside = lut.nx > 1 && lut.ny > 1 && lut.nt > 1 && fx >= 0.0f && fy >= 0.0f &&
                         ft >= 0.0f && fx <= (float)(lut.nx - 1) && fy <= (float)(lut.ny - 1) &&
                         ft <= (float)(lut.nt - 1);
-    if (inside) {   // warp-uniform: the warp works on one goal
-        const int ix = min(__float2int_rd(fx), lut.nx - 2), iy = min(__float2int_rd(fy), lut.ny - 2);
-        const int it = min(__float2int_rd(ft), lut.nt - 2);
-        const float wx = fx - (float)ix, wy = fy - (float)iy, wt = ft - (float)it;
-        const int cx = lane & 1, cy = (lane >> 1) & 1, ct = (lane >> 2) & 1;
-        const float4 cell = __ldg(lut.cells + ((size_t)(ix + cx) * lut.ny + (iy + cy)) * lut.nt + (it + ct));
-        const float w = (cx ? wx : 1.0f - wx) * (cy ? wy : 1.0f - wy) * (ct ? wt : 1.0f - wt);
-        float a = w * cell.x, b = w * cell.y, c = w * cell.z;
+    const int ix = max(min(__float2int_rd(fx), lut.nx - 2), 0), iy = max(min(__float2int_rd(fy), lut.ny - 2), 0);
+    const int it = max(min(__float2int_rd(ft), lut.nt - 2), 0);
+    const float wx = fx - (float)ix, wy = fy - (float)iy, wt = ft - (float)it;
+    const int cx = lane & 1, cy = (lane >> 1) & 1, ct = (lane >> 2) & 1;
+    const int jx = min(ix + cx, lut.nx - 1), jy = min(iy + cy, lut.ny - 1), jt = min(it + ct, lut.nt - 1);
+    const float4 cell = __ldg(lut.cells + ((size_t)jx * lut.ny + jy) * lut.nt + jt);
+    const float w = (cx ? wx : 1.0f - wx) * (cy ? wy : 1.0f - wy) * (ct ? wt : 1.0f - wt);
+    float a = w * cell.x, b = w * cell.y, c = w * cell.z;
 #pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-            a += __shfl_xor_sync(F1L_FULL, a, o);
-            b += __shfl_xor_sync(F1L_FULL, b, o);
-            c += __shfl_xor_sync(F1L_FULL, c, o);
-        }
-        if (__all_sync(F1L_FULL, cell.w != 0.0f)) return make_float4(a, b, c, 1.0f);
+    for (int o = 1; o < 8; o <<= 1) {
+        a += __shfl_xor_sync(F1L_FULL, a, o);
+        b += __shfl_xor_sync(F1L_FULL, b, o);
+        c += __shfl_xor_sync(F1L_FULL, c, o);
     }
-    return lut_lookup(lut, gx, gy, gth);
+    const unsigned conv = __ballot_sync(F1L_FULL, cell.w != 0.0f);
+    const bool ok = inside && ((conv >> (lane & 24)) & 0xffu) == 0xffu;
+    const float4 nearest = lut_lookup(lut, gx, gy, gth);
+    return ok ? make_float4(a, b, c, 1.0f) : nearest;
 }
 
 // G1 Hermite clothoid from (0,0,0) to the goal -- the generator the reference calls
@@ -226,15 +240,24 @@ __device__ __forceinline__ int clothoid_g1(SpiralF& sp, float gx, float gy, floa
     return it;
 }
 
-// generator dispatch (warp-uniform): fills `sp` for the goal, returns the quadrature passes
-__device__ __forceinline__ int generate_spiral(SpiralF& sp, const LutView& lut, const EvalParams& ep,
-                                               float gx, float gy, float gth, float p3, int lane) {
-    if (ep.generator == 1) return clothoid_g1(sp, gx, gy, gth, ep.n_newton, lane);
+// Cubic-spiral generator for the candidate of this lane's 8-lane group (`active`: the group has
+// one): LUT seed + Newton.  Returns the quadrature passes the group used.
+__device__ __forceinline__ int generate_cubic_g8(SpiralF& sp, const LutView& lut, const EvalParams& ep,
+                                                 float gx, float gy, float gth, float p3, int lane,
+                                                 bool active) {
     sp.p0 = 0.0f;
     sp.p3 = p3;
     const float4 seed = lut_seed(lut, gx, gy, gth, lane);
     sp.p1 = seed.x; sp.p2 = seed.y; sp.sf = seed.z;
-    return spiral_newton(sp, gx, gy, gth, ep.n_newton, lane);
+    return spiral_newton_g8(sp, gx, gy, gth, ep.n_newton, lane, active);
+}
+
+// generator dispatch for ONE candidate on the whole warp (warp-uniform arguments): fills `sp` for
+// the goal, returns the quadrature passes
+__device__ __forceinline__ int generate_spiral(SpiralF& sp, const LutView& lut, const EvalParams& ep,
+                                               float gx, float gy, float gth, float p3, int lane) {
+    if (ep.generator == 1) return clothoid_g1(sp, gx, gy, gth, ep.n_newton, lane);
+    return generate_cubic_g8(sp, lut, ep, gx, gy, gth, p3, lane, true);
 }
 
 // M arc samples, lane l owns samples [l*IPL, (l+1)*IPL).  Per-interval Simpson
@@ -319,6 +342,8 @@ struct EvalArgs {
     int c_begin, c_end;      // evaluated range
     int ctas_per_scn;        // CTAs per scenario
     int chunk;               // candidates per CTA
+    int item;                // candidates a warp takes at a time: 4 (their Newton solves share the
+                             // warp, cubic generator, >= 4 candidates per warp) or 1
     float inv_nW;            // 1 / nW (row = floor((c + 0.5) / nW) without an integer division)
     int nseg_pad;            // shared-memory window capacity (multiple of 32)
     // outputs (nullable)
@@ -753,6 +778,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
     // in grid-cell coordinates, two float4 per entry
     constexpr int PCAP = S * SG;
     float4* plist_all = reinterpret_cast<float4*>(slab_all + (size_t)NW * 2 * SLAB);   // [NW][PCAP][2]
+    // per-warp solutions of the four candidates of an item: (gx, gy, gth, p3), (p1, p2, sf, have | passes)
+    float4* item_all = plist_all + (size_t)NW * 2 * PCAP;                              // [NW][4][2]
 
     int s, cta;
     if (a.ctas_per_scn == 1) { s = blockIdx.x; cta = 0; }
@@ -804,7 +831,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             for (int i = tid; i < M; i += NW * 32) sprev[i] = a.prev_theta[i];
         }
         if (tid < F1L_MAX_OPP) sopp[tid] = q->opp[tid];
-        if (tid == 0) { s_next = cb + NW; s_work = 0ull; }
+        if (tid == 0) { s_next = cb + NW * a.item; s_work = 0ull; }
         // per-scenario collision constants live in shared memory, not in registers, so that the
         // candidate loop does not carry them through the deviation pass
         if (tid == 32 % (NW * 32)) {
@@ -824,14 +851,52 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
         slab_y[((r >> 1) * SG + g) * 2 + (r & 1)] = 0.0f;
     }
 
-    for (int c = cb + wid; c < ce;) {
+    // A warp takes `item` consecutive candidates at a time.  With item = 4 their goals, LUT seeds
+    // and Newton solves run together, one candidate per 8-lane group (spiral_newton_g8); the rest
+    // of the pipeline then handles the four one after the other on the whole warp.
+    const int item = a.item;
+    for (int c0 = cb + wid * item; c0 < ce;) {
+      float4* isol = item_all + (size_t)wid * 8;
+      if (item == 4) {   // warp-uniform
+          const int cg = c0 + (lane >> 3);
+          const bool active = cg < ce;
+          float ggx, ggy, ggth, gp3, gv_ref;
+          bool ghave;
+          candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.inv_nW, a.C, s, active ? cg : c0,
+                         a.ep.use_goal_kappa != 0, ggx, ggy, ggth, gp3, ghave, gv_ref);
+          SpiralF gsp;
+          const int g_pass = generate_cubic_g8(gsp, a.lut, a.ep, ggx, ggy, ggth, gp3, lane, active);
+          // through shared memory, not registers: nothing of this lives across the deviation pass
+          if ((lane & 7) == 0) {
+              isol[2 * (lane >> 3)] = make_float4(ggx, ggy, ggth, gp3);
+              isol[2 * (lane >> 3) + 1] = make_float4(gsp.p1, gsp.p2, gsp.sf,
+                                                      __int_as_float((ghave ? 256 : 0) | g_pass));
+          }
+          __syncwarp();
+      }
+      const int c_last = min(c0 + item, ce);
+      for (int c = c0; c < c_last; ++c) {
         // ---- goal, seed, Newton ----
         float gx, gy, gth, p3, v_ref;
         bool have_centre;
-        candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.inv_nW, a.C, s, c,
-                       a.ep.use_goal_kappa != 0, gx, gy, gth, p3, have_centre, v_ref);
         SpiralF sp;
-        const int n_pass = generate_spiral(sp, a.lut, a.ep, gx, gy, gth, p3, lane);
+        int n_pass;
+        if (item == 4) {   // the solution of candidate c, found by its 8-lane group
+            const float4 G = isol[2 * (c - c0)], Q = isol[2 * (c - c0) + 1];
+            gx = G.x; gy = G.y; gth = G.z; p3 = G.w;
+            v_ref = 0.0f;
+            const int hp = __float_as_int(Q.w);
+            have_centre = (hp & 256) != 0;
+            n_pass = hp & 255;
+            sp.p0 = 0.0f;
+            sp.p3 = p3;
+            sp.p1 = Q.x; sp.p2 = Q.y; sp.sf = Q.z;
+            spiral_set(sp);
+        } else {
+            candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.inv_nW, a.C, s, c,
+                           a.ep.use_goal_kappa != 0, gx, gy, gth, p3, have_centre, v_ref);
+            n_pass = generate_spiral(sp, a.lut, a.ep, gx, gy, gth, p3, lane);
+        }
 
         // ---- arc samples ----
         float x[IPL], y[IPL], th[IPL], kp[IPL], cs[IPL], sn[IPL];
@@ -1142,7 +1207,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             }
         }
 
-        int c_next = 0;
         if (lane == 0) {
             if (a.costs) a.costs[cand] = cost;
             if (a.flags) a.flags[cand] = (uint8_t)flags;
@@ -1154,9 +1218,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             const unsigned long long key =
                 ((unsigned long long)float_orderable(cost) << 32) | (unsigned)c;
             atomicMin(a.best + s, key);
-            c_next = atomicAdd(&s_next, 1);
         }
-        c = __shfl_sync(F1L_FULL, c_next, 0);
+      }
+      __syncwarp();   // all lanes have read the item's solutions
+      int c_next = 0;
+      if (lane == 0) c_next = atomicAdd(&s_next, item);
+      c0 = __shfl_sync(F1L_FULL, c_next, 0);
     }
     if (a.stats) {   // one pair of global atomics per CTA
         __syncthreads();
