@@ -283,6 +283,66 @@ __device__ inline Intersect64 intersect_point_warp(const P& pts, int n, double q
     return o;
 }
 
+// The same for one query per G-lane group (G = 8: four queries per warp) that share the point and
+// the start parameter and differ in the radius -- the lookahead rows of the goal grid, whose hits
+// lie a few segments ahead, so G consecutive segments per step are plenty.  Every group steps
+// through the same segment sequence; a group that has its hit keeps it and idles.  `active`: the
+// group has a query.  Only the first `max_steps` x G segments of the forward scan are visited:
+// `pending` returns whether this group's query is still open (the caller finishes it with
+// intersect_point_warp; a circle that misses the raceline scans the whole track, which 32 lanes
+// do four times faster than 8).  Call with the whole warp converged; the lanes of a group return
+// its result.
+template <int G, class P, class F>
+__device__ inline Intersect64 intersect_point_group(const P& pts, int n, double qx, double qy,
+                                                    double r, double t, bool wrap, int lane,
+                                                    const F& maybe, bool active, int max_steps,
+                                                    bool& pending) {
+    Intersect64 o;
+    o.px = 0.0; o.py = 0.0; o.t = 0.0; o.i = 0; o.found = 0;
+    const int gl = lane & (G - 1), gbase = lane & ~(G - 1);
+    const unsigned gmask = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
+    const int start_i = (int)t;                 // :78
+    const double start_t = t - (double)start_i;  // == t % 1.0 for t >= 0, exactly        // :79
+    bool done = !active;
+    pending = false;
+    int steps = 0;
+    for (int phase = 0; phase < (wrap ? 2 : 1); ++phase) {
+        const int lo = phase == 0 ? start_i : -1;          // :84 / :125
+        const int hi = phase == 0 ? n - 1 : start_i;       // exclusive
+        for (int base = lo; base < hi; base += G) {
+            if (__all_sync(F1L_FULL, done)) return o;
+            if (steps++ >= max_steps) { pending = !done; return o; }
+            const int i = base + gl;
+            double tt = -1.0, vx = 0.0, vy = 0.0;
+            double2 s = make_double2(0.0, 0.0);
+            if (!done && i < hi && maybe(i)) {
+                double t1, t2;
+                s = pts(pymod(i, n));
+                if (intersect_segment64(qx, qy, r, s, pts(pymod(i + 1, n)), t1, t2, vx, vy)) {
+                    if (phase == 0 && i == start_i) {       // :102-112
+                        if (t1 >= 0.0 && t1 <= 1.0 && t1 >= start_t) tt = t1;
+                        else if (t2 >= 0.0 && t2 <= 1.0 && t2 >= start_t) tt = t2;
+                    } else if (t1 >= 0.0 && t1 <= 1.0) tt = t1;   // :113 / :140
+                    else if (t2 >= 0.0 && t2 <= 1.0) tt = t2;     // :118 / :145
+                }
+            }
+            const unsigned m = (__ballot_sync(F1L_FULL, tt >= 0.0) >> gbase) & gmask;
+            const int src = gbase + (m ? __ffs(m) - 1 : 0);
+            const double px = xadd(s.x, xmul(tt, vx)), py = xadd(s.y, xmul(tt, vy));
+            const double ht = __shfl_sync(F1L_FULL, tt, src);
+            const double hx = __shfl_sync(F1L_FULL, px, src);
+            const double hy = __shfl_sync(F1L_FULL, py, src);
+            if (!done && m) {
+                o.found = 1;
+                o.i = base + (src - gbase);
+                o.t = ht; o.px = hx; o.py = hy;
+                done = true;
+            }
+        }
+    }
+    return o;
+}
+
 // prefilter on the uploaded track: FP32 distance of the query point to segment i (block-local
 // line form) against radius + 1 mm.  A root of the reference's quadratic in [0,1] is a point of
 // the (1e-6-shifted) segment at distance r from the query, so a segment farther than that cannot

@@ -434,16 +434,31 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
     double cth, sth;
     sincos(pth, &sth, &cth);
 
-    // one intersect_point per lookahead row (lattice_planner.py:249-251); a warp per row
+    // one intersect_point per lookahead row (lattice_planner.py:249-251); an 8-lane group per row,
+    // four rows per warp at a time
     XYTrack acc{a.tr.xy};
     const int lane = lt & 31;
-    for (int j = lt >> 5; j < a.nL; j += nt >> 5) {
-        const double L = a.lookaheads[j];
+    for (int j0 = (lt >> 5) * 4; j0 < a.nL; j0 += (nt >> 5) * 4) {
+        const int j = j0 + (lane >> 3);
+        const bool active = j < a.nL;
+        const double L = a.lookaheads[active ? j : j0];
         const float rr = (float)L + 1e-3f;
         const TrackPrefilter pf{a.tr, px, py, rr * rr};
-        const Intersect64 ip =
-            intersect_point_warp(acc, a.tr.n, px, py, L, (double)i_ego + t_ego, true, lane, pf);
-        if (lane == 0) {
+        bool pending;
+        Intersect64 ip = intersect_point_group<8>(acc, a.tr.n, px, py, L, (double)i_ego + t_ego,
+                                                  true, lane, pf, active, 4, pending);
+        // rows whose hit is not within the first 32 segments (mostly: no hit at all): the full
+        // 32-lane scan, one row after the other
+        for (unsigned open = __ballot_sync(F1L_FULL, pending) & 0x01010101u; open; open &= open - 1) {
+            const int src = __ffs(open) - 1;
+            const double Ls = __shfl_sync(F1L_FULL, L, src);
+            const float rs = (float)Ls + 1e-3f;
+            const TrackPrefilter pfs{a.tr, px, py, rs * rs};
+            const Intersect64 full =
+                intersect_point_warp(acc, a.tr.n, px, py, Ls, (double)i_ego + t_ego, true, lane, pfs);
+            if ((lane & ~7) == src) ip = full;
+        }
+        if (active && (lane & 7) == 0) {
             Centre ce;
             const int r = ip.found ? pymod(ip.i, a.tr.n) : 0;
             const double2 c = a.tr.xy[r];
@@ -1278,18 +1293,30 @@ __global__ void __launch_bounds__(32) select_kernel(SelectArgs a) {
     XYTraj4 acc{s_traj};
     double bd = CUDART_INF;
     int bi = 0x7fffffff;
-    for (int k = lane; k < M - 1; k += 32) {
-        const double2 p0 = acc(k), p1 = acc(k + 1);
+    {
+        // The vehicle-frame tracker queries the trajectory's own first point: segment 0 at
+        // distance exactly 0 is the first minimum whatever the other segments give, so the scan
+        // is skipped (any other outcome of segment 0 -- the literal mode, a degenerate
+        // trajectory -- takes the full scan).
+        const double2 p0 = acc(0), p1 = acc(1);
         double ux, uy, d, t;
         nearest_segment64(qx, qy, p0.x, p0.y, p1.x, p1.y, ux, uy, d, t);
-        // NaN distances (degenerate trajectory) never win; the reference would return them
-        if (nearest_better(d, k, bd, bi)) { bd = d; bi = k; }
+        if (d == 0.0) { bd = 0.0; bi = 0; }   // warp-uniform
     }
+    if (bi != 0) {
+        for (int k = lane; k < M - 1; k += 32) {
+            const double2 p0 = acc(k), p1 = acc(k + 1);
+            double ux, uy, d, t;
+            nearest_segment64(qx, qy, p0.x, p0.y, p1.x, p1.y, ux, uy, d, t);
+            // NaN distances (degenerate trajectory) never win; the reference would return them
+            if (nearest_better(d, k, bd, bi)) { bd = d; bi = k; }
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double od = __shfl_xor_sync(F1L_FULL, bd, o);
-        const int oi = __shfl_xor_sync(F1L_FULL, bi, o);
-        if (nearest_better(od, oi, bd, bi)) { bd = od; bi = oi; }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(F1L_FULL, bd, o);
+            const int oi = __shfl_xor_sync(F1L_FULL, bi, o);
+            if (nearest_better(od, oi, bd, bi)) { bd = od; bi = oi; }
+        }
     }
     int found = 0;
     double steer = 0.0, speed = 0.0;
