@@ -341,7 +341,7 @@ size_t eval_smem_bytes(int nseg_pad, int warps, int M) {
     b += (size_t)warps * 2 * (((sh.s + 1) / 2) * sh.sg * 2) * sizeof(float);   // pair-layout slabs
     b += (size_t)warps * 2 * (sh.s * sh.sg) * sizeof(float4);                  // grid-probe lists
     b += (size_t)warps * 8 * sizeof(float4);                                   // item solutions
-    b += (size_t)((M + 3) & ~3) * sizeof(float);
+    b += (size_t)F1L_MAX_M * sizeof(float);                                    // previous path
     b += F1L_MAX_OPP * sizeof(float4);
     return b;
 }

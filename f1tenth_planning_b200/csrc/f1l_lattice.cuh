@@ -780,21 +780,24 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
     __shared__ int s_gi[4];
     const int M = a.ep.M;
     const int ntab = a.nseg_pad + EVAL_SEG_PAD;
-    // window table, two float4 per segment: T0 = (ux, uy, -uy, 1/len), T1 = (-a.u, -a.n, -len, 0)
-    float4* sT = reinterpret_cast<float4*>(ev_smem);
-    float4* sopp = sT + 2 * (size_t)ntab;                                    // [F1L_MAX_OPP]
-    float* sprev = reinterpret_cast<float*>(sopp + F1L_MAX_OPP);             // [M] (padded to 4)
+    // Dynamic shared memory.  Everything of compile-time size comes first, at constant offsets --
+    // with the window table (run-time size) in front, the addresses of all the per-warp areas
+    // were re-derived inside the candidate loop: 8 % of the kernel's instructions.
+    // per-warp list of the footprints that need their nine grid probes: centre and half-axes
+    // in grid-cell coordinates, two float4 per entry
+    constexpr int PCAP = S * SG;
+    float4* plist_all = reinterpret_cast<float4*>(ev_smem);                             // [NW][PCAP][2]
+    // per-warp solutions of the four candidates of an item: (gx, gy, gth, p3), (p1, p2, sf, have | passes)
+    float4* item_all = plist_all + NW * 2 * PCAP;                                       // [NW][4][2]
+    float4* sopp = item_all + NW * 8;                                                   // [F1L_MAX_OPP]
     // per-warp sample slab in the pair layout of the deviation pass: element (j, sg, half) holds
     // sample (2j + half) * SG + sg, so that one 64-bit load yields a packed pair of samples
     constexpr int SROWS = (S + 1) / 2;
     constexpr int SLAB = SROWS * SG * 2;                                     // floats per coordinate
-    float* slab_all = sprev + ((M + 3) & ~3);                                // [NW][2][SLAB]
-    // per-warp list of the footprints that need their nine grid probes: centre and half-axes
-    // in grid-cell coordinates, two float4 per entry
-    constexpr int PCAP = S * SG;
-    float4* plist_all = reinterpret_cast<float4*>(slab_all + (size_t)NW * 2 * SLAB);   // [NW][PCAP][2]
-    // per-warp solutions of the four candidates of an item: (gx, gy, gth, p3), (p1, p2, sf, have | passes)
-    float4* item_all = plist_all + (size_t)NW * 2 * PCAP;                              // [NW][4][2]
+    float* slab_all = reinterpret_cast<float*>(sopp + F1L_MAX_OPP);          // [NW][2][SLAB]
+    float* sprev = slab_all + NW * 2 * SLAB;                                 // [F1L_MAX_M]
+    // window table, two float4 per segment: T0 = (ux, uy, -uy, 1/len), T1 = (-(a.u + h), -a.n, -h, 0)
+    float4* sT = reinterpret_cast<float4*>(sprev + F1L_MAX_M);               // [2 * ntab]
 
     int s, cta;
     if (a.ctas_per_scn == 1) { s = blockIdx.x; cta = 0; }

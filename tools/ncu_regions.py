@@ -28,7 +28,8 @@ def find(pat, start=0):
 
 k0 = find("eval_kernel(EvalArgs a)")
 marks = [("prologue (window table)", k0),
-         ("goal + LUT seed + Newton", find("// ---- goal, seed, Newton", k0)),
+         ("goals + LUT seeds + Newton, four candidates per warp", find("// A warp takes `item` consecutive", k0)),
+         ("solution hand-over (or single-candidate Newton)", find("// ---- goal, seed, Newton", k0)),
          ("arc samples", find("// ---- arc samples", k0)),
          ("curvature / validity / slab", find("// ---- curvature terms", k0)),
          ("similarity + collision", find("// ---- similarity", k0)),
