@@ -464,6 +464,7 @@ def run_ours(args):
     w_eff = seg_steps / seg_cands if seg_cands else float(PLAN_CFG["window"])
     step_flops, valid_frac, mean_passes = work_flops(flags, M, w_eff, float(n_opp.mean()))
     achieved_tflops = step_flops / (k_eval * 1e-3) / 1e12 if k_eval > 0 else None
+    mufu_ops = float((flags >> 4).astype(np.float64).sum()) * (2 * F.Q_NEWTON + 1) + flags.size * 5.0 * M
 
     # ---- side measurement: the same step with prune_window = 1 (bit-identical costs) ------------
     pruned = None
@@ -558,6 +559,11 @@ def run_ours(args):
             "kernel": "eval_kernel<4,13,8,4,7>", "kernel_ms": k_eval, "kernel_launches_timed": n_timed,
             "kernel_share_of_step": k_eval / (ms_total / args.steps) if k_eval else None,
             "flops_per_launch": step_flops,
+            # the secondary roofline SURVEY 8d names: MUFU (sin / cos / sqrt) operations of the
+            # step -- (2 Q + 1) per Newton pass and 5 per arc sample -- against the measured pipe peak
+            "mufu": {"achieved_gops": mufu_ops / (k_eval * 1e-3) / 1e9 if k_eval > 0 else None,
+                     "peak_gops": mufu_peak,
+                     "frac": mufu_ops / (k_eval * 1e-3) / 1e9 / mufu_peak if (k_eval > 0 and mufu_peak) else None},
             "mufu_peak_gops": mufu_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one eval_kernel launch of this workload
             # (ncu --set full; profiles/r1_eval_kernel.md) -- bench.py cannot run under ncu itself
