@@ -451,6 +451,7 @@ def run_ours(args):
     clocks = sampler.stop()
     ms_total = e0.elapsed_time(e1)
     k_sample, k_eval, k_select, n_timed = eng.mean_kernel_ms()
+    eval_shape = eng.last_eval_shape()   # the template instance the timed steps launched
     eng.set_timing(False)
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world_size > 1:
@@ -556,7 +557,7 @@ def run_ours(args):
             "frac": achieved_tflops / fp32_peak if achieved_tflops else None,
             "peak_source": "FFMA microbenchmark measured in this run (f1l_measure_peaks); "
                            "MEASURED_PEAKS.json has no FP32 entry; nominal 74.4",
-            "kernel": "eval_kernel<4,13,8,4,7>", "kernel_ms": k_eval, "kernel_launches_timed": n_timed,
+            "kernel": eval_shape["name"], "kernel_plan": eval_shape, "kernel_ms": k_eval, "kernel_launches_timed": n_timed,
             "kernel_share_of_step": k_eval / (ms_total / args.steps) if k_eval else None,
             "flops_per_launch": step_flops,
             # the secondary roofline SURVEY 8d names: MUFU (sin / cos / sqrt) operations of the

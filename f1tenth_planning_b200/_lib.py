@@ -86,6 +86,7 @@ SIGNATURES = {
                                             _ip]),
     "f1l_get_actuation_batch": (C.c_int, [_vp, _dp, C.c_int, C.c_double, _dp]),
     "f1l_get_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
+    "f1l_last_eval_shape": (C.c_int, [_vp, _ip, C.c_int]),
     "f1l_launch_count": (C.c_int64, [_vp]),
     "f1l_set_graph": (C.c_int, [_vp, C.c_int]),
     "f1l_set_timing": (C.c_int, [_vp, C.c_int]),
@@ -94,6 +95,8 @@ SIGNATURES = {
     "f1l_measure_peaks": (C.c_int, [_vp, _dp, _dp]),
     "f1l_measure_peaks_ex": (C.c_int, [_vp, _dp, C.c_int]),
     "f1l_debug_query_ctx": (C.c_int, [_vp, _fp, _ip]),
+    "f1l_debug_eval_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, C.c_int]),
+    "f1l_debug_pp_parts": (C.c_int, [C.c_int, C.c_int, C.c_int]),
 }
 
 _lib = None

@@ -84,7 +84,9 @@ struct f1l_ctx {
     // batch pipeline (host-pointer API)
     PipeSlot pipe[N_PIPE];
     // misc scratch for the pure-pursuit / intersect host APIs
-    DevBuf m_in, m_in2, m_o0, m_o1, m_o2, m_o3, m_o4, m_o5, pp_bk;
+    DevBuf m_in, m_in2, m_o0, m_o1, m_o2, m_o3, m_o4, m_o5, pp_key;
+    // template instance / CTA plan of the last eval_kernel launch (f1l_last_eval_shape)
+    int eval_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -325,14 +327,24 @@ CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count, bool cubic) {
     return best;
 }
 
-// K1 = scan + finish on one stream.  best_k: int32 scratch per pose (may alias o.nearest_i)
+// K1 = key preset + scan + finish on one stream.  key: 8 bytes of scratch per pose
 void launch_pp(const TrackView& tv, cudaStream_t stream, const double* poses, int pose_stride,
                int n_poses, double L, double wb, double max_reacquire, int front_axle, double k_path,
-               int32_t* best_k, const PPOut& o) {
-    pp_scan_kernel<<<(n_poses + PP_CTA_POSES - 1) / PP_CTA_POSES, PP_SCAN_THREADS, 0, stream>>>(
-        tv, poses, pose_stride, n_poses, front_axle, wb, best_k);
+               unsigned long long* key, int sm_count, const PPOut& o) {
+    static int per_sm = 0;   // resident one-warp scan CTAs per SM, from the occupancy calculator
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pp_scan_kernel, 32, 0) !=
+                cudaSuccess || per_sm <= 0)
+            per_sm = PP_TASK_MINB;
+    }
+    const int n_groups = (n_poses + PP_CTA_POSES - 1) / PP_CTA_POSES;
+    const int nblk = (tv.n - 1 + 31) >> 5;
+    const int n_parts = pp_task_parts(n_groups, nblk, per_sm * sm_count);
+    cudaMemsetAsync(key, 0xff, (size_t)n_poses * 8, stream);
+    pp_scan_kernel<<<n_groups * n_parts, 32, 0, stream>>>(tv, poses, pose_stride, n_poses,
+                                                         front_axle, wb, n_parts, key);
     pp_finish_kernel<<<(n_poses + PP_THREADS - 1) / PP_THREADS, PP_THREADS, 0, stream>>>(
-        tv, poses, pose_stride, n_poses, L, wb, max_reacquire, front_axle, k_path, best_k, o);
+        tv, poses, pose_stride, n_poses, L, wb, max_reacquire, front_axle, k_path, key, o);
 }
 
 size_t eval_smem_bytes(int nseg_pad, int warps, int M) {
@@ -413,7 +425,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
         po.actuation = nullptr;
         po.status = nullptr;
         po.front = nullptr;
-        launch_pp(sa.tr, stream, poses, 4, S, -1.0, 0.33, 0.0, 0, 0.0, near_i, po);
+        launch_pp(sa.tr, stream, poses, 4, S, -1.0, 0.33, 0.0, 0, 0.0, best, h->sm_count, po);   // `best` doubles as K1's key scratch: the sampler resets it
         sample_warp_kernel<<<(S + SAMPLE_WARPS - 1) / SAMPLE_WARPS, SAMPLE_WARPS * 32, 0, stream>>>(
             sa, near_i, near4, S);
         h->launches += 2;
@@ -462,6 +474,13 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     const long long n_ctas = (long long)S * ea.ctas_per_scn;
     if (n_ctas > 0x7fffffffLL) return F1L_ERR_TOO_LARGE;
     eval_entry(M, wpc)<<<(unsigned)n_ctas, wpc * 32, smem, stream>>>(ea);
+    {
+        const EvalShape sh = eval_shape(M);
+        const int info[8] = {sh.ipl, sh.s, sh.sg, wpc,
+                             wpc == 4 ? EVAL_MINB4 : wpc == 7 ? EVAL_MINB7 : EVAL_MINB8,
+                             ea.chunk, ea.ctas_per_scn, ea.item};
+        for (int i = 0; i < 8; ++i) h->eval_info[i] = info[i];
+    }
     if (time_it) cudaEventRecord(ev[2], stream);
 
     SelectArgs se;
@@ -573,6 +592,29 @@ int f1l_get_stats(f1l_handle h, uint64_t* out, int n) {
     CK(cudaMemset(h->stats.p, 0, sizeof(v)));
     out[0] = v[0];
     out[1] = v[1];
+    return F1L_OK;
+}
+
+int f1l_debug_eval_plan(int n_cand, int n_scenarios, int M, int sm_count, int generator,
+                        int32_t* out, int n) {
+    if (!out || n < 4 || n_cand <= 0 || n_scenarios <= 0 || M < 2 || M > F1L_MAX_M || sm_count <= 0)
+        return F1L_ERR_INVALID_ARG;
+    const CtaPlan cp = plan_ctas(n_cand, n_scenarios, M, sm_count, generator == 0);
+    out[0] = cp.nw;
+    out[1] = cp.chunk;
+    out[2] = cp.ctas_per_scn;
+    out[3] = (generator == 0 && cp.chunk >= 4 * cp.nw) ? EVAL_ITEM : 1;
+    return F1L_OK;
+}
+
+int f1l_debug_pp_parts(int n_poses, int n_waypoints, int slots) {
+    if (n_poses <= 0 || n_waypoints < 2 || slots <= 0) return F1L_ERR_INVALID_ARG;
+    return pp_task_parts((n_poses + PP_CTA_POSES - 1) / PP_CTA_POSES, (n_waypoints - 1 + 31) >> 5, slots);
+}
+
+int f1l_last_eval_shape(f1l_handle h, int32_t* out, int n) {
+    if (!h || !out || n < 8) return F1L_ERR_INVALID_ARG;
+    for (int i = 0; i < 8; ++i) out[i] = h->eval_info[i];
     return F1L_OK;
 }
 
@@ -727,7 +769,7 @@ int f1l_destroy(f1l_handle h) {
                       &h->lut, &h->lookaheads, &h->widths, &h->prev, &h->q_res, &h->q_in, &h->q_goals,
                       &h->q_ctx, &h->q_centres, &h->q_best, &h->q_detail, &h->q_params, &h->q_flags, &h->q_states, &h->q_headings, &h->b_ctx, &h->b_centres,
                       &h->b_best, &h->b_near_i, &h->b_near4, &h->stats, &h->m_in, &h->m_in2, &h->m_o0, &h->m_o1, &h->m_o2, &h->m_o3,
-                      &h->m_o4, &h->m_o5, &h->pp_bk};
+                      &h->m_o4, &h->m_o5, &h->pp_key};
     for (DevBuf* b : bufs) release(*b);
     for (int i = 0; i < N_PIPE; ++i) {
         PipeSlot& p = h->pipe[i];
@@ -1220,13 +1262,9 @@ int f1l_pure_pursuit_batch_dev(f1l_handle h, const double* poses_dev, int n_pose
     o.actuation = actuation_dev;
     o.status = status_dev;
     o.front = nullptr;
-    int32_t* bk = nearest_i_dev;
-    if (!bk) {   // scratch for the scan result (one call in flight per handle)
-        ENS(h->pp_bk, (size_t)n_poses * 4);
-        bk = (int32_t*)h->pp_bk.p;
-    }
+    ENS(h->pp_key, (size_t)n_poses * 8);   // scan scratch (one call in flight per handle)
     launch_pp(track_view(h), (cudaStream_t)stream, poses_dev, 3, n_poses, L, h->cfg.wheelbase,
-              h->cfg.max_reacquire, 0, 0.0, bk, o);
+              h->cfg.max_reacquire, 0, 0.0, (unsigned long long*)h->pp_key.p, h->sm_count, o);
     h->launches += 2;
     CK(cudaGetLastError());
     return F1L_OK;
@@ -1276,13 +1314,9 @@ int f1l_front_axle_batch_dev(f1l_handle h, const double* poses_dev, int n_poses,
     o.actuation = nullptr;
     o.status = nullptr;
     o.front = front_dev;
-    int32_t* bk = nearest_i_dev;
-    if (!bk) {
-        ENS(h->pp_bk, (size_t)n_poses * 4);
-        bk = (int32_t*)h->pp_bk.p;
-    }
+    ENS(h->pp_key, (size_t)n_poses * 8);
     launch_pp(track_view(h), (cudaStream_t)stream, poses_dev, 4, n_poses, 0.0, wheelbase, 0.0, 1,
-              k_path, bk, o);
+              k_path, (unsigned long long*)h->pp_key.p, h->sm_count, o);
     h->launches += 2;
     CK(cudaGetLastError());
     return F1L_OK;

@@ -4,33 +4,37 @@
 // (intersect_point), :153-161 (get_actuation) and pure_pursuit.py:56-122.
 //
 // Two kernels:
-//   pp_scan_kernel    FP32 scan.  A CTA owns 128 poses -- four per lane, as two packed FP32x2
-//                     pairs -- and its PP_PARTS warps each scan their share of the track's
-//                     32-segment blocks for all of them.  Every lane of a warp reads the same
-//                     table entry (a broadcast load, L1-resident: 48 KB for a 2000-waypoint
-//                     track).  Why this shape: a broadcast LDS / LDG still writes 32 x 24 B back
-//                     to the register file and an SM moves 128 B per clock, so one pose per lane
-//                     is bound by that write-back at 24 cycles per (pose, segment) per warp
-//                     (measured: l1tex data pipe 87 % busy) -- four poses per lane cut it to 6
-//                     and the packed FFMA2 math (7 FMA-pipe + 1 ALU instruction per pose and
-//                     segment, the deviation loop of eval_kernel) becomes the bound.  Splitting
-//                     the TRACK over the warps of a CTA instead of the poses over more CTAs keeps
-//                     the machine full at BASELINE config 2, where 10^5 poses at four per lane
-//                     are only 782 warps.  The scan runs on a line form of each segment in the
-//                     frame of its 32-segment block (origin kept in float64), which keeps
-//                     |coordinates| small where it matters; it only has to find the right
-//                     neighbourhood.
-//   pp_finish_kernel  one thread per pose, float64: the winner and its +-2 neighbours are
-//                     re-evaluated operation by operation like the reference, so index / t / dist
-//                     / projection agree with the numba path to rounding; then the lookahead
-//                     search and get_actuation (or the Stanley / LQR front-axle errors).
+//   pp_scan_kernel    FP32 scan, a grid of ONE-WARP CTAs: a task = (group of 128 poses, part of the
+//                     track).  A lane holds four poses as two packed FP32x2 pairs; every lane of
+//                     the warp reads the same table entry (a broadcast load, L1-resident: 48 KB
+//                     for a 2000-waypoint track).  Why four poses per lane: a broadcast LDS / LDG
+//                     still writes 32 x 24 B back to the register file and an SM moves 128 B per
+//                     clock, so one pose per lane is bound by that write-back at 24 cycles per
+//                     (pose, segment) per warp (measured: l1tex data pipe 87 % busy) -- four
+//                     poses per lane cut it to 6 and the packed FFMA2 math (7 FMA-pipe + 1 ALU
+//                     instruction per pose and segment, the deviation loop of eval_kernel)
+//                     becomes the bound.  Why tasks: 10^5 poses at four per lane are only 782
+//                     warps, so the TRACK is split as well; the host picks the number of parts
+//                     so that groups x parts fills whole waves of the resident warp slots
+//                     (pp_task_parts, occupancy from the CUDA calculator) and the hardware CTA
+//                     scheduler balances the one-warp CTAs -- the earlier fixed shape (8-warp
+//                     CTAs = 8 parts, CTA barrier, shared-memory combine) ran 2.64 waves at
+//                     BASELINE config 2 and left small batches on a fraction of the SMs.  The
+//                     parts of a pose meet in a 64-bit atomicMin.  The scan runs on a line form
+//                     of each segment in the frame of its 32-segment block (origin kept in
+//                     float64), which keeps |coordinates| small where it matters; it only has to
+//                     find the right neighbourhood.
+//   pp_finish_kernel  one thread per pose.  First the warp re-scans, pose by pose, the winning
+//                     32-segment block for the segment index (lanes = segments).  Then float64:
+//                     the winner and its +-2 neighbours are re-evaluated operation by operation
+//                     like the reference, so index / t / dist / projection agree with the numba
+//                     path to rounding; then the lookahead search and get_actuation (or the
+//                     Stanley / LQR front-axle errors).
 #pragma once
 #include "f1l_common.cuh"
 
-#define PP_PARTS 8             // warps of a scan CTA, each scanning 1/PP_PARTS of the track
 #define PP_LANE_POSES 4        // poses per lane (two packed pairs)
-#define PP_CTA_POSES (32 * PP_LANE_POSES)
-#define PP_SCAN_THREADS (32 * PP_PARTS)
+#define PP_CTA_POSES (32 * PP_LANE_POSES)   // poses of a scan task
 #define PP_THREADS 128         // finish kernel
 
 struct PPOut {
@@ -77,31 +81,21 @@ __device__ __forceinline__ f32x2 track_seg_d2_pair(f32x2 px, f32x2 py, float4 A,
     return ffma2(e, e, fmul2(n, n));
 }
 
-#ifndef PP_SCAN_MINB
-#define PP_SCAN_MINB 1
+#ifndef PP_TASK_MINB
+#define PP_TASK_MINB 24    // resident one-warp scan CTAs per SM asked of the compiler (80 registers)
 #endif
-__global__ void __launch_bounds__(PP_SCAN_THREADS, PP_SCAN_MINB)
-pp_scan_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, int n_poses,
-               int front_axle, double wb, int32_t* __restrict__ best_k) {
-    __shared__ float s_d[PP_PARTS][PP_CTA_POSES];
-    __shared__ int s_b[PP_PARTS][PP_CTA_POSES];
-    const int lane = threadIdx.x & 31, part = threadIdx.x >> 5;
-    const int base = blockIdx.x * PP_CTA_POSES;
-    double qx[PP_LANE_POSES], qy[PP_LANE_POSES];
-#pragma unroll
-    for (int p = 0; p < PP_LANE_POSES; ++p) {
-        double qth;
-        pp_query_point(poses, pose_stride, min(base + p * 32 + lane, n_poses - 1), front_axle, wb,
-                       qx[p], qy[p], qth);
-    }
-    const int nseg = tr.n - 1, nblk = (nseg + 31) >> 5;
-    const int b0 = (int)((long long)nblk * part / PP_PARTS);
-    const int b1 = (int)((long long)nblk * (part + 1) / PP_PARTS);
-    // The scan keeps only the running minimum of each 32-segment block (no index bookkeeping
-    // in the inner loop) and remembers the best block; the exact index is recovered afterwards
-    // by re-scanning that one block.
-    float best[PP_LANE_POSES];
-    int bblk[PP_LANE_POSES];
+#ifndef PP_UNROLL
+#define PP_UNROLL 2
+#endif
+
+// FP32 scan of the 32-segment blocks [b0, b1) for the PP_LANE_POSES poses of this lane: the
+// running minimum of each block (no index bookkeeping in the inner loop) and the best block; the
+// exact index is recovered afterwards by re-scanning that one block.
+__device__ __forceinline__ void pp_scan_blocks(const TrackView& tr, const double (&qx)[PP_LANE_POSES],
+                                               const double (&qy)[PP_LANE_POSES], int b0, int b1,
+                                               float (&best)[PP_LANE_POSES],
+                                               int (&bblk)[PP_LANE_POSES]) {
+    const int nseg = tr.n - 1;
 #pragma unroll
     for (int p = 0; p < PP_LANE_POSES; ++p) { best[p] = CUDART_INF_F; bblk[p] = 0; }
     for (int blk = b0; blk < b1; ++blk) {
@@ -117,9 +111,6 @@ pp_scan_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, 
         float m[PP_LANE_POSES];
 #pragma unroll
         for (int p = 0; p < PP_LANE_POSES; ++p) m[p] = CUDART_INF_F;
-#ifndef PP_UNROLL
-#define PP_UNROLL 2
-#endif
         constexpr int kUnroll = PP_UNROLL;
         if (kn == 32) {
 #pragma unroll kUnroll
@@ -152,55 +143,95 @@ pp_scan_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, 
         for (int p = 0; p < PP_LANE_POSES; ++p)
             if (m[p] < best[p]) { best[p] = m[p]; bblk[p] = blk; }
     }
+}
+
+// The 32 lanes evaluate the 32 segments of block `blk` for one query point; the lowest lane
+// that attains the block minimum gives the segment index (the first minimum, utils.py:66).
+__device__ __forceinline__ int pp_rescan_block(const TrackView& tr, double x, double y, int blk,
+                                               int lane) {
+    const int nseg = tr.n - 1;
+    const double2 o = tr.blk_origin[blk];
+    const float prx = (float)(x - o.x) * TRACK_SCALE, pry = (float)(y - o.y) * TRACK_SCALE;
+    const int k = (blk << 5) + lane;
+    float d2 = CUDART_INF_F;
+    if (k < nseg) d2 = track_seg_d2(prx, pry, __ldg(tr.segA + k), __ldg(tr.segB + k));
+    const unsigned bits = __float_as_uint(d2);   // d2 >= 0: the bit pattern orders like the value
+    const unsigned mn = __reduce_min_sync(F1L_FULL, bits);
+    const unsigned hit = __ballot_sync(F1L_FULL, bits == mn);
+    return (blk << 5) + __ffs(hit) - 1;
+}
+
+// One-warp CTAs, one per (group of 128 poses, part of the track).  The parts of a pose meet in a
+// 64-bit atomicMin on (bits(d^2) << 32 | block): the smaller distance wins and, at equal
+// distance, the earlier block -- the first minimum in track order (utils.py:66).  `key` is
+// preset to all ones; the winning block is re-scanned for the segment index by pp_finish_kernel.
+__global__ void __launch_bounds__(32, PP_TASK_MINB)
+pp_scan_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, int n_poses,
+               int front_axle, double wb, int n_parts, unsigned long long* __restrict__ key) {
+    const int lane = threadIdx.x;
+    const int grp = blockIdx.x / n_parts, part = blockIdx.x - grp * n_parts;
+    const int base = grp * PP_CTA_POSES;
+    double qx[PP_LANE_POSES], qy[PP_LANE_POSES];
 #pragma unroll
     for (int p = 0; p < PP_LANE_POSES; ++p) {
-        s_d[part][p * 32 + lane] = best[p];
-        s_b[part][p * 32 + lane] = bblk[p];
+        double qth;
+        pp_query_point(poses, pose_stride, min(base + p * 32 + lane, n_poses - 1), front_axle, wb,
+                       qx[p], qy[p], qth);
     }
-    __syncthreads();
-    // Each warp finishes PP_CTA_POSES / PP_PARTS poses: lane i < 16 combines pose i's block
-    // minima over the parts (track order, strict <: the first minimum, utils.py:66); then, pose
-    // by pose, the 32 lanes evaluate the 32 segments of the winning block and the lowest lane
-    // that attains the block minimum gives the segment index.
-    constexpr int PER_WARP = PP_CTA_POSES / PP_PARTS;
-    int my_blk = 0;
-    if (lane < PER_WARP) {
-        const int pl = part * PER_WARP + lane;
-        float d = s_d[0][pl];
-        my_blk = s_b[0][pl];
+    const int nblk = (tr.n - 1 + 31) >> 5;
+    const int b0 = (int)((long long)nblk * part / n_parts);
+    const int b1 = (int)((long long)nblk * (part + 1) / n_parts);
+    float best[PP_LANE_POSES];
+    int bblk[PP_LANE_POSES];
+    pp_scan_blocks(tr, qx, qy, b0, b1, best, bblk);
 #pragma unroll
-        for (int q = 1; q < PP_PARTS; ++q)
-            if (s_d[q][pl] < d) { d = s_d[q][pl]; my_blk = s_b[q][pl]; }
-    }
-    for (int i = 0; i < PER_WARP; ++i) {
-        const int gid = base + part * PER_WARP + i;
-        if (gid >= n_poses) break;   // warp-uniform
-        const int blk = __shfl_sync(F1L_FULL, my_blk, i);
-        double x, y, th;
-        pp_query_point(poses, pose_stride, gid, front_axle, wb, x, y, th);
-        const double2 o = tr.blk_origin[blk];
-        const float prx = (float)(x - o.x) * TRACK_SCALE, pry = (float)(y - o.y) * TRACK_SCALE;
-        const int k = (blk << 5) + lane;
-        float d2 = CUDART_INF_F;
-        if (k < nseg) d2 = track_seg_d2(prx, pry, __ldg(tr.segA + k), __ldg(tr.segB + k));
-        const unsigned bits = __float_as_uint(d2);   // d2 >= 0: the bit pattern orders like the value
-        const unsigned mn = __reduce_min_sync(F1L_FULL, bits);
-        const unsigned hit = __ballot_sync(F1L_FULL, bits == mn);
-        if (lane == 0) best_k[gid] = (blk << 5) + __ffs(hit) - 1;
+    for (int p = 0; p < PP_LANE_POSES; ++p) {
+        const int gid = base + p * 32 + lane;
+        if (gid < n_poses && b1 > b0)
+            atomicMin(key + gid, ((unsigned long long)__float_as_uint(best[p]) << 32) | (unsigned)bblk[p]);
     }
 }
 
-// `best_k` may alias out.nearest_i (each thread reads its element before writing it)
+// Parts of the track per pose group such that groups x parts one-warp tasks fill whole waves of
+// `slots` resident warps: the most efficient count in [6, 24] (fewer, longer tasks on ties); a
+// task pays a fixed prologue / epilogue of about 1.5 blocks' worth of work.
+static inline int pp_task_parts(int n_groups, int nblk, int slots) {
+    int best_p = 8;
+    double best_eff = -1.0;
+    for (int p = 6; p <= 24 && p <= nblk; ++p) {
+        const double w = (double)n_groups * p / slots;
+        const double waves = w <= 1.0 ? 1.0 : (double)(long long)(w + 0.999999);
+        const double eff = (w / waves) * ((double)nblk / p) / ((double)nblk / p + 1.5);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_p = p; }
+    }
+    if (best_p > nblk) best_p = nblk > 0 ? nblk : 1;
+    return best_p;
+}
+
+// `key`: the packed (d^2, block) minima of pp_scan_kernel, one per pose
 __global__ void __launch_bounds__(PP_THREADS)
 pp_finish_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, int n_poses, double L, double wb,
-                 double max_reacquire, int front_axle, double k_path, const int32_t* best_k, PPOut out) {
+                 double max_reacquire, int front_axle, double k_path,
+                 const unsigned long long* __restrict__ key, PPOut out) {
     const int nseg = tr.n - 1;
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= n_poses) return;
-    const int pid = gid;
+    const int pid = min(gid, n_poses - 1);
     double qx, qy, qth;
     pp_query_point(poses, pose_stride, pid, front_axle, wb, qx, qy, qth);
-    const int bk = best_k[gid];
+    // the warp re-scans the winning block of each of its 32 poses, all lanes on one pose at a time
+    int bk = 0;
+    {
+        const int lane = threadIdx.x & 31;
+        const int my_blk = (int)(unsigned)(key[pid] & 0xffffffffull);
+        const int n_live = min(32, n_poses - (gid - lane));   // warp-uniform
+        for (int i = 0; i < n_live; ++i) {
+            const int blk = __shfl_sync(F1L_FULL, my_blk, i);
+            const double x = __shfl_sync(F1L_FULL, qx, i), y = __shfl_sync(F1L_FULL, qy, i);
+            const int k = pp_rescan_block(tr, x, y, blk, lane);
+            if (lane == i) bk = k;
+        }
+    }
+    if (gid >= n_poses) return;
     // float64 epilogue: exact nearest among the neighbours, then pure_pursuit.py:69-83
     const Nearest64 nr = refine_nearest64(tr.xy, nseg, qx, qy, bk);
     if (front_axle) {

@@ -362,6 +362,16 @@ class Engine:
         self._ck(self._L.f1l_get_stats(self._h, out, 2))
         return int(out[0]), int(out[1])
 
+    def last_eval_shape(self):
+        """Template instance and CTA plan of the last eval_kernel launch (f1l_last_eval_shape):
+        dict with ipl, s, sg, nw, minb, chunk, ctas_per_scenario, item and the instance `name`."""
+        out = (C.c_int32 * 8)()
+        self._ck(self._L.f1l_last_eval_shape(self._h, out, 8))
+        keys = ("ipl", "s", "sg", "nw", "minb", "chunk", "ctas_per_scenario", "item")
+        d = {k: int(v) for k, v in zip(keys, out)}
+        d["name"] = "eval_kernel<%d,%d,%d,%d,%d>" % tuple(out[:5])
+        return d
+
     def set_graph(self, on):
         """replay the single-query chain as a CUDA graph (default on)"""
         self._ck(self._L.f1l_set_graph(self._h, int(bool(on))))

@@ -256,6 +256,12 @@ int f1l_get_actuation_batch(f1l_handle h, const double* in, int n, double wheelb
  * window length.  n >= 2. */
 int f1l_get_stats(f1l_handle h, uint64_t* out, int n);
 
+/* Which eval_kernel<IPL, S, SG, NW, MINB> instance the last f1l_plan* call launched and its CTA
+ * plan: out[0..4] = IPL, S, SG, NW (warps per CTA), MINB (resident CTAs per SM asked of the
+ * compiler); out[5] = candidates per CTA, out[6] = CTAs per scenario, out[7] = candidates a warp
+ * solves together (4 = shared Newton).  n >= 8.  Evidence for bench.py / profiles. */
+int f1l_last_eval_shape(f1l_handle h, int32_t* out, int n);
+
 /* Timing / evidence helpers: number of kernels launched by this handle so far, and the device
  * time (ms, CUDA events on the handle's stream) of the kernels of the last host-pointer call. */
 int64_t f1l_launch_count(f1l_handle h);
@@ -278,6 +284,16 @@ int f1l_measure_peaks(f1l_handle h, double* fp32_tflops, double* mufu_gops);
 /* Extended probes: out[0] FFMA TFLOP/s, out[1] MUFU Gop/s, out[2] packed FFMA2 (fma.rn.f32x2)
  * TFLOP/s, out[3] warp-instructions per clock per SM of an FFMA + FMNMX mix (n >= 4). */
 int f1l_measure_peaks_ex(f1l_handle h, double* out, int n);
+
+/* Host-side launch planning, callable without a device (tests of the host logic):
+ * f1l_debug_eval_plan: the CTA plan of eval_kernel for n_scenarios queries of n_cand candidates
+ * and M arc samples on sm_count SMs -- out[0] = warps per CTA, out[1] = candidates per CTA,
+ * out[2] = CTAs per scenario, out[3] = candidates a warp solves together (n >= 4).
+ * f1l_debug_pp_parts: into how many parts pp_scan_kernel splits a track of n_waypoints for
+ * n_poses poses when `slots` one-warp CTAs are resident on the device (> 0), or an error (< 0). */
+int f1l_debug_eval_plan(int n_cand, int n_scenarios, int M, int sm_count, int generator,
+                        int32_t* out, int n);
+int f1l_debug_pp_parts(int n_poses, int n_waypoints, int slots);
 
 /* Debug / test hook: the float32 per-query constants of the last f1l_plan* call, for
  * teacher-forced collision checks.  out_f[72]: cos, sin of the pose heading; grid transform A00
