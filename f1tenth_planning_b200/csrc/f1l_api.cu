@@ -1007,7 +1007,11 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
         d_goals = (const float4*)h->q_goals.p;
     }
 
-    ENS(h->q_res, sizeof(QHeader) + F1L_MAX_M * sizeof(float4));
+    if (!h->q_res.p) {
+        ENS(h->q_res, sizeof(QHeader) + F1L_MAX_M * sizeof(float4));
+        // the header's padding words travel with the D2H copy: defined bytes (initcheck-clean)
+        CK(cudaMemsetAsync(h->q_res.p, 0, sizeof(QHeader), st));
+    }
     char* dres = (char*)h->q_res.p;
     BatchOut o;
     o.steer_speed = (double*)(dres + offsetof(QHeader, steer));
