@@ -334,8 +334,10 @@ def extras(track, grid, device):
 
 def sharded_dense_query(track, grid, device, rank, world_size, dev):
     """config 5 across ranks: every rank evaluates a contiguous block of the 65536 candidates of
-    ONE query (f1l_plan_shard), then an 8-byte-per-rank gather of (cost, idx) picks the winner
-    (SURVEY 8e).  Latency = barrier-to-result on the slowest rank."""
+    ONE query (f1l_plan_shard) and the ranks' (cost, idx) minima are exchanged --
+    (a) inside the select kernel through peer memory over NVLink (Engine.attach_peers; every
+    rank's plan() returns the global winner), (b) for comparison by a 16-byte NCCL all-gather plus
+    a host min (sharding.reduce_best).  Latency = barrier-to-result on the slowest rank."""
     import torch
     import torch.distributed as dist
     from f1tenth_planning_b200 import sharding
@@ -348,29 +350,40 @@ def sharded_dense_query(track, grid, device, rank, world_size, dev):
     C = eng.n_candidates
     lo, hi = sharding.block(C, rank, world_size)
     poses, opp, n_opp = synth.scenario_batch(track, 16, 8, 1005)   # same on every rank
-    ts, tp = [], []
-    best = None
-    for i in range(3 + 30):
-        s = i % 16
-        dist.barrier()
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        d = eng.plan(poses[s], opp[s], update_prev=False, detail=False, shard=(lo, hi))
-        t1 = time.perf_counter()
-        best = sharding.reduce_best(d.best_cost, d.best_idx)
-        dt = time.perf_counter() - t0
-        if i >= 3:
-            ts.append(dt)
-            tp.append(t1 - t0)
-    t = torch.tensor(ts, dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+    def run(n_rep, reduce_on_host):
+        ts, tp, bests = [], [], []
+        for i in range(3 + n_rep):
+            s = i % 16
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            d = eng.plan(poses[s], opp[s], update_prev=False, detail=False, shard=(lo, hi))
+            t1 = time.perf_counter()
+            best = (sharding.reduce_best(d.best_cost, d.best_idx) if reduce_on_host
+                    else (float(d.best_cost), int(d.best_idx)))
+            dt = time.perf_counter() - t0
+            if i >= 3:
+                ts.append(dt)
+                tp.append(t1 - t0)
+                bests.append((float(np.float32(best[0])), int(best[1])))
+        t = torch.tensor(ts, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.cpu().numpy(), np.array(tp), bests
+
+    ts_n, tp_n, best_n = run(32, True)        # (b) NCCL all-gather + host min
+    eng.attach_peers()
+    ts_p, _, best_p = run(32, False)          # (a) peer memory, inside the select kernel
+    eng.detach_peers()
     eng.close()
-    ts = t.cpu().numpy()
-    return {"c5_sharded_plan_p50_us": 1e6 * float(np.percentile(ts, 50)),
-            "c5_sharded_plan_p99_us": 1e6 * float(np.percentile(ts, 99)),
-            "c5_sharded_candidates_per_s": C / float(np.percentile(ts, 50)),
-            "c5_sharded_local_plan_p50_us": 1e6 * float(np.percentile(tp, 50)),
-            "c5_candidates_per_rank": hi - lo, "c5_last_best": list(best)}
+    return {"c5_sharded_plan_p50_us": 1e6 * float(np.percentile(ts_p, 50)),
+            "c5_sharded_plan_p99_us": 1e6 * float(np.percentile(ts_p, 99)),
+            "c5_sharded_candidates_per_s": C / float(np.percentile(ts_p, 50)),
+            "c5_sharded_exchange": "peer memory (CUDA IPC over NVLink, system-scope atomicMin in select_kernel)",
+            "c5_sharded_nccl_gather_p50_us": 1e6 * float(np.percentile(ts_n, 50)),
+            "c5_sharded_local_plan_p50_us": 1e6 * float(np.percentile(tp_n, 50)),
+            "c5_sharded_paths_agree": best_n == best_p,
+            "c5_candidates_per_rank": hi - lo, "c5_last_best": list(best_p[-1])}
 
 
 def run_ours(args):

@@ -41,7 +41,7 @@ struct f1l_ctx {
     int use_graph = 1;
     unsigned long long epoch = 0;   // bumped by every upload / config change
     cudaGraphExec_t gexec = nullptr;
-    unsigned long long gkey[2] = {~0ull, ~0ull};
+    unsigned long long gkey[3] = {~0ull, ~0ull, ~0ull};
     int timed = 0;  // events of the last pipeline launch are valid
 #define F1L_EV_SLOTS 64
     cudaEvent_t ev[4 * F1L_EV_SLOTS] = {nullptr};
@@ -85,6 +85,10 @@ struct f1l_ctx {
     PipeSlot pipe[N_PIPE];
     // misc scratch for the pure-pursuit / intersect host APIs
     DevBuf m_in, m_in2, m_o0, m_o1, m_o2, m_o3, m_o4, m_o5, pp_key;
+    // peer-memory exchange of candidate-sharded queries (f1l_xchg_*): the local block, the peers'
+    // blocks as mapped by cudaIpcOpenMemHandle (own rank: the local pointer)
+    DevBuf xchg;
+    XchgView xview = {0, 0, {nullptr}};
     // template instance / CTA plan of the last eval_kernel launch (f1l_last_eval_shape)
     int eval_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -372,6 +376,8 @@ struct BatchOut {
     float4* states = nullptr;
     float2* headings = nullptr;
     float* prev_out = nullptr;
+    const XchgView* xc = nullptr;      // sharded single query: exchange the argmin with the peers
+    int32_t* xchg_status = nullptr;
 };
 
 // sampler -> eval -> select for S scenarios on `stream`; all pointers are device pointers
@@ -484,6 +490,9 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     if (time_it) cudaEventRecord(ev[2], stream);
 
     SelectArgs se;
+    if (o.xc && S == 1) se.xc = *o.xc;
+    else { se.xc.world = 0; se.xc.rank = 0; }
+    se.xchg_status = o.xchg_status;
     se.tr = sa.tr;
     se.lut = ea.lut;
     se.ep = ep;
@@ -575,6 +584,7 @@ const char* f1l_strerror(int code) {
         case F1L_ERR_TOO_LARGE: return "problem too large for this build (window / grid limits)";
         case F1L_ERR_NO_GOALS: return "no goal grid set (f1l_set_goal_grid) and no explicit goals";
         case F1L_ERR_ALLOC: return "host allocation failed";
+        case F1L_ERR_PEER_TIMEOUT: return "a peer rank did not arrive at the sharded-query exchange";
         default: return "unknown f1l status";
     }
 }
@@ -765,6 +775,8 @@ int f1l_destroy(f1l_handle h) {
     if (!h) return F1L_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    f1l_xchg_detach(h);
+    release(h->xchg);
     DevBuf* bufs[] = {&h->xy, &h->v, &h->psi, &h->kappa, &h->segA, &h->segB, &h->blk, &h->grid, &h->clear, &h->clear_tmp,
                       &h->lut, &h->lookaheads, &h->widths, &h->prev, &h->q_res, &h->q_in, &h->q_goals,
                       &h->q_ctx, &h->q_centres, &h->q_best, &h->q_detail, &h->q_params, &h->q_flags, &h->q_states, &h->q_headings, &h->b_ctx, &h->b_centres,
@@ -952,7 +964,7 @@ int f1l_clear_prev_path(f1l_handle h) {
 // ---- single query -------------------------------------------------------------------------
 static int plan_internal(f1l_handle h, const double pose[4], const double* opp, int n_opp,
                          const double* goals, int n_goals, int c_begin, int c_end,
-                         int update_prev, f1l_plan_result* out) {
+                         int update_prev, f1l_plan_result* out, bool exchange = false) {
     if (!h || !pose || !out) return F1L_ERR_INVALID_ARG;
     if (n_opp < 0 || n_opp > F1L_MAX_OPP || (n_opp > 0 && !opp)) return F1L_ERR_INVALID_ARG;
     if (h->n < 2) return F1L_ERR_NO_TRACK;
@@ -1027,7 +1039,12 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     o.states = out->states ? (float4*)h->q_states.p : nullptr;
     o.headings = out->headings ? (float2*)h->q_headings.p : nullptr;
     o.prev_out = update_prev ? (float*)h->prev.p : nullptr;
-    const bool sharded = c_begin != 0 || (c_end > 0 && c_end < C);
+    exchange = exchange && h->xview.world > 1;
+    if (exchange) {   // the ranks' minima meet inside select_kernel (peer memory over NVLink)
+        o.xc = &h->xview;
+        o.xchg_status = (int32_t*)(dres + offsetof(QHeader, pad));
+    }
+    const bool sharded = exchange || c_begin != 0 || (c_end > 0 && c_end < C);
     QHeader* hd = (QHeader*)h->h_out;
     float* htraj = (float*)((char*)h->h_out + sizeof(QHeader));
     const QInput* din = (const QInput*)h->q_in.p;
@@ -1052,14 +1069,17 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
             CK(cudaMemcpyAsync(h->h_detail, ddet, detail_bytes, cudaMemcpyDeviceToHost, st));
         return F1L_OK;
     };
-    if (h->use_graph && !goals && !sharded && !h->timing) {
+    if (h->use_graph && !goals && !h->timing) {
         // the whole chain as one CUDA graph, re-captured only when an upload / config change or
         // the set of requested outputs alters a kernel argument
         const unsigned long long mask = (want_detail ? 256u : 0u) | (out->terms ? 1u : 0u) | (out->flags ? 2u : 0u) |
                                         (out->goals ? 4u : 0u) | (out->params ? 8u : 0u) |
                                         (out->states ? 16u : 0u) | (out->headings ? 32u : 0u) |
-                                        (update_prev ? 64u : 0u) | (h->has_prev ? 128u : 0u);
-        if (!h->gexec || h->gkey[0] != h->epoch || h->gkey[1] != mask) {
+                                        (update_prev ? 64u : 0u) | (h->has_prev ? 128u : 0u) |
+                                        (exchange ? 512u : 0u);
+        // a candidate shard is a constant of the captured kernels too
+        const unsigned long long shard_key = ((unsigned long long)(unsigned)c_begin << 32) | (unsigned)c_end;
+        if (!h->gexec || h->gkey[0] != h->epoch || h->gkey[1] != mask || h->gkey[2] != shard_key) {
             if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
             const int64_t launches0 = h->launches;
             cudaGraph_t graph = nullptr;
@@ -1074,6 +1094,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
             if (ce != cudaSuccess) { h->gexec = nullptr; return fail(h, ce, "cudaGraphInstantiate"); }
             h->gkey[0] = h->epoch;
             h->gkey[1] = mask;
+            h->gkey[2] = shard_key;
         }
         CK(cudaGraphLaunch(h->gexec, st));
         h->launches += 3;
@@ -1090,6 +1111,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
         h->has_prev = 1;
         h->prev_m = M;
     }
+    if (exchange && hd->pad != 0) return F1L_ERR_PEER_TIMEOUT;
     out->steer = hd->steer;
     out->speed = hd->speed;
     out->best_idx = hd->best_idx;
@@ -1116,7 +1138,64 @@ int f1l_plan(f1l_handle h, const double pose[4], const double* opp, int n_opp, i
 
 int f1l_plan_shard(f1l_handle h, const double pose[4], const double* opp, int n_opp, int c_begin,
                    int c_end, f1l_plan_result* out) {
-    return plan_internal(h, pose, opp, n_opp, nullptr, 0, c_begin, c_end, 0, out);
+    // with peers attached (f1l_xchg_attach) every rank returns the GLOBAL winner
+    return plan_internal(h, pose, opp, n_opp, nullptr, 0, c_begin, c_end, 0, out, true);
+}
+
+// ---- peer-memory exchange (CUDA IPC over NVLink P2P) -----------------------------------------
+int f1l_xchg_export(f1l_handle h, uint8_t* handle_out, int n) {
+    if (!h || !handle_out || n < (int)sizeof(cudaIpcMemHandle_t)) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (h->xview.world > 1) return F1L_ERR_INVALID_ARG;   // detach first
+    // a whole 2 MB allocation granule of its own: the IPC handle maps exactly this block
+    ENS(h->xchg, (size_t)2 << 20);
+    unsigned long long init[F1L_XCHG_WORDS];
+    for (int i = 0; i < F1L_XCHG_WORDS; ++i) init[i] = i < 4 ? ~0ull : 0ull;
+    CK(cudaMemcpy(h->xchg.p, init, sizeof(init), cudaMemcpyHostToDevice));
+    cudaIpcMemHandle_t mh;
+    CK(cudaIpcGetMemHandle(&mh, h->xchg.p));
+    memcpy(handle_out, &mh, sizeof(mh));
+    return F1L_OK;
+}
+
+int f1l_xchg_attach(f1l_handle h, int rank, int world, const uint8_t* handles) {
+    if (!h || !handles || world < 1 || world > F1L_MAX_RANKS || rank < 0 || rank >= world)
+        return F1L_ERR_INVALID_ARG;
+    if (!h->xchg.p || h->xview.world > 1) return F1L_ERR_INVALID_ARG;   // export first / detach first
+    CK(cudaSetDevice(h->device));
+    XchgView v;
+    v.world = world;
+    v.rank = rank;
+    for (int r = 0; r < F1L_MAX_RANKS; ++r) v.peer[r] = nullptr;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { v.peer[r] = (unsigned long long*)h->xchg.p; continue; }
+        cudaIpcMemHandle_t mh;
+        memcpy(&mh, handles + (size_t)r * sizeof(mh), sizeof(mh));
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; ++q)
+                if (q != rank && v.peer[q]) cudaIpcCloseMemHandle(v.peer[q]);
+            return fail(h, e, "cudaIpcOpenMemHandle");
+        }
+        v.peer[r] = (unsigned long long*)p;
+    }
+    h->xview = v;
+    h->epoch++;   // a captured graph holds the old kernel arguments
+    return F1L_OK;
+}
+
+int f1l_xchg_detach(f1l_handle h) {
+    if (!h) return F1L_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < h->xview.world; ++r)
+        if (r != h->xview.rank && h->xview.peer[r]) cudaIpcCloseMemHandle(h->xview.peer[r]);
+    h->xview.world = 0;
+    h->xview.rank = 0;
+    for (int r = 0; r < F1L_MAX_RANKS; ++r) h->xview.peer[r] = nullptr;
+    h->epoch++;
+    return F1L_OK;
 }
 
 int f1l_plan_goals(f1l_handle h, const double pose[4], const double* goals, int n_goals,

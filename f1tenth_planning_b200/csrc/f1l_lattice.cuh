@@ -358,7 +358,64 @@ struct EvalArgs {
     unsigned long long* stats; // [2] deviation-pass work counters (segment steps, candidates) or null
 };
 
+// Peer-memory exchange of a candidate-sharded query (the one exchange step of the
+// path).  Every rank owns a 128-byte block in its HBM, mapped into the other ranks' address
+// spaces with CUDA IPC (NVLink P2P): u64 words [0..3] argmin-key slots, [4..7] arrival counters,
+// [8] call sequence number (local), [9] sticky timeout flag (local).
+#define F1L_MAX_RANKS 16
+#define F1L_XCHG_WORDS 16
+#ifndef F1L_XCHG_TIMEOUT_CYCLES
+#define F1L_XCHG_TIMEOUT_CYCLES 4000000000ll   // ~2 s at 1.965 GHz: a dead peer must not hang the GPU
+#endif
+struct XchgView {
+    int world, rank;                                // world <= 1: no exchange
+    unsigned long long* peer[F1L_MAX_RANKS];        // peer[rank] is the local block
+};
+
+// Lanes r < world each push this rank's packed (cost, index) key into rank r's slot with a
+// system-scope atomicMin over NVLink, fence, then bump rank r's arrival counter; lane 0 waits until
+// all `world` arrivals are visible in the local block and reads the global minimum -- every rank
+// ends with the same key, the first minimum of the concatenated cost vector (np.argmin).  Slots
+// are used round-robin by call number and a call resets the slot two calls ahead: a peer can only
+// be one call ahead of the slowest rank (it waits for everybody's arrival), so a slot is never
+// reset while somebody may still write or read it.  Returns the global key; *timed_out is set
+// when a peer did not arrive within F1L_XCHG_TIMEOUT_CYCLES.
+__device__ __forceinline__ unsigned long long xchg_global_min(const XchgView& xc, unsigned long long key,
+                                                              int lane, int* timed_out) {
+    unsigned long long* mine = xc.peer[xc.rank];
+    const unsigned seq = (unsigned)(*(volatile unsigned long long*)(mine + 8));
+    const int slot = (int)(seq & 3u);
+    if (lane < xc.world) {
+        unsigned long long* dst = xc.peer[lane];
+        atomicMin_system(dst + slot, key);
+        __threadfence_system();
+        atomicAdd_system(dst + 4 + slot, 1ull);
+    }
+    __syncwarp();
+    unsigned long long g = key;
+    int bad = 0;
+    if (lane == 0) {
+        const long long t0 = clock64();
+        volatile unsigned long long* cnt = mine + 4 + slot;
+        while (*cnt < (unsigned long long)xc.world) {
+            if (clock64() - t0 > F1L_XCHG_TIMEOUT_CYCLES) { bad = 1; break; }
+        }
+        __threadfence_system();
+        g = *(volatile unsigned long long*)(mine + slot);
+        const int nxt = (slot + 2) & 3;
+        mine[nxt] = ~0ull;
+        mine[4 + nxt] = 0ull;
+        mine[8] = (unsigned long long)(seq + 1u);
+        if (bad) mine[9] = 1ull;
+        bad |= (int)(*(volatile unsigned long long*)(mine + 9));
+    }
+    *timed_out = __shfl_sync(F1L_FULL, bad, 0);
+    return __shfl_sync(F1L_FULL, g, 0);
+}
+
 struct SelectArgs {
+    XchgView xc;            // sharded single query: global argmin over the ranks' shards
+    int32_t* xchg_status;   // [1] != 0: a peer did not arrive (nullable)
     TrackView tr;
     LutView lut;
     EvalParams ep;
@@ -1261,7 +1318,12 @@ __global__ void __launch_bounds__(32) select_kernel(SelectArgs a) {
     const int s = blockIdx.x, lane = threadIdx.x;
     const int M = a.ep.M;
     const QueryCtx* __restrict__ q = a.ctx + s;
-    const unsigned long long key = a.best[s];
+    unsigned long long key = a.best[s];
+    if (a.xc.world > 1) {   // (S == 1) the ranks' local minima meet over NVLink peer memory
+        int timed_out = 0;
+        key = xchg_global_min(a.xc, key, lane, &timed_out);
+        if (lane == 0 && a.xchg_status) *a.xchg_status = timed_out;
+    }
     int idx = (int)(key & 0xffffffffu);
     float cost = orderable_float((uint32_t)(key >> 32));
     const bool none = (key == ~0ull) || !(cost < CUDART_INF_F);

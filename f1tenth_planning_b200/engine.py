@@ -63,6 +63,7 @@ class Engine:
         self.n_lookaheads = 0
         self.n_widths = 0
         self.n_waypoints = 0
+        self.peer_world = 0
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self):
@@ -287,6 +288,38 @@ class Engine:
                                             _vp(best_idx), _vp(best_cost), _vp(best_traj),
                                             _vp(costs), _vp(flags), _vp(steer_speed),
                                             C.c_void_p(st)))
+
+    # -- candidate sharding over peer memory -------------------------------------------------
+    def export_peer_handle(self):
+        """64-byte CUDA IPC handle of this engine's exchange block (f1l_xchg_export)."""
+        buf = (C.c_uint8 * 64)()
+        self._ck(self._L.f1l_xchg_export(self._h, buf, 64))
+        return bytes(buf)
+
+    def attach_peer_handles(self, rank, handles):
+        """handles: the export_peer_handle() bytes of every rank, in rank order (f1l_xchg_attach).
+        Afterwards plan(shard=...) is collective and returns the global winner on every rank."""
+        world = len(handles)
+        blob = (C.c_uint8 * (64 * world)).from_buffer_copy(b"".join(handles))
+        self._ck(self._L.f1l_xchg_attach(self._h, int(rank), world, blob))
+        self.peer_world = world
+
+    def attach_peers(self, group=None):
+        """Exchange the IPC handles over torch.distributed (any backend) and attach; collective."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        handles = [None] * world
+        dist.all_gather_object(handles, self.export_peer_handle(), group=group)
+        self.attach_peer_handles(rank, handles)
+        dist.barrier(group=group)   # nobody starts a collective query before everybody is attached
+
+    def detach_peers(self, group=None):
+        if group is not False:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.barrier(group=group)   # nobody unmaps a block a peer may still write
+        self._ck(self._L.f1l_xchg_detach(self._h))
+        self.peer_world = 0
 
     # -- pure pursuit -----------------------------------------------------------------------
     def pure_pursuit_batch(self, poses, lookahead_distance, out=None):

@@ -1,6 +1,14 @@
 """Multi-GPU partitioning of the lattice path.  Scenarios (config 4) and the
 candidates of one dense query (config 5) are independent, so ranks take contiguous blocks and
-the only exchange is the final gather of one (cost, index) pair per rank -- 8 bytes."""
+the only exchange is the final gather of one (cost, index) pair per rank -- 8 bytes.
+
+Two ways to do that exchange for a candidate-sharded query:
+  * Engine.attach_peers(): the select kernel itself pushes the rank's packed (cost, index) key
+    into every peer's HBM over NVLink (CUDA IPC mapped peer memory, system-scope atomicMin) and
+    every rank's plan(shard=...) returns the global winner -- no host round trip, no collective
+    library call on the latency path (GPU ranks of one node);
+  * reduce_best(): a torch.distributed all-gather of the pair plus a host min -- any backend
+    (gloo on CPU), used by the CPU tests and as the cross-check of the first."""
 import numpy as np
 
 

@@ -37,7 +37,8 @@ typedef enum {
     F1L_ERR_NO_DEVICE = -4,
     F1L_ERR_TOO_LARGE = -5,
     F1L_ERR_NO_GOALS = -6,
-    F1L_ERR_ALLOC = -7
+    F1L_ERR_ALLOC = -7,
+    F1L_ERR_PEER_TIMEOUT = -8
 } f1l_status;
 
 #define F1L_N_TERMS 5       /* length, max|kappa|, mean|kappa|, similarity, raceline deviation */
@@ -167,9 +168,28 @@ int f1l_plan(f1l_handle h, const double pose[4], const double* opp, int n_opp,
              int update_prev, f1l_plan_result* out);
 
 /* Same, but only candidates [c_begin, c_end) are evaluated (candidate sharding of one dense
- * query across GPUs; best_idx is still the global index). */
+ * query across GPUs; best_idx is still the global index).  Without attached peers the result is
+ * the winner of the shard; with f1l_xchg_attach it is the winner over all ranks' shards. */
 int f1l_plan_shard(f1l_handle h, const double pose[4], const double* opp, int n_opp,
                    int c_begin, int c_end, f1l_plan_result* out);
+
+/*
+ * Peer-memory exchange for f1l_plan_shard ("final step = gather of G (cost, idx)
+ * pairs"; replaces an 8-byte NCCL all-gather plus host min).  Each rank (one process per GPU, or
+ * several handles of one node) exports a 128-byte block of its HBM as a CUDA IPC handle
+ * (f1l_xchg_export, 64 bytes), the caller gathers the `world` handles by any means (the Python
+ * layer uses torch.distributed) and attaches them in rank order (f1l_xchg_attach: maps the peers'
+ * blocks over NVLink P2P).  From then on f1l_plan_shard is collective: every rank calls it for
+ * the same query with its own [c_begin, c_end), the select kernel pushes the rank's packed
+ * (cost, index) minimum into every peer's block with system-scope atomics and waits for all
+ * arrivals, and every rank returns the GLOBAL best_idx / best_cost / best_traj / steer / speed.
+ * A peer that does not arrive within ~2 s yields F1L_ERR_PEER_TIMEOUT (the GPU never hangs).
+ * All ranks must have attached before the first collective call and must stop calling before
+ * any of them detaches or is destroyed (barrier on the caller's side).  world <= 16.
+ */
+int f1l_xchg_export(f1l_handle h, uint8_t* handle_out, int n);   /* n >= 64 */
+int f1l_xchg_attach(f1l_handle h, int rank, int world, const uint8_t* handles /* [world][64] */);
+int f1l_xchg_detach(f1l_handle h);
 
 /* Same pipeline with caller-supplied local goals [C,3] (vehicle frame) instead of the built-in
  * sampler.  Replaces the user `sample_func` plug-in (lattice_planner.py:77-98,113-128). */

@@ -235,6 +235,34 @@ def test_g1_clothoid_generator(ellipse, corridor):
         assert H.close(stt, ref, scale=H.traj_scale(ref)).all()
 
 
+def test_generators_reproduce_analytic_known_answers(ellipse):
+    """Known answers that need no oracle: the G1 clothoid joining the two poses of a circular arc
+    is that arc (kappa = 1/R, no curvature rate, length R phi), and both generators return the
+    straight line for a goal straight ahead.  FP32 device states within 1e-4 (north_star)."""
+    arcs = [(R, phi) for R in (0.8, 2.0, 5.0, 40.0) for phi in (0.05, 0.3, 1.0, np.pi / 2, -0.7, -1.4)
+            if R * abs(phi) <= 6.0]
+    goals = np.array([[R * np.sin(abs(p)), np.sign(p) * R * (1 - np.cos(p)), p] for R, p in arcs])
+    la, wd = synth.goal_grid(1)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, generator=1, kappa_max=0.0)
+    states, params, valid = eng.generate(goals)
+    assert valid.all()
+    for (R, phi), st, pr in zip(arcs, states, params):
+        s = np.linspace(0, R * abs(phi), cfg.n_samples)
+        ref = np.stack([R * np.sin(s / R), np.sign(phi) * R * (1 - np.cos(s / R)), np.sign(phi) * s / R,
+                        np.full_like(s, np.sign(phi) / R)], axis=1)
+        assert H.close(st, ref, scale=H.traj_scale(ref)).all(), (R, phi, np.abs(st - ref).max(axis=0))
+        assert abs(pr[2] - R * abs(phi)) <= 1e-4 * R * abs(phi)            # length
+        assert abs(pr[0] - np.sign(phi) / R) <= 1e-4 * max(1.0 / R, 1.0)   # kappa0
+    line = np.array([[0.4, 0.0, 0.0], [2.0, 0.0, 0.0], [4.0, 0.0, 0.0]])
+    for gen in (0, 1):
+        eng.configure(generator=gen)
+        states, params, valid = eng.generate(line)
+        assert valid.all()
+        for g, st in zip(line, states):
+            np.testing.assert_allclose(st[:, 0], np.linspace(0, g[0], cfg.n_samples), atol=1e-4 * g[0] + 1e-6)
+            assert np.abs(st[:, 1:]).max() <= 1e-5
+
+
 def test_real_track_and_map_fixtures(golden_spielberg):
     """Spielberg raceline + its ROS map and the Levine raceline + SLAM map (reference fixtures,
     carried as tests/golden/maps.npz): plan parity against the oracle along the tracks."""

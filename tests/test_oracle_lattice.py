@@ -204,3 +204,71 @@ def test_g1_clothoid_against_ode(goal):
     # the reference's own example goal, G1Hermite(0,0,0,1,1,0) (test_pyclothoids.py:23): symmetric
     if goal == (1.0, 1.0, 0.0):
         np.testing.assert_allclose(st[:, 3], -st[::-1, 3], atol=1e-9)
+
+
+@pytest.mark.parametrize("R", [0.8, 2.0, 5.0, 40.0])
+@pytest.mark.parametrize("phi", [0.05, 0.3, 1.0, np.pi / 2, -0.7, -1.4])
+def test_g1_clothoid_known_answers_circular_arcs(R, phi):
+    """Analytic known answers of G1 Hermite interpolation (the boundary lattice_planner.py:196
+    crosses into pyclothoids): the pose reached after turning by phi on a circle of radius R is
+    joined by that arc -- kappa = sign(phi)/R, no curvature rate, length R |phi|."""
+    goal = (R * np.sin(abs(phi)), np.sign(phi) * R * (1 - np.cos(phi)), phi)
+    kdl, st, ok = co.clothoid(goal, n_newton=10, m=100)
+    assert ok
+    # tolerances: the oracle integrates with composite Simpson on Q = 32 intervals (DESIGN 3)
+    np.testing.assert_allclose(kdl[0], np.sign(phi) / R, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(kdl[1], 0.0, atol=1e-6 / R ** 2)
+    np.testing.assert_allclose(kdl[2], R * abs(phi), rtol=1e-7)
+    s = np.linspace(0, R * abs(phi), 100)
+    np.testing.assert_allclose(st[:, 0], R * np.sin(s / R), atol=1e-6 * max(R, 1))
+    np.testing.assert_allclose(st[:, 1], np.sign(phi) * R * (1 - np.cos(s / R)), atol=1e-6 * max(R, 1))
+    np.testing.assert_allclose(st[:, 2], np.sign(phi) * s / R, atol=1e-6)
+
+
+@pytest.mark.parametrize("L", [0.2, 1.0, 4.0])
+def test_g1_clothoid_known_answer_straight_line(L):
+    kdl, st, ok = co.clothoid((L, 0.0, 0.0), n_newton=10, m=50)
+    assert ok
+    np.testing.assert_allclose(kdl, [0.0, 0.0, L], atol=1e-12)
+    np.testing.assert_allclose(st[:, 0], np.linspace(0, L, 50), atol=1e-12)
+    assert np.abs(st[:, 1:]).max() < 1e-12
+
+
+def test_g1_clothoid_mirror_symmetry():
+    """Reflecting the goal about the x axis reflects the clothoid (y, theta, kappa change sign)."""
+    for g in [(1.0, 1.0, 0.0), (2.5, -0.8, -0.4), (3.0, 0.5, -0.3), (0.5, -0.6, -1.2)]:
+        k1, s1, ok1 = co.clothoid(g, n_newton=10, m=64)
+        k2, s2, ok2 = co.clothoid((g[0], -g[1], -g[2]), n_newton=10, m=64)
+        assert ok1 and ok2
+        np.testing.assert_allclose(k2, [-k1[0], -k1[1], k1[2]], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(s2, s1 * np.array([1.0, -1.0, -1.0, -1.0]), atol=1e-9)
+
+
+@pytest.mark.parametrize("R", [1.5, 4.0, 30.0])
+@pytest.mark.parametrize("phi", [0.1, 0.6, 1.2, -0.5])
+def test_spiral_known_answers_circular_arcs(R, phi):
+    """Analytic known answers of the cubic-spiral boundary-value problem: with the
+    end curvatures pinned to 1/R the spiral joining the two poses of a circular arc is the arc --
+    every knot equals 1/R and s_f = R |phi|."""
+    k = np.sign(phi) / R
+    goal = (R * np.sin(abs(phi)), np.sign(phi) * R * (1 - np.cos(phi)), phi)
+    q, st = co.spiral(goal, p0=k, p3=k, n_newton=12, seed=[0.0, 0.0, np.hypot(goal[0], goal[1])], m=100)
+    # tolerances: composite Simpson on Q = 32 intervals inside the Newton residual (DESIGN 3)
+    np.testing.assert_allclose(q[:2], [k, k], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(q[2], R * abs(phi), rtol=1e-7)
+    s = np.linspace(0, R * abs(phi), 100)
+    np.testing.assert_allclose(st[:, 0], R * np.sin(s / R), atol=1e-6 * max(R, 1))
+    np.testing.assert_allclose(st[:, 1], np.sign(phi) * R * (1 - np.cos(s / R)), atol=1e-6 * max(R, 1))
+    np.testing.assert_allclose(st[:, 3], k, rtol=1e-5)
+
+
+def test_spiral_known_answer_straight_line_and_mirror():
+    q, st = co.spiral((2.0, 0.0, 0.0), n_newton=8, m=40)
+    np.testing.assert_allclose(q, [0.0, 0.0, 2.0], atol=1e-12)
+    np.testing.assert_allclose(st[:, 0], np.linspace(0, 2.0, 40), atol=1e-12)
+    assert np.abs(st[:, 1:]).max() < 1e-12
+    for g in [(1.0, 0.2, 0.1), (2.5, -0.8, -0.4), (3.5, 1.2, 0.6)]:
+        q1, s1 = co.spiral(g, n_newton=12, m=64)
+        q2, s2 = co.spiral((g[0], -g[1], -g[2]), n_newton=12, m=64)
+        np.testing.assert_allclose(q2, [-q1[0], -q1[1], q1[2]], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(s2, s1 * np.array([1.0, -1.0, -1.0, -1.0]), atol=1e-9)
