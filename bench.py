@@ -351,14 +351,29 @@ def sharded_dense_query(track, grid, device, rank, world_size, dev):
     lo, hi = sharding.block(C, rank, world_size)
     poses, opp, n_opp = synth.scenario_batch(track, 16, 8, 1005)   # same on every rank
 
-    def run(n_rep, reduce_on_host):
+    start = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def run(n_rep, reduce_on_host, by_rows):
+        """Every rank starts query i at the same instant: rank 0 broadcasts a start time 2 ms
+        ahead on the host's monotonic clock (time.perf_counter is CLOCK_MONOTONIC, shared by the
+        processes of one node) and the ranks spin until it comes -- a barrier's exit skew
+        (~100 us between ranks) would otherwise be charged to the query.  Latency of a query =
+        the latest finish over the ranks minus that common start."""
         ts, tp, bests = [], [], []
         for i in range(3 + n_rep):
             s = i % 16
-            dist.barrier()
             torch.cuda.synchronize(dev)
-            t0 = time.perf_counter()
-            d = eng.plan(poses[s], opp[s], update_prev=False, detail=False, shard=(lo, hi))
+            dist.barrier()
+            if rank == 0:
+                start[0] = time.perf_counter() + 2e-3
+            dist.broadcast(start, 0)
+            t0 = float(start.item())
+            while time.perf_counter() < t0:
+                pass
+            if by_rows:
+                d = eng.plan(poses[s], opp[s], update_prev=False, detail=False, rows=(rank, world_size))
+            else:
+                d = eng.plan(poses[s], opp[s], update_prev=False, detail=False, shard=(lo, hi))
             t1 = time.perf_counter()
             best = (sharding.reduce_best(d.best_cost, d.best_idx) if reduce_on_host
                     else (float(d.best_cost), int(d.best_idx)))
@@ -371,18 +386,26 @@ def sharded_dense_query(track, grid, device, rank, world_size, dev):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.cpu().numpy(), np.array(tp), bests
 
-    ts_n, tp_n, best_n = run(32, True)        # (b) NCCL all-gather + host min
+    ts_n, tp_n, best_n = run(32, True, False)   # (b) contiguous blocks, NCCL all-gather + host min
+    _, tp_r, _ = run(32, True, True)            # local time of a row-interleaved shard
     eng.attach_peers()
-    ts_p, _, best_p = run(32, False)          # (a) peer memory, inside the select kernel
+    ts_c, _, best_c = run(32, False, False)     # peer memory, contiguous blocks
+    ts_p, _, best_p = run(32, False, True)      # (a) peer memory, row-interleaved shards
     eng.detach_peers()
     eng.close()
+    tl = torch.tensor([np.percentile(tp_n, 50), np.percentile(tp_r, 50)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tl, op=dist.ReduceOp.MAX)   # the slowest rank's local plan
+    tl = tl.cpu().numpy()
     return {"c5_sharded_plan_p50_us": 1e6 * float(np.percentile(ts_p, 50)),
             "c5_sharded_plan_p99_us": 1e6 * float(np.percentile(ts_p, 99)),
             "c5_sharded_candidates_per_s": C / float(np.percentile(ts_p, 50)),
-            "c5_sharded_exchange": "peer memory (CUDA IPC over NVLink, system-scope atomicMin in select_kernel)",
-            "c5_sharded_nccl_gather_p50_us": 1e6 * float(np.percentile(ts_n, 50)),
-            "c5_sharded_local_plan_p50_us": 1e6 * float(np.percentile(tp_n, 50)),
-            "c5_sharded_paths_agree": best_n == best_p,
+            "c5_sharded_exchange": "row-interleaved shards (f1l_plan_rows); argmin over peer memory (CUDA IPC "
+                                   "over NVLink, system-scope atomicMin in select_kernel)",
+            "c5_sharded_blocks_peer_p50_us": 1e6 * float(np.percentile(ts_c, 50)),
+            "c5_sharded_blocks_nccl_gather_p50_us": 1e6 * float(np.percentile(ts_n, 50)),
+            "c5_sharded_local_plan_p50_us": {"rows_slowest_rank": 1e6 * float(tl[1]),
+                                             "blocks_slowest_rank": 1e6 * float(tl[0])},
+            "c5_sharded_paths_agree": best_n == best_p and best_c == best_p,
             "c5_candidates_per_rank": hi - lo, "c5_last_best": list(best_p[-1])}
 
 
@@ -542,7 +565,10 @@ def run_ours(args):
 
     sharded = None
     if world_size > 1 and not args.no_extras:
-        sharded = sharded_dense_query(track, grid, local, rank, world_size, dev)
+        try:
+            sharded = sharded_dense_query(track, grid, local, rank, world_size, dev)
+        except Exception as e:   # the headline line must not depend on the side measurement
+            sharded = {"c5_sharded_error": "%s: %s" % (type(e).__name__, e)}
 
     if rank != 0:
         if world_size > 1:

@@ -41,7 +41,7 @@ struct f1l_ctx {
     int use_graph = 1;
     unsigned long long epoch = 0;   // bumped by every upload / config change
     cudaGraphExec_t gexec = nullptr;
-    unsigned long long gkey[3] = {~0ull, ~0ull, ~0ull};
+    unsigned long long gkey[4] = {~0ull, ~0ull, ~0ull, ~0ull};
     int timed = 0;  // events of the last pipeline launch are valid
 #define F1L_EV_SLOTS 64
     cudaEvent_t ev[4 * F1L_EV_SLOTS] = {nullptr};
@@ -376,6 +376,7 @@ struct BatchOut {
     float4* states = nullptr;
     float2* headings = nullptr;
     float* prev_out = nullptr;
+    int row0 = 0, row_step = 1;        // row-interleaved shard (c_begin / c_end are shard-local)
     const XchgView* xc = nullptr;      // sharded single query: exchange the argmin with the peers
     int32_t* xchg_status = nullptr;
 };
@@ -462,6 +463,8 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     ea.C = C;
     ea.c_begin = c_begin;
     ea.c_end = c_end;
+    ea.row0 = o.row0;
+    ea.row_step = o.row_step > 1 ? o.row_step : 1;
     ea.chunk = cp.chunk;
     ea.ctas_per_scn = cp.ctas_per_scn;
     // four candidates per warp at a time (shared Newton) when every warp has at least four
@@ -504,7 +507,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     se.inv_nW = 1.0f / (float)(h->nW > 0 ? h->nW : 1);
     se.goals = goals;
     se.C = C;
-    se.c_begin = c_begin;
+    se.c_begin = o.row_step > 1 ? c_begin + o.row0 * h->nW : c_begin;   // first evaluated candidate
     se.best = best;
     se.best_idx = o.best_idx;
     se.best_cost = o.best_cost;
@@ -964,7 +967,8 @@ int f1l_clear_prev_path(f1l_handle h) {
 // ---- single query -------------------------------------------------------------------------
 static int plan_internal(f1l_handle h, const double pose[4], const double* opp, int n_opp,
                          const double* goals, int n_goals, int c_begin, int c_end,
-                         int update_prev, f1l_plan_result* out, bool exchange = false) {
+                         int update_prev, f1l_plan_result* out, bool exchange = false,
+                         int row0 = 0, int row_step = 1) {
     if (!h || !pose || !out) return F1L_ERR_INVALID_ARG;
     if (n_opp < 0 || n_opp > F1L_MAX_OPP || (n_opp > 0 && !opp)) return F1L_ERR_INVALID_ARG;
     if (h->n < 2) return F1L_ERR_NO_TRACK;
@@ -1039,12 +1043,21 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     o.states = out->states ? (float4*)h->q_states.p : nullptr;
     o.headings = out->headings ? (float2*)h->q_headings.p : nullptr;
     o.prev_out = update_prev ? (float*)h->prev.p : nullptr;
+    if (row_step > 1) {   // row-interleaved shard: rows row0, row0 + row_step, ... of the goal grid
+        if (goals || row0 < 0 || row0 >= row_step) return F1L_ERR_INVALID_ARG;
+        const int n_rows = row0 < h->nL ? (h->nL - row0 + row_step - 1) / row_step : 0;
+        if (n_rows <= 0) return F1L_ERR_INVALID_ARG;
+        o.row0 = row0;
+        o.row_step = row_step;
+        c_begin = 0;
+        c_end = n_rows * h->nW;
+    }
     exchange = exchange && h->xview.world > 1;
     if (exchange) {   // the ranks' minima meet inside select_kernel (peer memory over NVLink)
         o.xc = &h->xview;
         o.xchg_status = (int32_t*)(dres + offsetof(QHeader, pad));
     }
-    const bool sharded = exchange || c_begin != 0 || (c_end > 0 && c_end < C);
+    const bool sharded = exchange || row_step > 1 || c_begin != 0 || (c_end > 0 && c_end < C);
     QHeader* hd = (QHeader*)h->h_out;
     float* htraj = (float*)((char*)h->h_out + sizeof(QHeader));
     const QInput* din = (const QInput*)h->q_in.p;
@@ -1079,7 +1092,9 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
                                         (exchange ? 512u : 0u);
         // a candidate shard is a constant of the captured kernels too
         const unsigned long long shard_key = ((unsigned long long)(unsigned)c_begin << 32) | (unsigned)c_end;
-        if (!h->gexec || h->gkey[0] != h->epoch || h->gkey[1] != mask || h->gkey[2] != shard_key) {
+        const unsigned long long rows_key = ((unsigned long long)(unsigned)row_step << 32) | (unsigned)row0;
+        if (!h->gexec || h->gkey[0] != h->epoch || h->gkey[1] != mask || h->gkey[2] != shard_key ||
+            h->gkey[3] != rows_key) {
             if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
             const int64_t launches0 = h->launches;
             cudaGraph_t graph = nullptr;
@@ -1095,6 +1110,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
             h->gkey[0] = h->epoch;
             h->gkey[1] = mask;
             h->gkey[2] = shard_key;
+            h->gkey[3] = rows_key;
         }
         CK(cudaGraphLaunch(h->gexec, st));
         h->launches += 3;
@@ -1140,6 +1156,13 @@ int f1l_plan_shard(f1l_handle h, const double pose[4], const double* opp, int n_
                    int c_end, f1l_plan_result* out) {
     // with peers attached (f1l_xchg_attach) every rank returns the GLOBAL winner
     return plan_internal(h, pose, opp, n_opp, nullptr, 0, c_begin, c_end, 0, out, true);
+}
+
+int f1l_plan_rows(f1l_handle h, const double pose[4], const double* opp, int n_opp, int row_begin,
+                  int row_step, f1l_plan_result* out) {
+    if (row_step < 1) return F1L_ERR_INVALID_ARG;
+    if (row_step == 1) return plan_internal(h, pose, opp, n_opp, nullptr, 0, 0, 0, 0, out, true);
+    return plan_internal(h, pose, opp, n_opp, nullptr, 0, 0, 0, 0, out, true, row_begin, row_step);
 }
 
 // ---- peer-memory exchange (CUDA IPC over NVLink P2P) -----------------------------------------

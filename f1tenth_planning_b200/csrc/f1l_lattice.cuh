@@ -339,7 +339,9 @@ struct EvalArgs {
     const float4* goals;     // explicit goals [S,C] (gx, gy, gth, p3) or null
     const float* prev_theta; // [M] or null
     int C;                   // candidates per scenario
-    int c_begin, c_end;      // evaluated range
+    int c_begin, c_end;      // evaluated range (of shard-local indices when row_step > 1)
+    int row0, row_step;      // row-interleaved shard: local index v -> lookahead row
+                             // row0 + (v / nW) * row_step, same width column (row_step 1: c = v)
     int ctas_per_scn;        // CTAs per scenario
     int chunk;               // candidates per CTA
     int item;                // candidates a warp takes at a time: 4 (their Newton solves share the
@@ -435,6 +437,17 @@ struct SelectArgs {
     float4* best_traj;      // [S,M]
     float* prev_theta_out;  // [M] (single query, update_prev)
 };
+
+// Candidate index of shard-local index v.  A row-interleaved shard (rank r of W takes lookahead
+// rows r, r + W, ...: near and far goals cost differently, contiguous blocks would leave the ranks
+// unbalanced) walks local indices v = 0 .. n_rows * nW - 1; the candidate keeps its global index
+// c = row * nW + column, so costs / flags land where the unsharded query puts them and the
+// argmin key orders like np.argmin on the whole cost vector.
+__device__ __forceinline__ int shard_candidate(int v, int nW, float inv_nW, int row0, int row_step) {
+    if (row_step == 1) return v;   // uniform
+    const int rv = __float2int_rd(((float)v + 0.5f) * inv_nW);
+    return v + (row0 + rv * (row_step - 1)) * nW;
+}
 
 // goal of candidate c of scenario s: centre + width * normal, or the explicit goal
 __device__ __forceinline__ void candidate_goal(const Centre* __restrict__ centres,
@@ -937,7 +950,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
           const bool active = cg < ce;
           float ggx, ggy, ggth, gp3, gv_ref;
           bool ghave;
-          candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.inv_nW, a.C, s, active ? cg : c0,
+          candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.inv_nW, a.C, s,
+                         shard_candidate(active ? cg : c0, a.nW, a.inv_nW, a.row0, a.row_step),
                          a.ep.use_goal_kappa != 0, ggx, ggy, ggth, gp3, ghave, gv_ref);
           SpiralF gsp;
           const int g_pass = generate_cubic_g8(gsp, a.lut, a.ep, ggx, ggy, ggth, gp3, lane, active);
@@ -950,14 +964,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
           __syncwarp();
       }
       const int c_last = min(c0 + item, ce);
-      for (int c = c0; c < c_last; ++c) {
+      for (int v = c0; v < c_last; ++v) {
+        const int c = shard_candidate(v, a.nW, a.inv_nW, a.row0, a.row_step);
         // ---- goal, seed, Newton ----
         float gx, gy, gth, p3, v_ref;
         bool have_centre;
         SpiralF sp;
         int n_pass;
         if (item == 4) {   // the solution of candidate c, found by its 8-lane group
-            const float4 G = isol[2 * (c - c0)], Q = isol[2 * (c - c0) + 1];
+            const float4 G = isol[2 * (v - c0)], Q = isol[2 * (v - c0) + 1];
             gx = G.x; gy = G.y; gth = G.z; p3 = G.w;
             v_ref = 0.0f;
             const int hp = __float_as_int(Q.w);

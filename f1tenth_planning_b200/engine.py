@@ -198,15 +198,20 @@ class Engine:
         return self._n_samples
 
     def plan(self, pose, opponent_poses=None, update_prev=True, detail=True, want_states=False,
-             shard=None, want_headings=False):
-        """One query.  pose = (x, y, theta, velocity).  shard = (c_begin, c_end) evaluates a
-        candidate range only (dense-sweep sharding across GPUs)."""
+             shard=None, want_headings=False, rows=None):
+        """One query.  pose = (x, y, theta, velocity).  Dense-sweep sharding across GPUs:
+        shard = (c_begin, c_end) evaluates a candidate range only, rows = (row_begin, row_step)
+        the lookahead rows row_begin, row_begin + row_step, ... (balanced across ranks).  With
+        attach_peers() both are collective and return the global winner on every rank."""
         pose = _f64(pose).ravel()
         if pose.size != 4:
             raise ValueError("pose must be (x, y, theta, velocity)")
         opp, k = self._opp(opponent_poses)
         res, bufs = self._result(self.n_candidates, detail, want_states, want_headings)
-        if shard is None:
+        if rows is not None:
+            code = self._L.f1l_plan_rows(self._h, pose.ctypes.data, opp.ctypes.data if k else None,
+                                         k, int(rows[0]), int(rows[1]), C.byref(res))
+        elif shard is None:
             code = self._L.f1l_plan(self._h, pose.ctypes.data, opp.ctypes.data if k else None, k,
                                     int(bool(update_prev)), C.byref(res))
         else:

@@ -173,13 +173,21 @@ int f1l_plan(f1l_handle h, const double pose[4], const double* opp, int n_opp,
 int f1l_plan_shard(f1l_handle h, const double pose[4], const double* opp, int n_opp,
                    int c_begin, int c_end, f1l_plan_result* out);
 
+/* Row-interleaved shard: only the lookahead rows row_begin, row_begin + row_step, ... of the goal
+ * grid are evaluated (all widths of each).  Near and far goals cost differently (short spirals
+ * fail validation early, long ones meet more opponents and walls), so rank r of W taking rows
+ * r, r + W, ... balances the ranks where contiguous blocks do not.  Indices stay global; the
+ * peer exchange applies as for f1l_plan_shard.  0 <= row_begin < row_step. */
+int f1l_plan_rows(f1l_handle h, const double pose[4], const double* opp, int n_opp,
+                  int row_begin, int row_step, f1l_plan_result* out);
+
 /*
  * Peer-memory exchange for f1l_plan_shard ("final step = gather of G (cost, idx)
  * pairs"; replaces an 8-byte NCCL all-gather plus host min).  Each rank (one process per GPU, or
  * several handles of one node) exports a 128-byte block of its HBM as a CUDA IPC handle
  * (f1l_xchg_export, 64 bytes), the caller gathers the `world` handles by any means (the Python
  * layer uses torch.distributed) and attaches them in rank order (f1l_xchg_attach: maps the peers'
- * blocks over NVLink P2P).  From then on f1l_plan_shard is collective: every rank calls it for
+ * blocks over NVLink P2P).  From then on f1l_plan_shard / f1l_plan_rows are collective: every rank calls it for
  * the same query with its own [c_begin, c_end), the select kernel pushes the rank's packed
  * (cost, index) minimum into every peer's block with system-scope atomics and waits for all
  * arrivals, and every rank returns the GLOBAL best_idx / best_cost / best_traj / steer / speed.

@@ -44,10 +44,13 @@ def main():
     eng.configure(kappa_max=0.0)
 
     eng.attach_peers()
-    for rep in range(3):
+    for rep in range(4):
         eng.set_graph(rep != 1)                                   # graph replay and plain launches
         for s in range(12):
-            d = eng.plan(poses[s], opp[s, :n_opp[s]], update_prev=False, detail=False, shard=(lo, hi))
+            if rep < 2:   # contiguous candidate blocks
+                d = eng.plan(poses[s], opp[s, :n_opp[s]], update_prev=False, detail=False, shard=(lo, hi))
+            else:         # row-interleaved shards
+                d = eng.plan(poses[s], opp[s, :n_opp[s]], update_prev=False, detail=False, rows=(rank, world))
             w = whole[s]
             assert d.best_idx == w.best_idx, (rank, rep, s, d.best_idx, w.best_idx)
             assert np.float32(d.best_cost) == np.float32(w.best_cost)

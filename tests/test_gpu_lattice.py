@@ -235,6 +235,51 @@ def test_g1_clothoid_generator(ellipse, corridor):
         assert H.close(stt, ref, scale=H.traj_scale(ref)).all()
 
 
+def test_row_interleaved_shards_match_unsharded(ellipse, corridor):
+    """f1l_plan_rows: rank r of W evaluates lookahead rows r, r + W, ...; the shards' costs and
+    flags are the unsharded ones at the same global indices (bit for bit), untouched candidates
+    stay +inf, and the shard winners reduce to the unsharded winner."""
+    la, wd = np.linspace(0.5, 3.6, 21), np.linspace(-1.1, 1.1, 9)     # 21 rows: ragged over W = 2, 4
+    eng, cfg, world = H.make_pair(ellipse, la, wd, grid=corridor, kappa_max=0.0)
+    nL, nW = len(la), len(wd)
+    for seed in (61, 62):
+        pose, opp = H.scenario(ellipse, seed, 5)
+        whole = eng.plan(pose, opp, update_prev=False)
+        for W in (2, 4, 21):
+            best = []
+            seen = np.zeros(nL * nW, bool)
+            for r in range(W):
+                d = eng.plan(pose, opp, update_prev=False, rows=(r, W))
+                mine = np.zeros((nL, nW), bool)
+                mine[r::W] = True
+                mine = mine.ravel()
+                assert np.array_equal(d.costs[mine], whole.costs[mine])
+                assert np.array_equal(d.flags[mine], whole.flags[mine])
+                assert np.isinf(d.costs[~mine]).all() and (d.flags[~mine] == 0).all()
+                assert mine[d.best_idx]
+                if np.isfinite(whole.costs[mine]).any():
+                    assert d.best_idx == int(np.argmin(np.where(mine, whole.costs, np.inf)))
+                else:   # all +inf: the first evaluated candidate
+                    assert d.best_idx == r * nW and d.no_feasible
+                best.append((float(d.best_cost), int(d.best_idx)))
+                seen |= mine
+            assert seen.all()
+            assert min(best)[1] == whole.best_idx
+    # a block and a row shard with the same (c_begin, c_end) must not share a captured graph
+    la2 = np.linspace(0.5, 3.6, 20)
+    eng.set_goal_grid(la2, wd)
+    whole = eng.plan(pose, opp, update_prev=False)
+    blk = eng.plan(pose, opp, update_prev=False, shard=(0, 10 * nW))
+    row = eng.plan(pose, opp, update_prev=False, rows=(0, 2))
+    mine = np.zeros((20, nW), bool)
+    mine[0::2] = True
+    assert np.array_equal(row.costs[mine.ravel()], whole.costs[mine.ravel()])
+    assert np.isinf(row.costs[~mine.ravel()]).all()
+    assert np.array_equal(blk.costs[:10 * nW], whole.costs[:10 * nW]) and np.isinf(blk.costs[10 * nW:]).all()
+    with pytest.raises(Exception):
+        eng.plan(pose, opp, update_prev=False, rows=(3, 2))       # row_begin >= row_step
+
+
 def test_generators_reproduce_analytic_known_answers(ellipse):
     """Known answers that need no oracle: the G1 clothoid joining the two poses of a circular arc
     is that arc (kappa = 1/R, no curvature rate, length R phi), and both generators return the
