@@ -464,10 +464,19 @@ def run_ours(args):
         eng.plan_batch_dev(tp, to, tn, best_idx=o_idx, best_cost=o_cost, best_traj=o_traj,
                            costs=o_costs, flags=o_flags, steer_speed=o_ss)
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    # one nvidia-smi process on rank 0 watches every GPU of the job (eight concurrent ones on an
+    # 8-GPU box took longer to start than the whole run and returned no rows)
+    sampler = ClockSampler(",".join(str(i) for i in range(world_size)) if world_size > 1 else local)
+    if rank == 0:
+        sampler.start()
+    n_warm, t_warm = 0, time.time()
+    # warm-up goes on (GPU under load) until the sampler has delivered its first row, 10 s at most
+    while n_warm < max(args.warmup, 3) or (rank == 0 and sampler.proc is not None and not sampler.rows
+                                           and time.time() - t_warm < 10.0):
         step()
+        n_warm += 1
+        if n_warm % 4 == 0:
+            torch.cuda.synchronize(dev)
     torch.cuda.synchronize(dev)
     eng.set_timing(True)
     if world_size > 1:
@@ -577,7 +586,7 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "warmup": max(args.warmup, 3), "warmup_steps_run": n_warm, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {
