@@ -65,6 +65,7 @@ class LatticePlanner():
         self._widths = synth.DEFAULT_WIDTHS.copy()           # :229
         self._grid_dirty = True
         self._map = None
+        self._shard = None         # (rank, world) after shard_across()
         self.last = None
 
     # -- reference plug-in API ------------------------------------------------------------------
@@ -169,6 +170,24 @@ class LatticePlanner():
             self._grid_dirty = False
         return self._engine
 
+    # -- one dense query across the GPUs of a node --------------------------------------------------
+    def shard_across(self, group=None):
+        """Collective over a torch.distributed group (one process per GPU): from now on plan() /
+        plan_detailed() evaluate only this rank's lookahead rows (rank, rank + world, ...) and the
+        ranks' minima meet inside the select kernel over NVLink peer memory, so every rank returns
+        the global winner.  Every rank must then call plan() with the same arguments.  Queries
+        that run user plug-ins (sample / cost / selection functions) stay unsharded; the
+        previous-path memory of the similarity cost is not updated by sharded queries."""
+        import torch.distributed as dist
+        eng = self._sync()
+        eng.attach_peers(group)
+        self._shard = (dist.get_rank(group), dist.get_world_size(group))
+
+    def unshard(self, group=None):
+        if self._shard is not None and self._engine is not None:
+            self._engine.detach_peers(group)
+        self._shard = None
+
     # -- planning -------------------------------------------------------------------------------
     def plan_detailed(self, pose_x, pose_y, pose_theta, velocity, waypoints=None,
                       opponent_poses=None, want_states=False):
@@ -184,6 +203,8 @@ class LatticePlanner():
             goal_grid = np.asarray(self.sample(pose_x, pose_y, pose_theta, velocity, self.waypoints),
                                    dtype=np.float64).reshape(-1, 3)
             d = eng.plan_goals(pose, goal_grid, opponent_poses, want_states=need_states)
+        elif self._shard is not None and not need_states:
+            d = eng.plan(pose, opponent_poses, rows=self._shard)
         else:
             d = eng.plan(pose, opponent_poses, want_states=need_states)
         if custom_cost or custom_select:

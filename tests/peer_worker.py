@@ -67,6 +67,28 @@ def main():
     d = eng.plan(poses[1], opp[1, :n_opp[1]], update_prev=False, detail=False, shard=(lo, hi))
     assert lo <= d.best_idx < hi
     eng.close()
+
+    # the reference-facing planner: shard_across() makes plan() collective
+    from f1tenth_planning_b200 import LatticePlanner
+    pl = LatticePlanner(waypoints=track, device=dev)
+    pl.set_goal_grid(np.linspace(0.5, 3.5, 24), np.linspace(-1.2, 1.2, 21))
+    pl.set_map(*grid)
+    ref = [pl.plan_detailed(*poses[s], opponent_poses=opp[s, :n_opp[s]]) for s in range(3)]
+    pl2 = LatticePlanner(waypoints=track, device=dev)
+    pl2.set_goal_grid(np.linspace(0.5, 3.5, 24), np.linspace(-1.2, 1.2, 21))
+    pl2.set_map(*grid)
+    pl2.shard_across()
+    for s in range(3):
+        steer, speed, traj = pl2.plan(*poses[s], opponent_poses=opp[s, :n_opp[s]])
+        # (the unsharded planner above updated its previous-path memory; compare first query only
+        #  for the cost, all queries for self-consistency across ranks through the index)
+        if s == 0:
+            assert pl2.last.best_idx == ref[0].best_idx and steer == ref[0].steer
+            assert np.array_equal(pl2.last.best_traj, ref[0].best_traj)
+        got = [None] * world
+        dist.all_gather_object(got, int(pl2.last.best_idx))
+        assert len(set(got)) == 1, got
+    pl2.unshard()
     dist.barrier()
     dist.destroy_process_group()
     print("peer worker %d/%d ok (device %d, candidates [%d, %d))" % (rank, world, dev, lo, hi))
