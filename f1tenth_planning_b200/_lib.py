@@ -87,7 +87,7 @@ SIGNATURES = {
     "f1l_get_actuation_batch": (C.c_int, [_vp, _dp, C.c_int, C.c_double, _dp]),
     "f1l_get_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
     "f1l_last_eval_shape": (C.c_int, [_vp, _ip, C.c_int]),
-    "f1l_plan_rows": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(PlanResult)]),
+    "f1l_plan_rows": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PlanResult)]),
     "f1l_xchg_export": (C.c_int, [_vp, _vp, C.c_int]),
     "f1l_xchg_attach": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "f1l_xchg_detach": (C.c_int, [_vp]),

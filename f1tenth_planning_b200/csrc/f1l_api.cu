@@ -87,6 +87,7 @@ struct f1l_ctx {
     DevBuf m_in, m_in2, m_o0, m_o1, m_o2, m_o3, m_o4, m_o5, pp_key;
     // peer-memory exchange of candidate-sharded queries (f1l_xchg_*): the local block, the peers'
     // blocks as mapped by cudaIpcOpenMemHandle (own rank: the local pointer)
+    int pp_per_sm = 0;   // resident pp_scan_kernel CTAs per SM (pp_slots)
     DevBuf xchg;
     XchgView xview = {0, 0, {nullptr}};
     // template instance / CTA plan of the last eval_kernel launch (f1l_last_eval_shape)
@@ -331,19 +332,25 @@ CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count, bool cubic) {
     return best;
 }
 
-// K1 = key preset + scan + finish on one stream.  key: 8 bytes of scratch per pose
+// resident one-warp scan CTAs on the handle's device, from the occupancy calculator (once)
+int pp_slots(f1l_handle h) {
+    if (h->pp_per_sm <= 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pp_scan_kernel, 32, 0) != cudaSuccess || n <= 0)
+            n = PP_TASK_MINB;
+        h->pp_per_sm = n;
+    }
+    return h->pp_per_sm * h->sm_count;
+}
+
+// K1 = key preset + scan + finish on one stream.  key: 8 bytes of scratch per pose; slots: one-warp
+// scan CTAs resident on the device (pp_slots)
 void launch_pp(const TrackView& tv, cudaStream_t stream, const double* poses, int pose_stride,
                int n_poses, double L, double wb, double max_reacquire, int front_axle, double k_path,
-               unsigned long long* key, int sm_count, const PPOut& o) {
-    static int per_sm = 0;   // resident one-warp scan CTAs per SM, from the occupancy calculator
-    if (per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pp_scan_kernel, 32, 0) !=
-                cudaSuccess || per_sm <= 0)
-            per_sm = PP_TASK_MINB;
-    }
+               unsigned long long* key, int slots, const PPOut& o) {
     const int n_groups = (n_poses + PP_CTA_POSES - 1) / PP_CTA_POSES;
     const int nblk = (tv.n - 1 + 31) >> 5;
-    const int n_parts = pp_task_parts(n_groups, nblk, per_sm * sm_count);
+    const int n_parts = pp_task_parts(n_groups, nblk, slots);
     cudaMemsetAsync(key, 0xff, (size_t)n_poses * 8, stream);
     pp_scan_kernel<<<n_groups * n_parts, 32, 0, stream>>>(tv, poses, pose_stride, n_poses,
                                                          front_axle, wb, n_parts, key);
@@ -432,7 +439,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
         po.actuation = nullptr;
         po.status = nullptr;
         po.front = nullptr;
-        launch_pp(sa.tr, stream, poses, 4, S, -1.0, 0.33, 0.0, 0, 0.0, best, h->sm_count, po);   // `best` doubles as K1's key scratch: the sampler resets it
+        launch_pp(sa.tr, stream, poses, 4, S, -1.0, 0.33, 0.0, 0, 0.0, best, pp_slots(h), po);   // `best` doubles as K1's key scratch: the sampler resets it
         sample_warp_kernel<<<(S + SAMPLE_WARPS - 1) / SAMPLE_WARPS, SAMPLE_WARPS * 32, 0, stream>>>(
             sa, near_i, near4, S);
         h->launches += 2;
@@ -1159,10 +1166,10 @@ int f1l_plan_shard(f1l_handle h, const double pose[4], const double* opp, int n_
 }
 
 int f1l_plan_rows(f1l_handle h, const double pose[4], const double* opp, int n_opp, int row_begin,
-                  int row_step, f1l_plan_result* out) {
+                  int row_step, int update_prev, f1l_plan_result* out) {
     if (row_step < 1) return F1L_ERR_INVALID_ARG;
-    if (row_step == 1) return plan_internal(h, pose, opp, n_opp, nullptr, 0, 0, 0, 0, out, true);
-    return plan_internal(h, pose, opp, n_opp, nullptr, 0, 0, 0, 0, out, true, row_begin, row_step);
+    if (row_step == 1) return plan_internal(h, pose, opp, n_opp, nullptr, 0, 0, 0, update_prev, out, true);
+    return plan_internal(h, pose, opp, n_opp, nullptr, 0, 0, 0, update_prev, out, true, row_begin, row_step);
 }
 
 // ---- peer-memory exchange (CUDA IPC over NVLink P2P) -----------------------------------------
@@ -1370,7 +1377,7 @@ int f1l_pure_pursuit_batch_dev(f1l_handle h, const double* poses_dev, int n_pose
     o.front = nullptr;
     ENS(h->pp_key, (size_t)n_poses * 8);   // scan scratch (one call in flight per handle)
     launch_pp(track_view(h), (cudaStream_t)stream, poses_dev, 3, n_poses, L, h->cfg.wheelbase,
-              h->cfg.max_reacquire, 0, 0.0, (unsigned long long*)h->pp_key.p, h->sm_count, o);
+              h->cfg.max_reacquire, 0, 0.0, (unsigned long long*)h->pp_key.p, pp_slots(h), o);
     h->launches += 2;
     CK(cudaGetLastError());
     return F1L_OK;
@@ -1422,7 +1429,7 @@ int f1l_front_axle_batch_dev(f1l_handle h, const double* poses_dev, int n_poses,
     o.front = front_dev;
     ENS(h->pp_key, (size_t)n_poses * 8);
     launch_pp(track_view(h), (cudaStream_t)stream, poses_dev, 4, n_poses, 0.0, wheelbase, 0.0, 1,
-              k_path, (unsigned long long*)h->pp_key.p, h->sm_count, o);
+              k_path, (unsigned long long*)h->pp_key.p, pp_slots(h), o);
     h->launches += 2;
     CK(cudaGetLastError());
     return F1L_OK;

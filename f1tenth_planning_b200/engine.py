@@ -202,7 +202,8 @@ class Engine:
         """One query.  pose = (x, y, theta, velocity).  Dense-sweep sharding across GPUs:
         shard = (c_begin, c_end) evaluates a candidate range only, rows = (row_begin, row_step)
         the lookahead rows row_begin, row_begin + row_step, ... (balanced across ranks).  With
-        attach_peers() both are collective and return the global winner on every rank."""
+        attach_peers() both are collective and return the global winner on every rank (and
+        rows= then honours update_prev: every rank stores the same previous path)."""
         pose = _f64(pose).ravel()
         if pose.size != 4:
             raise ValueError("pose must be (x, y, theta, velocity)")
@@ -210,7 +211,8 @@ class Engine:
         res, bufs = self._result(self.n_candidates, detail, want_states, want_headings)
         if rows is not None:
             code = self._L.f1l_plan_rows(self._h, pose.ctypes.data, opp.ctypes.data if k else None,
-                                         k, int(rows[0]), int(rows[1]), C.byref(res))
+                                         k, int(rows[0]), int(rows[1]),
+                                         int(bool(update_prev) and self.peer_world > 1), C.byref(res))
         elif shard is None:
             code = self._L.f1l_plan(self._h, pose.ctypes.data, opp.ctypes.data if k else None, k,
                                     int(bool(update_prev)), C.byref(res))

@@ -176,8 +176,7 @@ class LatticePlanner():
         plan_detailed() evaluate only this rank's lookahead rows (rank, rank + world, ...) and the
         ranks' minima meet inside the select kernel over NVLink peer memory, so every rank returns
         the global winner.  Every rank must then call plan() with the same arguments.  Queries
-        that run user plug-ins (sample / cost / selection functions) stay unsharded; the
-        previous-path memory of the similarity cost is not updated by sharded queries."""
+        that run user plug-ins (sample / cost / selection functions) stay unsharded."""
         import torch.distributed as dist
         eng = self._sync()
         eng.attach_peers(group)

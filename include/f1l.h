@@ -177,9 +177,11 @@ int f1l_plan_shard(f1l_handle h, const double pose[4], const double* opp, int n_
  * grid are evaluated (all widths of each).  Near and far goals cost differently (short spirals
  * fail validation early, long ones meet more opponents and walls), so rank r of W taking rows
  * r, r + W, ... balances the ranks where contiguous blocks do not.  Indices stay global; the
- * peer exchange applies as for f1l_plan_shard.  0 <= row_begin < row_step. */
+ * peer exchange applies as for f1l_plan_shard.  0 <= row_begin < row_step.  update_prev != 0
+ * stores the winner's theta column as the next call's prev_path like f1l_plan -- the winner of
+ * this call, i.e. the global one only with peers attached (every rank then stores the same). */
 int f1l_plan_rows(f1l_handle h, const double pose[4], const double* opp, int n_opp,
-                  int row_begin, int row_step, f1l_plan_result* out);
+                  int row_begin, int row_step, int update_prev, f1l_plan_result* out);
 
 /*
  * Peer-memory exchange for f1l_plan_shard ("final step = gather of G (cost, idx)
