@@ -150,9 +150,10 @@ def test_stanley_front_axle_matches_reference(golden_spielberg):
 @pytest.mark.parametrize("n_wp", [2, 3, 9, 32, 33, 34, 65, 255, 257, 1025])
 @pytest.mark.parametrize("n_poses", [1, 31, 129, 300])
 def test_scan_shapes_small_tracks_and_ragged_batches(n_wp, n_poses):
-    """K1's scan splits the track's 32-segment blocks over the 8 warps of a CTA and packs four
-    poses per lane: tracks with fewer blocks than warps, partial last blocks and batches that are
-    not a multiple of 128 poses must give the oracle's answer."""
+    """K1's scan splits the track's 32-segment blocks over 6..24 one-warp tasks per group of 128
+    poses and packs four poses per lane: tracks with fewer blocks than parts, partial last blocks
+    and batches that are not a multiple of 128 poses (or of the finish kernel's 32-pose warps) must
+    give the oracle's answer."""
     from f1tenth_planning_b200.engine import Engine
     rng = np.random.default_rng(n_wp * 1000 + n_poses)
     phi = np.sort(rng.uniform(0.0, 1.5 * np.pi, n_wp))     # open arc, irregular spacing
