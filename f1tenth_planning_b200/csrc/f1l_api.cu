@@ -1073,8 +1073,9 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     // select runs (stream order), so one buffer suffices.
     auto enqueue = [&](bool time_it) -> int {
         CK(cudaMemcpyAsync(h->q_in.p, hin, sizeof(QInput), cudaMemcpyHostToDevice, st));
-        if (sharded) {
-            // sharded evaluation: untouched candidates keep +inf / zero flags
+        if (sharded && want_detail) {
+            // sharded evaluation: untouched candidates keep +inf / zero flags (only when the
+            // per-candidate arrays travel back at all)
             fill_f32_kernel<<<(C + 255) / 256, 256, 0, st>>>(o.costs, (size_t)C, INFINITY);
             h->launches += 1;
             if (o.flags) CK(cudaMemsetAsync(o.flags, 0, (size_t)C, st));
