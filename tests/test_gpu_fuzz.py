@@ -59,3 +59,30 @@ def test_random_configuration(seed):
         d = eng.plan(poses[0], o_in, update_prev=False, want_states=True)
         o = co.plan(ocfg, world, poses[0], o_in, want_states=True)
         H.compare_plan(d, o, ocfg)
+        # the same query cut into W row-interleaved shards (f1l_plan_rows) and into W contiguous
+        # blocks (f1l_plan_shard): per-candidate results at the same global indices, bit for bit
+        W = int(rng.integers(2, 5))
+        nL, nW = len(la), len(wd)
+        for mode in ("rows", "blocks"):
+            seen = np.zeros(nL * nW, bool)
+            best = []
+            for r in range(min(W, nL)):
+                if mode == "rows":
+                    p = eng.plan(poses[0], o_in, update_prev=False, rows=(r, min(W, nL)))
+                    mine = np.zeros((nL, nW), bool)
+                    mine[r::min(W, nL)] = True
+                    mine = mine.ravel()
+                else:
+                    from f1tenth_planning_b200 import sharding
+                    lo, hi = sharding.block(nL * nW, r, min(W, nL))
+                    p = eng.plan(poses[0], o_in, update_prev=False, shard=(lo, hi))
+                    mine = np.zeros(nL * nW, bool)
+                    mine[lo:hi] = True
+                assert np.array_equal(p.costs[mine], d.costs[mine]), (mode, r)
+                assert np.array_equal(p.flags[mine], d.flags[mine]), (mode, r)
+                assert np.isinf(p.costs[~mine]).all()
+                best.append((float(p.best_cost), int(p.best_idx)))
+                seen |= mine
+            assert seen.all()
+            if np.isfinite(d.costs).any():
+                assert min(best)[1] == d.best_idx, (mode, best, d.best_idx)
