@@ -185,15 +185,18 @@ int f1l_plan_rows(f1l_handle h, const double pose[4], const double* opp, int n_o
 
 /*
  * Peer-memory exchange for f1l_plan_shard ("final step = gather of G (cost, idx)
- * pairs"; replaces an 8-byte NCCL all-gather plus host min).  Each rank (one process per GPU, or
- * several handles of one node) exports a 128-byte block of its HBM as a CUDA IPC handle
+ * pairs"; replaces an 8-byte NCCL all-gather plus host min).  Each rank (one PROCESS per rank --
+ * CUDA IPC handles cannot be opened by the process that exported them; ranks may share a GPU)
+ * exports a 128-byte block of its HBM as a CUDA IPC handle
  * (f1l_xchg_export, 64 bytes), the caller gathers the `world` handles by any means (the Python
  * layer uses torch.distributed) and attaches them in rank order (f1l_xchg_attach: maps the peers'
  * blocks over NVLink P2P).  From then on f1l_plan_shard / f1l_plan_rows are collective: every rank calls it for
  * the same query with its own [c_begin, c_end), the select kernel pushes the rank's packed
  * (cost, index) minimum into every peer's block with system-scope atomics and waits for all
  * arrivals, and every rank returns the GLOBAL best_idx / best_cost / best_traj / steer / speed.
- * A peer that does not arrive within ~2 s yields F1L_ERR_PEER_TIMEOUT (the GPU never hangs).
+ * A peer that does not arrive within ~2 s yields F1L_ERR_PEER_TIMEOUT (the GPU never hangs); the
+ * condition is sticky -- the ranks' call numbers no longer agree -- until every rank has detached,
+ * exported and attached again.
  * All ranks must have attached before the first collective call and must stop calling before
  * any of them detaches or is destroyed (barrier on the caller's side).  world <= 16.
  */
