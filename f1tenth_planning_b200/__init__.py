@@ -14,6 +14,7 @@ _LAZY = {
     "sample_lookahead_square": ("lattice_planner", "sample_lookahead_square"),
     "PurePursuitPlanner": ("pure_pursuit", "PurePursuitPlanner"),
     "StanleyPlanner": ("stanley", "StanleyPlanner"),
+    "LQRPlanner": ("lqr", "LQRPlanner"),
     "Engine": ("engine", "Engine"),
     "F1LError": ("_lib", "F1LError"),
     "nearest_point": ("utils", "nearest_point"),

@@ -172,3 +172,26 @@ def test_scan_shapes_small_tracks_and_ragged_batches(n_wp, n_poses):
     np.testing.assert_allclose(r.nearest[same], o["nearest"][same], rtol=1e-9, atol=1e-9)
     np.testing.assert_array_equal(r.status[same], o["status"][same])
     np.testing.assert_allclose(r.actuation[same], o["actuation"][same], rtol=1e-9, atol=1e-9)
+
+
+def test_lqr_control_points_match_reference(golden_spielberg):
+    """LQRPlanner.calc_control_points (lqr.py:60-102) on K1's front-axle mode vs the golden vectors
+    minted from the reference controllers (the same five quantities Stanley's step shares)."""
+    import os
+    from f1tenth_planning_b200 import LQRPlanner
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "stanley.npz"))
+    wp = golden_spielberg["waypoints"]
+    pl = LQRPlanner(waypoints=wp)
+    cp, idx = pl.calc_control_points_batch(g["states"])
+    same = idx == g["target_index"]
+    assert (~same).mean() < 0.02
+    np.testing.assert_allclose(cp[same], g["front"][same][:, :5], rtol=1e-9, atol=1e-9)
+    one = pl.calc_control_points(g["states"][0], wp)
+    np.testing.assert_allclose(one, g["front"][0, :5], rtol=1e-9, atol=1e-9)
+    assert pl.vehicle_control_theta_e == one[0] and pl.vehicle_control_e_cog == one[1]
+    with pytest.raises(NotImplementedError):
+        pl.plan(0.0, 0.0, 0.0, 1.0)
+    with pytest.raises(ValueError):
+        LQRPlanner().calc_control_points(np.zeros(4))
+    with pytest.raises(ValueError):
+        pl.calc_control_points(np.zeros(4), waypoints=np.zeros((5, 4)))

@@ -71,3 +71,14 @@ def test_flop_model_matches_survey():
     assert abs(flops.candidate_flops(M=200, W=128, K=8) - 500e3) < 2e3    # C5: ~500 kFLOP
     assert abs(flops.pose_flops(2000) - 34e3) < 1e2                        # C2: ~34 kFLOP
     assert flops.candidate_flops(full=False) < 0.1 * flops.candidate_flops(full=True)
+
+
+def test_lqr_mirror_error_conventions():
+    """LQRPlanner keeps lqr.py's waypoint checks; the Riccati part is not silently emulated."""
+    from f1tenth_planning_b200 import LQRPlanner
+    with pytest.raises(ValueError):
+        LQRPlanner().calc_control_points(np.zeros(4))
+    with pytest.raises(ValueError):
+        LQRPlanner().calc_control_points(np.zeros(4), waypoints=np.zeros((5, 4)))
+    with pytest.raises(NotImplementedError):
+        LQRPlanner(waypoints=np.zeros((5, 5))).plan(0.0, 0.0, 0.0, 1.0)
