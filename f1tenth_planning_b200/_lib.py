@@ -45,7 +45,8 @@ class PlanResult(C.Structure):
                 ("n_candidates", C.c_int32), ("best_cost", C.c_float), ("reserved", C.c_int32),
                 # float* / uint8_t* in the header; void* here so that plain addresses can be stored
                 ("best_traj", _vp), ("costs", _vp), ("terms", _vp), ("flags", _vp),
-                ("goals", _vp), ("params", _vp), ("states", _vp), ("headings", _vp)]
+                ("goals", _vp), ("params", _vp), ("states", _vp), ("headings", _vp),
+                ("best_traj_map", _vp)]
 
 
 # name -> (restype, argtypes); must list every symbol include/f1l.h declares
@@ -71,6 +72,7 @@ SIGNATURES = {
     "f1l_plan_shard": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.POINTER(PlanResult)]),
     "f1l_plan_goals": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.c_int,
                                  C.POINTER(PlanResult)]),
+    "f1l_select_candidate": (C.c_int, [_vp, C.c_int, C.c_float, C.c_int, C.POINTER(PlanResult)]),
     "f1l_generate": (C.c_int, [_vp, _dp, C.c_int, _fp, _fp, _bp]),
     "f1l_plan_batch_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp,
                                      _vp, _vp, _vp]),

@@ -92,6 +92,9 @@ struct f1l_ctx {
     XchgView xview = {0, 0, {nullptr}};
     // template instance / CTA plan of the last eval_kernel launch (f1l_last_eval_shape)
     int eval_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // the last single query, for f1l_select_candidate: candidate count, explicit goals?, epoch
+    int lastq_C = 0, lastq_goals = 0;
+    unsigned long long lastq_epoch = ~0ull;
 };
 
 namespace {
@@ -109,6 +112,8 @@ int fail(f1l_handle h, cudaError_t e, const char* what) {
 
 int ensure(f1l_handle h, DevBuf& b, size_t bytes) {
     if (bytes <= b.cap && b.p) return F1L_OK;
+    // a captured single-query graph bakes device pointers in: any (re)allocation invalidates it
+    h->epoch++;
     if (b.p) {
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaFree(b.p));
@@ -375,6 +380,7 @@ struct BatchOut {
     int32_t* status = nullptr;
     double* steer_speed = nullptr;
     float4* best_traj = nullptr;
+    double* best_traj_map = nullptr;   // [S,M,4] map frame (X, Y, v, Theta)
     float* costs = nullptr;
     float* terms = nullptr;
     uint8_t* flags = nullptr;
@@ -386,7 +392,41 @@ struct BatchOut {
     int row0 = 0, row_step = 1;        // row-interleaved shard (c_begin / c_end are shard-local)
     const XchgView* xc = nullptr;      // sharded single query: exchange the argmin with the peers
     int32_t* xchg_status = nullptr;
+    bool empty_shard = false;          // this rank owns no candidate of the query: it evaluates nothing
+                                       // but still takes part in the exchange (key = ~0)
 };
+
+// select_kernel arguments of a pipeline over S scenarios (first_cand: the first evaluated candidate,
+// returned when nothing at all was evaluated)
+SelectArgs select_args(f1l_handle h, const TrackView& tv, const LutView& lut, const EvalParams& ep,
+                       const QueryCtx* ctx, const Centre* centres, const float4* goals, int C,
+                       int first_cand, const unsigned long long* best, int S, const BatchOut& o) {
+    SelectArgs se;
+    if (o.xc && S == 1) se.xc = *o.xc;
+    else { se.xc.world = 0; se.xc.rank = 0; }
+    se.xchg_status = o.xchg_status;
+    se.tr = tv;
+    se.lut = lut;
+    se.ep = ep;
+    se.ctx = ctx;
+    se.centres = centres;
+    se.widths = (const float*)h->widths.p;
+    se.nL = h->nL;
+    se.nW = h->nW;
+    se.inv_nW = 1.0f / (float)(h->nW > 0 ? h->nW : 1);
+    se.goals = goals;
+    se.C = C;
+    se.c_begin = first_cand < C ? first_cand : 0;   // (a rank without rows)
+    se.best = best;
+    se.best_idx = o.best_idx;
+    se.best_cost = o.best_cost;
+    se.status = o.status;
+    se.steer_speed = o.steer_speed;
+    se.best_traj = o.best_traj;
+    se.best_traj_map = o.best_traj_map;
+    se.prev_theta_out = o.prev_out;
+    return se;
+}
 
 // sampler -> eval -> select for S scenarios on `stream`; all pointers are device pointers
 int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, const double* opp,
@@ -398,8 +438,11 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     const int C = goals ? n_goals : h->nL * h->nW;
     if (C <= 0) return F1L_ERR_NO_GOALS;
     if (c_begin < 0) c_begin = 0;
-    if (c_end <= 0 || c_end > C) c_end = C;
-    if (c_begin >= c_end) return F1L_ERR_INVALID_ARG;
+    if (o.empty_shard) { c_begin = 0; c_end = 0; }
+    else {
+        if (c_end <= 0 || c_end > C) c_end = C;
+        if (c_begin >= c_end) return F1L_ERR_INVALID_ARG;
+    }
     if (max_opp > F1L_MAX_OPP || max_opp < 0) return F1L_ERR_INVALID_ARG;
     const int M = h->cfg.n_samples;
     const EvalParams ep = eval_params(h);
@@ -407,7 +450,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     int nseg = h->cfg.window;
     if (nseg <= 0 || nseg > nsegs) nseg = nsegs;
     const int nseg_pad = (nseg + 31) & ~31;
-    const int n_cand = c_end - c_begin;
+    const int n_cand = o.empty_shard ? 1 : c_end - c_begin;
     const CtaPlan cp = plan_ctas(n_cand, S, M, h->sm_count, ep.generator == 0);
     const int wpc = cp.nw;
     const size_t smem = eval_smem_bytes(nseg_pad, wpc, M);
@@ -489,7 +532,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     ea.stats = (unsigned long long*)h->stats.p;
     const long long n_ctas = (long long)S * ea.ctas_per_scn;
     if (n_ctas > 0x7fffffffLL) return F1L_ERR_TOO_LARGE;
-    eval_entry(M, wpc)<<<(unsigned)n_ctas, wpc * 32, smem, stream>>>(ea);
+    if (!o.empty_shard) eval_entry(M, wpc)<<<(unsigned)n_ctas, wpc * 32, smem, stream>>>(ea);
     {
         const EvalShape sh = eval_shape(M);
         const int info[8] = {sh.ipl, sh.s, sh.sg, wpc,
@@ -499,30 +542,9 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     }
     if (time_it) cudaEventRecord(ev[2], stream);
 
-    SelectArgs se;
-    if (o.xc && S == 1) se.xc = *o.xc;
-    else { se.xc.world = 0; se.xc.rank = 0; }
-    se.xchg_status = o.xchg_status;
-    se.tr = sa.tr;
-    se.lut = ea.lut;
-    se.ep = ep;
-    se.ctx = ctx;
-    se.centres = centres;
-    se.widths = ea.widths;
-    se.nL = h->nL;
-    se.nW = h->nW;
-    se.inv_nW = 1.0f / (float)(h->nW > 0 ? h->nW : 1);
-    se.goals = goals;
-    se.C = C;
-    se.c_begin = o.row_step > 1 ? c_begin + o.row0 * h->nW : c_begin;   // first evaluated candidate
-    se.best = best;
-    se.best_idx = o.best_idx;
-    se.best_cost = o.best_cost;
-    se.status = o.status;
-    se.steer_speed = o.steer_speed;
-    se.best_traj = o.best_traj;
-    se.prev_theta_out = o.prev_out;
-    select_entry(M)<<<S, 32, 0, stream>>>(se);
+    const SelectArgs se = select_args(h, sa.tr, ea.lut, ep, ctx, centres, goals, C,
+                                      o.row_step > 1 ? c_begin + o.row0 * h->nW : c_begin, best, S, o);
+    select_entry(M)<<<S, SELECT_THREADS, 0, stream>>>(se);
     if (time_it) {
         cudaEventRecord(ev[3], stream);
         h->timed = 1;
@@ -546,6 +568,10 @@ struct QHeader {
     float pad2[3];                       // -> 48 bytes, keeps the float4 trajectory 16-aligned
 };
 static_assert(sizeof(QHeader) == 48, "QHeader layout");
+// result block: header | best trajectory float4[F1L_MAX_M] | map-frame trajectory double[F1L_MAX_M][4]
+#define Q_OFF_TRAJ (sizeof(QHeader))
+#define Q_OFF_MAP (Q_OFF_TRAJ + F1L_MAX_M * sizeof(float4))
+#define Q_RES_BYTES (Q_OFF_MAP + F1L_MAX_M * 4 * sizeof(double))
 
 // pinned-host / device input block of a single query (fixed size, so that the copy is a constant
 // node of the CUDA graph): the opponent count travels in the block, not as a kernel argument
@@ -745,7 +771,7 @@ int f1l_create(f1l_handle* out, int device, const f1l_config* cfg) {
     }
     if (e == cudaSuccess) e = cudaHostAlloc(&h->h_in, 1024, cudaHostAllocDefault);
     if (e == cudaSuccess) {
-        h->h_out_cap = sizeof(QHeader) + F1L_MAX_M * sizeof(float4);
+        h->h_out_cap = Q_RES_BYTES;
         e = cudaHostAlloc(&h->h_out, h->h_out_cap, cudaHostAllocDefault);
     }
     if (e == cudaSuccess) {
@@ -1031,7 +1057,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     }
 
     if (!h->q_res.p) {
-        ENS(h->q_res, sizeof(QHeader) + F1L_MAX_M * sizeof(float4));
+        ENS(h->q_res, Q_RES_BYTES);
         // the header's padding words travel with the D2H copy: defined bytes (initcheck-clean)
         CK(cudaMemsetAsync(h->q_res.p, 0, sizeof(QHeader), st));
     }
@@ -1041,7 +1067,8 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     o.best_idx = (int32_t*)(dres + offsetof(QHeader, best_idx));
     o.status = (int32_t*)(dres + offsetof(QHeader, no_feasible));
     o.best_cost = (float*)(dres + offsetof(QHeader, best_cost));
-    o.best_traj = (float4*)(dres + sizeof(QHeader));
+    o.best_traj = (float4*)(dres + Q_OFF_TRAJ);
+    o.best_traj_map = out->best_traj_map ? (double*)(dres + Q_OFF_MAP) : nullptr;
     o.costs = (float*)(ddet + off_costs);
     o.terms = out->terms ? (float*)(ddet + off_terms) : nullptr;
     o.flags = out->flags ? (uint8_t*)(ddet + off_flags) : nullptr;
@@ -1053,7 +1080,13 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     if (row_step > 1) {   // row-interleaved shard: rows row0, row0 + row_step, ... of the goal grid
         if (goals || row0 < 0 || row0 >= row_step) return F1L_ERR_INVALID_ARG;
         const int n_rows = row0 < h->nL ? (h->nL - row0 + row_step - 1) / row_step : 0;
-        if (n_rows <= 0) return F1L_ERR_INVALID_ARG;
+        // More ranks than lookahead rows: with peers attached the call is collective, so a rank
+        // without rows must still arrive at the exchange (it contributes key = ~0 and returns the
+        // global winner like everybody else); alone there is nothing to answer.
+        if (n_rows <= 0) {
+            if (!(exchange && h->xview.world > 1)) return F1L_ERR_INVALID_ARG;
+            o.empty_shard = true;
+        }
         o.row0 = row0;
         o.row_step = row_step;
         c_begin = 0;
@@ -1086,6 +1119,9 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
                                 h->has_prev ? (const float*)h->prev.p : nullptr, o, time_it);
         if (r != F1L_OK) return r;
         CK(cudaMemcpyAsync(hd, h->q_res.p, sizeof(QHeader) + (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+        if (o.best_traj_map)
+            CK(cudaMemcpyAsync((char*)h->h_out + Q_OFF_MAP, dres + Q_OFF_MAP, (size_t)M * 32,
+                               cudaMemcpyDeviceToHost, st));
         if (want_detail)
             CK(cudaMemcpyAsync(h->h_detail, ddet, detail_bytes, cudaMemcpyDeviceToHost, st));
         return F1L_OK;
@@ -1097,7 +1133,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
                                         (out->goals ? 4u : 0u) | (out->params ? 8u : 0u) |
                                         (out->states ? 16u : 0u) | (out->headings ? 32u : 0u) |
                                         (update_prev ? 64u : 0u) | (h->has_prev ? 128u : 0u) |
-                                        (exchange ? 512u : 0u);
+                                        (exchange ? 512u : 0u) | (out->best_traj_map ? 1024u : 0u);
         // a candidate shard is a constant of the captured kernels too
         const unsigned long long shard_key = ((unsigned long long)(unsigned)c_begin << 32) | (unsigned)c_end;
         const unsigned long long rows_key = ((unsigned long long)(unsigned)row_step << 32) | (unsigned)row0;
@@ -1136,6 +1172,9 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
         h->prev_m = M;
     }
     if (exchange && hd->pad != 0) return F1L_ERR_PEER_TIMEOUT;
+    h->lastq_C = C;
+    h->lastq_goals = goals != nullptr;
+    h->lastq_epoch = h->epoch;
     out->steer = hd->steer;
     out->speed = hd->speed;
     out->best_idx = hd->best_idx;
@@ -1144,6 +1183,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     out->n_candidates = C;
     out->best_cost = hd->best_cost;
     if (out->best_traj) memcpy(out->best_traj, htraj, (size_t)M * 16);
+    if (out->best_traj_map) memcpy(out->best_traj_map, (char*)h->h_out + Q_OFF_MAP, (size_t)M * 32);
     if (want_detail) {
         const char* hdet = (const char*)h->h_detail;
         if (out->costs) memcpy(out->costs, hdet + off_costs, (size_t)C * 4);
@@ -1171,6 +1211,54 @@ int f1l_plan_rows(f1l_handle h, const double pose[4], const double* opp, int n_o
     if (row_step < 1) return F1L_ERR_INVALID_ARG;
     if (row_step == 1) return plan_internal(h, pose, opp, n_opp, nullptr, 0, 0, 0, update_prev, out, true);
     return plan_internal(h, pose, opp, n_opp, nullptr, 0, 0, 0, update_prev, out, true, row_begin, row_step);
+}
+
+int f1l_select_candidate(f1l_handle h, int idx, float cost, int update_prev, f1l_plan_result* out) {
+    if (!h || !out) return F1L_ERR_INVALID_ARG;
+    // the sampler context, goal centres / explicit goals of the last query must still be current
+    if (h->lastq_epoch != h->epoch || idx < 0 || idx >= h->lastq_C) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int M = h->cfg.n_samples, C = h->lastq_C;
+    unsigned long long* hkey = (unsigned long long*)h->h_in;   // pinned staging
+    uint32_t cb;
+    memcpy(&cb, &cost, 4);
+    const uint32_t ord = (cb & 0x80000000u) ? ~cb : (cb | 0x80000000u);   // float_orderable
+    *hkey = ((unsigned long long)ord << 32) | (unsigned)idx;
+    CK(cudaMemcpyAsync(h->q_best.p, hkey, 8, cudaMemcpyHostToDevice, st));
+    char* dres = (char*)h->q_res.p;
+    BatchOut o;
+    o.steer_speed = (double*)(dres + offsetof(QHeader, steer));
+    o.best_idx = (int32_t*)(dres + offsetof(QHeader, best_idx));
+    o.status = (int32_t*)(dres + offsetof(QHeader, no_feasible));
+    o.best_cost = (float*)(dres + offsetof(QHeader, best_cost));
+    o.best_traj = (float4*)(dres + Q_OFF_TRAJ);
+    o.best_traj_map = out->best_traj_map ? (double*)(dres + Q_OFF_MAP) : nullptr;
+    o.prev_out = update_prev ? (float*)h->prev.p : nullptr;
+    const SelectArgs se = select_args(h, track_view(h), lut_view(h), eval_params(h),
+                                      (const QueryCtx*)h->q_ctx.p, (const Centre*)h->q_centres.p,
+                                      h->lastq_goals ? (const float4*)h->q_goals.p : nullptr, C, 0,
+                                      (const unsigned long long*)h->q_best.p, 1, o);
+    select_entry(M)<<<1, SELECT_THREADS, 0, st>>>(se);
+    h->launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h->h_out, dres, Q_OFF_TRAJ + (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+    if (o.best_traj_map)
+        CK(cudaMemcpyAsync((char*)h->h_out + Q_OFF_MAP, dres + Q_OFF_MAP, (size_t)M * 32,
+                           cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (update_prev) { h->has_prev = 1; h->prev_m = M; }
+    const QHeader* hd = (const QHeader*)h->h_out;
+    out->steer = hd->steer;
+    out->speed = hd->speed;
+    out->best_idx = hd->best_idx;
+    out->no_feasible = hd->no_feasible;
+    out->tracker_found = hd->tracker_found;
+    out->n_candidates = C;
+    out->best_cost = hd->best_cost;
+    if (out->best_traj) memcpy(out->best_traj, (char*)h->h_out + Q_OFF_TRAJ, (size_t)M * 16);
+    if (out->best_traj_map) memcpy(out->best_traj_map, (char*)h->h_out + Q_OFF_MAP, (size_t)M * 32);
+    return F1L_OK;
 }
 
 // ---- peer-memory exchange (CUDA IPC over NVLink P2P) -----------------------------------------
@@ -1458,6 +1546,10 @@ int f1l_intersect_point_batch(f1l_handle h, const double* points, const double* 
                               double radius, int wrap, double* out, int32_t* out_i) {
     if (!h || !points || !t_start || n <= 0 || !out || !out_i) return F1L_ERR_INVALID_ARG;
     if (h->n < 2) return F1L_ERR_NO_TRACK;
+    // the scan indexes waypoint int(t) and its wrap loop reduces indices in [-1, int(t)] with one
+    // conditional add: start parameters outside [0, N) (or NaN) would read out of bounds
+    for (int i = 0; i < n; ++i)
+        if (!(t_start[i] >= 0.0 && t_start[i] < (double)h->n)) return F1L_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     ENS(h->m_in, (size_t)n * 16);

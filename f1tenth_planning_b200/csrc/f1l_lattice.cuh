@@ -435,6 +435,7 @@ struct SelectArgs {
     int32_t* status;        // [S,2] no_feasible, tracker_found
     double* steer_speed;    // [S,2]
     float4* best_traj;      // [S,M]
+    double* best_traj_map;  // [S,M,4] map frame (X, Y, v, Theta): SURVEY B.8, closed-loop tracking
     float* prev_theta_out;  // [M] (single query, update_prev)
 };
 
@@ -1327,8 +1328,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
 // ---------------------------------------------------------------------------------------------
 // K5: select + regenerate + tracker, one warp per scenario
 // ---------------------------------------------------------------------------------------------
+#define SELECT_THREADS 32
 template <int IPL>
-__global__ void __launch_bounds__(32) select_kernel(SelectArgs a) {
+__global__ void __launch_bounds__(SELECT_THREADS) select_kernel(SelectArgs a) {
     __shared__ float4 s_traj[F1L_MAX_M];
     const int s = blockIdx.x, lane = threadIdx.x;
     const int M = a.ep.M;
@@ -1360,6 +1362,26 @@ __global__ void __launch_bounds__(32) select_kernel(SelectArgs a) {
             s_traj[i] = st;
             if (a.best_traj) a.best_traj[(size_t)s * M + i] = st;
             if (a.prev_theta_out) a.prev_theta_out[i] = th[j];
+        }
+    }
+    if (a.best_traj_map) {   // warp-uniform
+        // map-frame copy with a speed column, what a tracker in the map frame consumes:
+        // X = pose + R(theta_pose) (x, y), Theta = theta + theta_pose, v = raceline speed at the
+        // goal centre (explicit goals: the ego speed), in float64 from the float32 states
+        double sth, cth;
+        sincos(q->th, &sth, &cth);
+        const double v_col = v_ref >= 0.0f ? (double)v_ref : q->vel;
+#pragma unroll
+        for (int j = 0; j < IPL; ++j) {
+            const int i = lane * IPL + j;
+            if (i < M) {
+                double* o = a.best_traj_map + 4 * ((size_t)s * M + i);
+                const double xd = (double)x[j], yd = (double)y[j];
+                o[0] = q->px + (cth * xd - sth * yd);
+                o[1] = q->py + (sth * xd + cth * yd);
+                o[2] = v_col;
+                o[3] = (double)th[j] + q->th;
+            }
         }
     }
     __syncwarp();

@@ -18,7 +18,8 @@ _dp, _fp, _ip, _bp = _lib._dp, _lib._fp, _lib._ip, _lib._bp
 
 PlanDetail = namedtuple("PlanDetail", [
     "steer", "speed", "best_traj", "best_idx", "best_cost", "costs", "terms", "flags", "goals",
-    "params", "states", "no_feasible", "tracker_found", "headings"])
+    "params", "states", "no_feasible", "tracker_found", "headings", "best_traj_map"],
+    defaults=[None])
 
 BatchPlan = namedtuple("BatchPlan", ["best_idx", "best_cost", "best_traj", "costs", "flags",
                                      "steer_speed"])
@@ -153,11 +154,14 @@ class Engine:
         self._ck(self._L.f1l_set_prev_path(self._h, _ptr(t, _fp), t.size))
 
     # -- single query -----------------------------------------------------------------------
-    def _result(self, C_, detail, want_states, want_headings=False):
+    def _result(self, C_, detail, want_states, want_headings=False, want_map=False):
         M = self.n_samples
         res = _lib.PlanResult()
         bufs = {"best_traj": np.empty((M, 4), np.float32)}
         res.best_traj = bufs["best_traj"].ctypes.data
+        if want_map:
+            bufs["best_traj_map"] = np.empty((M, 4), np.float64)
+            res.best_traj_map = bufs["best_traj_map"].ctypes.data
         if detail:
             bufs["costs"] = np.empty(C_, np.float32)
             bufs["terms"] = np.empty((C_, N_TERMS), np.float32)
@@ -182,7 +186,8 @@ class Engine:
         return PlanDetail(res.steer, res.speed, bufs["best_traj"], res.best_idx, res.best_cost,
                           bufs.get("costs"), bufs.get("terms"), bufs.get("flags"),
                           bufs.get("goals"), bufs.get("params"), bufs.get("states"),
-                          bool(res.no_feasible), bool(res.tracker_found), bufs.get("headings"))
+                          bool(res.no_feasible), bool(res.tracker_found), bufs.get("headings"),
+                          bufs.get("best_traj_map"))
 
     @staticmethod
     def _opp(opponent_poses):
@@ -198,7 +203,7 @@ class Engine:
         return self._n_samples
 
     def plan(self, pose, opponent_poses=None, update_prev=True, detail=True, want_states=False,
-             shard=None, want_headings=False, rows=None):
+             shard=None, want_headings=False, rows=None, want_map=False):
         """One query.  pose = (x, y, theta, velocity).  Dense-sweep sharding across GPUs:
         shard = (c_begin, c_end) evaluates a candidate range only, rows = (row_begin, row_step)
         the lookahead rows row_begin, row_begin + row_step, ... (balanced across ranks).  With
@@ -208,7 +213,7 @@ class Engine:
         if pose.size != 4:
             raise ValueError("pose must be (x, y, theta, velocity)")
         opp, k = self._opp(opponent_poses)
-        res, bufs = self._result(self.n_candidates, detail, want_states, want_headings)
+        res, bufs = self._result(self.n_candidates, detail, want_states, want_headings, want_map)
         if rows is not None:
             code = self._L.f1l_plan_rows(self._h, pose.ctypes.data, opp.ctypes.data if k else None,
                                          k, int(rows[0]), int(rows[1]),
@@ -223,14 +228,23 @@ class Engine:
         return self._detail(res, bufs)
 
     def plan_goals(self, pose, goals, opponent_poses=None, update_prev=True, detail=True,
-                   want_states=False):
+                   want_states=False, want_map=False):
         pose = _f64(pose).ravel()
         g = _f64(goals).reshape(-1, 3)
         opp, k = self._opp(opponent_poses)
-        res, bufs = self._result(g.shape[0], detail, want_states)
+        res, bufs = self._result(g.shape[0], detail, want_states, want_map=want_map)
         self._ck(self._L.f1l_plan_goals(self._h, pose.ctypes.data, g.ctypes.data, g.shape[0],
                                         opp.ctypes.data if k else None, k, int(bool(update_prev)),
                                         C.byref(res)))
+        return self._detail(res, bufs)
+
+    def select_candidate(self, idx, cost=0.0, update_prev=True, want_map=False):
+        """Tracker output and trajectory of candidate `idx` of the last plan() / plan_goals() query
+        (a selection made by user code, f1l_select_candidate) -> PlanDetail without the
+        per-candidate arrays."""
+        res, bufs = self._result(0, False, False, want_map=want_map)
+        self._ck(self._L.f1l_select_candidate(self._h, int(idx), float(cost), int(bool(update_prev)),
+                                              C.byref(res)))
         return self._detail(res, bufs)
 
     def generate(self, goals):
@@ -450,6 +464,25 @@ class Engine:
         i = np.zeros(6, np.int32)
         self._ck(self._L.f1l_debug_query_ctx(self._h, _ptr(f, _fp), _ptr(i, _ip)))
         return f, i
+
+
+_fp_weights = {}
+
+
+def fingerprint(arr):
+    """(shape, 64-bit multilinear hash) of a float64 array: sum of (bit pattern x odd random
+    weight) mod 2^64 over EVERY element, so any in-place edit of any row changes it (a single
+    changed element always does: odd weights are invertible mod 2^64).  ~8 us for a 2000 x 5
+    raceline, against ~50 us for zlib.crc32 over the same bytes -- cheap enough to run on every
+    plan() call, which is what detects an edited raceline."""
+    a = np.ascontiguousarray(arr, dtype=np.float64)
+    v = a.reshape(-1).view(np.uint64)
+    w = _fp_weights.get(v.size)
+    if w is None:
+        w = np.random.default_rng(0x5eed + v.size).integers(0, 2 ** 63, size=v.size, dtype=np.uint64)
+        w = w * np.uint64(2) + np.uint64(1)
+        _fp_weights[v.size] = w
+    return a.shape, int(np.dot(v, w))
 
 
 def pinned_empty(shape, dtype):

@@ -26,11 +26,11 @@ With no plug-ins registered every stage runs on the GPU.  A registered ``sample_
 only the sampler (its goals are uploaded); registered ``cost_funcs`` are user Python code and are
 evaluated on the host over GPU-generated trajectories, as the reference's ``eval`` does.
 """
-import zlib
 
 import numpy as np
 
-from .engine import Engine, PlanDetail, FLAG_VALID  # noqa: F401
+from .engine import (Engine, PlanDetail, FLAG_VALID, FLAG_COLLIDE_OPP, FLAG_COLLIDE_MAP,  # noqa: F401
+                     fingerprint)
 from .pure_pursuit import PurePursuitPlanner
 from . import synth
 
@@ -52,15 +52,15 @@ class LatticePlanner():
         self.selection_func = None
         self.cost_weights = None   # weights for registered python cost functions (eval)
 
-        self.tracker = PurePursuitPlanner(device=device)   # :55 (default wheelbase, as upstream)
+        # :55 (default wheelbase, as upstream).  Kept for API parity; plan() tracks on the device
+        # (select_kernel), also for user-selected candidates
+        self.tracker = PurePursuitPlanner(device=device)
 
         self._device = device
         config.setdefault("wheelbase", float(wheelbase))
         self._config = config
         self._engine = None
         self._key = None
-        self._wp_obj = None
-        self._wp_crc = None
         self._lookaheads = synth.DEFAULT_LOOKAHEADS.copy()   # :228
         self._widths = synth.DEFAULT_WIDTHS.copy()           # :229
         self._grid_dirty = True
@@ -148,23 +148,17 @@ class LatticePlanner():
             self._engine = Engine(device=self._device, **self._config)
             if self._map is not None:
                 self._engine.set_grid(*self._map)
-        # Has the raceline changed?  A full checksum costs 15 us per call at 2000 waypoints, a
-        # tenth of a plan(): the same array object is re-checked on a stride-16 subsample (its
-        # rows change together when a raceline is replaced), a new object in full.
+        # Has the raceline changed?  Every element takes part in the fingerprint (in-place edits of
+        # single rows are detected), ~8 us per call.
         wp = self.waypoints
         arr = wp if isinstance(wp, np.ndarray) else np.asarray(wp, dtype=np.float64)
-        sub = zlib.crc32(np.ascontiguousarray(arr[::16], dtype=np.float64).tobytes())
-        fast_key = (arr.shape, sub)
-        if not (wp is self._wp_obj and fast_key == self._key):
+        key = fingerprint(arr)
+        if key != self._key:
             w = np.ascontiguousarray(arr, dtype=np.float64)
-            full = zlib.crc32(w.tobytes())
-            if not (fast_key == self._key and full == self._wp_crc):
-                if w.ndim != 2 or w.shape[1] < 4:
-                    raise ValueError('Waypoints needs to be a (Nxm), m >= 4 (x, y, v, psi[, kappa]), numpy array!')
-                self._engine.set_track(w)
-                self._key = fast_key
-                self._wp_crc = full
-        self._wp_obj = wp
+            if w.ndim != 2 or w.shape[1] < 4:
+                raise ValueError('Waypoints needs to be a (Nxm), m >= 4 (x, y, v, psi[, kappa]), numpy array!')
+            self._engine.set_track(w)
+            self._key = key
         if self._grid_dirty:
             self._engine.set_goal_grid(self._lookaheads, self._widths)
             self._grid_dirty = False
@@ -189,41 +183,52 @@ class LatticePlanner():
 
     # -- planning -------------------------------------------------------------------------------
     def plan_detailed(self, pose_x, pose_y, pose_theta, velocity, waypoints=None,
-                      opponent_poses=None, want_states=False):
-        """Full result of one query as a PlanDetail (see engine.PlanDetail)."""
+                      opponent_poses=None, want_states=False, want_map=False):
+        """Full result of one query as a PlanDetail (see engine.PlanDetail).  want_map adds
+        ``best_traj_map`` [M,4] = (X, Y, v, Theta), the best trajectory in the map frame with a
+        speed column (what a map-frame tracker consumes)."""
         if waypoints is not None:
             self.waypoints = waypoints
         eng = self._sync()
         pose = np.array([pose_x, pose_y, pose_theta, velocity], dtype=np.float64)
         custom_cost = len(self.cost_funcs) > 0
         custom_select = self.selection_func is not None and self.selection_func is not np.argmin
-        need_states = want_states or custom_cost or custom_select
+        plugins = custom_cost or custom_select
+        need_states = want_states or custom_cost
         if self.sample_func is not None:
             goal_grid = np.asarray(self.sample(pose_x, pose_y, pose_theta, velocity, self.waypoints),
                                    dtype=np.float64).reshape(-1, 3)
-            d = eng.plan_goals(pose, goal_grid, opponent_poses, want_states=need_states)
-        elif self._shard is not None and not need_states:
-            d = eng.plan(pose, opponent_poses, rows=self._shard)
+            d = eng.plan_goals(pose, goal_grid, opponent_poses, want_states=need_states,
+                               want_map=want_map and not plugins)
+        elif self._shard is not None and not (need_states or plugins):
+            d = eng.plan(pose, opponent_poses, rows=self._shard, want_map=want_map)
         else:
-            d = eng.plan(pose, opponent_poses, want_states=need_states)
-        if custom_cost or custom_select:
-            # user python plug-ins: evaluate on the host over the GPU-generated trajectories
-            all_traj = d.states.astype(np.float64)
-            all_traj[:, :, 3] = np.abs(all_traj[:, :, 3])   # utils.py:293 column = |kappa|
+            d = eng.plan(pose, opponent_poses, want_states=need_states,
+                         want_map=want_map and not plugins)
+        if plugins:
+            # User python plug-ins (lattice_planner.py:130-172) run on the host over the
+            # GPU-generated trajectories; candidates the GPU found invalid or in collision keep
+            # cost +inf whatever the user functions say.  The chosen candidate then goes back to
+            # the device, which regenerates it and runs the same tracker as the built-in
+            # selection (f1l_select_candidate) -- same frame, speed column, literal_tracker,
+            # wheelbase and max_reacquire, and it becomes the next call's previous path.
+            bad = ((d.flags & FLAG_VALID) == 0) | ((d.flags & (FLAG_COLLIDE_OPP | FLAG_COLLIDE_MAP)) != 0)
             if custom_cost:
+                all_traj = d.states.astype(np.float64)
+                all_traj[:, :, 3] = np.abs(all_traj[:, :, 3])   # utils.py:293 column = |kappa|
                 weights = self.cost_weights
                 if weights is None:
                     weights = [1.0 / len(self.cost_funcs)] * len(self.cost_funcs)
                 costs = np.asarray(self.eval(all_traj, weights), dtype=np.float64)
+                costs[bad] = np.inf
             else:
                 costs = d.costs.astype(np.float64)
             idx = int(self.select(costs))
-            best = d.states[idx].copy()
-            steer, speed = self.tracker.plan(pose_x, pose_y, pose_theta,
-                                             eng.config.tracker_lookahead,
-                                             all_traj[idx])                  # :208-212
-            d = d._replace(steer=steer, speed=speed, best_traj=best, best_idx=idx,
-                           best_cost=float(costs[idx]), costs=costs.astype(np.float32))
+            t = eng.select_candidate(idx, costs[idx], update_prev=True, want_map=want_map)
+            d = d._replace(steer=t.steer, speed=t.speed, best_traj=t.best_traj, best_idx=idx,
+                           best_cost=float(costs[idx]), costs=costs.astype(np.float32),
+                           no_feasible=t.no_feasible, tracker_found=t.tracker_found,
+                           best_traj_map=t.best_traj_map)
         self.last = d
         return d
 
@@ -257,7 +262,7 @@ def sample_lookahead_square(pose_x, pose_y, pose_theta, velocity, waypoints,
     repairs listed in DESIGN.md: every centre gets every width, offsets along the raceline
     normal, goals in the vehicle frame).  Runs the GPU sampler; returns [n_L*n_W, 3]."""
     w = np.ascontiguousarray(waypoints, dtype=np.float64)
-    key = (w.shape, zlib.crc32(w.tobytes()))
+    key = fingerprint(w)
     pl = _sampler_planners.get("p")
     if pl is None:
         pl = LatticePlanner()

@@ -2,11 +2,10 @@
 batched CUDA kernel (K1).  `plan` keeps the reference signature and return order
 (steering_angle, speed); `plan_batch` is the additive batched form (BASELINE config 2)."""
 import warnings
-import zlib
 
 import numpy as np
 
-from .engine import Engine
+from .engine import Engine, fingerprint
 
 
 class PurePursuitPlanner():
@@ -35,7 +34,7 @@ class PurePursuitPlanner():
             self._engine.configure(wheelbase=float(self.wheelbase),
                                    max_reacquire=float(self.max_reacquire))
         w = np.ascontiguousarray(self.waypoints, dtype=np.float64)
-        key = (w.shape, zlib.crc32(w.tobytes()))
+        key = fingerprint(w)
         if key != self._key:
             self._engine.set_track(w)
             self._key = key

@@ -3,11 +3,10 @@ controller, Hoffmann et al. 2007), backed by the batched CUDA nearest-point kern
 front-axle mode).  `plan` keeps the reference signature and return order (steering_angle, speed);
 `plan_batch` is the additive batched form.  LQR's `calc_control_points`
 (control/lqr/lqr.py:60-102) is the same front-axle computation: use `front_axle_errors`."""
-import zlib
 
 import numpy as np
 
-from .engine import Engine
+from .engine import Engine, fingerprint
 
 
 class StanleyPlanner():
@@ -30,7 +29,7 @@ class StanleyPlanner():
         if self._engine is None:
             self._engine = Engine(device=self._device)
         w = np.ascontiguousarray(self.waypoints, dtype=np.float64)
-        key = (w.shape, zlib.crc32(w.tobytes()))
+        key = fingerprint(w)
         if key != self._key:
             self._engine.set_track(w)
             self._key = key

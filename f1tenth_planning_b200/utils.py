@@ -12,11 +12,10 @@ The free functions take the trajectory on every call like the reference does; th
 cached on the array's content so repeated calls on the same track upload once.
 """
 import math
-import zlib
 
 import numpy as np
 
-from .engine import Engine
+from .engine import Engine, fingerprint
 
 _engines = {}      # device -> Engine used by the free functions
 _track_key = {}    # device -> key of the trajectory currently uploaded
@@ -30,7 +29,7 @@ def _engine_for(trajectory, device=None):
     if eng is None:
         eng = Engine(device=device)
         _engines[device] = eng
-    key = (traj.shape, zlib.crc32(traj.tobytes()))
+    key = fingerprint(traj)
     if _track_key.get(device) != key:
         eng.set_track(traj)
         _track_key[device] = key
@@ -51,6 +50,9 @@ def intersect_point(point, radius, trajectory, t=0.0, wrap=False, device=None):
     """First intersection of the circle (point, radius) with the trajectory starting at parameter
     t.  Returns (p (2,) | None, i | None, t | None) like utils/utils.py:69-151."""
     eng = _engine_for(trajectory, device)
+    if not (0.0 <= float(t) < eng.n_waypoints):
+        # the reference indexes trajectory[int(t)] unchecked (numba: no bounds check)
+        raise IndexError("start parameter t=%r outside [0, %d)" % (t, eng.n_waypoints))
     out, out_i = eng.intersect_point_batch(np.array([[float(point[0]), float(point[1])]]),
                                            np.array([float(t)]), radius, wrap)
     if out[0, 3] == 0.0:

@@ -156,6 +156,12 @@ typedef struct {
     float* states;           /* [C,M,4] every trajectory (debug / custom cost functions) */
     float* headings;         /* [C,M,2] (cos, sin) of the sample headings used by the footprint
                                 (teacher-forced collision tests) */
+    double* best_traj_map;   /* [M,4] the best trajectory in the MAP frame with a speed column,
+                                (X, Y, v, Theta): X = pose + R(theta_pose) (x, y), Theta = theta +
+                                theta_pose, v = raceline speed at the goal centre (explicit goals:
+                                the ego speed).  The form a map-frame tracker consumes -- the
+                                reference hands its tracker the vehicle-frame array against a
+                                map-frame pose (lattice_planner.py:208-212). */
 } f1l_plan_result;
 
 /*
@@ -177,7 +183,10 @@ int f1l_plan_shard(f1l_handle h, const double pose[4], const double* opp, int n_
  * grid are evaluated (all widths of each).  Near and far goals cost differently (short spirals
  * fail validation early, long ones meet more opponents and walls), so rank r of W taking rows
  * r, r + W, ... balances the ranks where contiguous blocks do not.  Indices stay global; the
- * peer exchange applies as for f1l_plan_shard.  0 <= row_begin < row_step.  update_prev != 0
+ * peer exchange applies as for f1l_plan_shard.  0 <= row_begin < row_step.  A rank whose
+ * row_begin is beyond the last row (more ranks than rows) evaluates nothing: with peers attached
+ * it still joins the exchange and returns the global winner, alone it is F1L_ERR_INVALID_ARG.
+ * update_prev != 0
  * stores the winner's theta column as the next call's prev_path like f1l_plan -- the winner of
  * this call, i.e. the global one only with peers attached (every rank then stores the same). */
 int f1l_plan_rows(f1l_handle h, const double pose[4], const double* opp, int n_opp,
@@ -208,6 +217,16 @@ int f1l_xchg_detach(f1l_handle h);
  * sampler.  Replaces the user `sample_func` plug-in (lattice_planner.py:77-98,113-128). */
 int f1l_plan_goals(f1l_handle h, const double pose[4], const double* goals, int n_goals,
                    const double* opp, int n_opp, int update_prev, f1l_plan_result* out);
+
+/* Selection made by the caller (the reference's `selection_func` / `cost_funcs` plug-ins,
+ * lattice_planner.py:57-75,100-111,159-172, which are user Python code): regenerates candidate
+ * `idx` of the LAST f1l_plan / f1l_plan_goals query on this handle and runs the tracker on it
+ * exactly as the built-in selection would (literal_tracker, wheelbase, max_reacquire, raceline
+ * speed), filling steer / speed / tracker_found / best_idx / best_cost (= `cost`, no_feasible =
+ * !(cost < inf)) / best_traj / best_traj_map of *out; the per-candidate arrays are not touched.
+ * F1L_ERR_INVALID_ARG if no query has run since the last upload / configuration change or idx is
+ * out of range. */
+int f1l_select_candidate(f1l_handle h, int idx, float cost, int update_prev, f1l_plan_result* out);
 
 /* Trajectory generation only: goals [C,3] -> states [C,M,4], params [C,4], flags [C] (host).
  * Replaces the Clothoid.G1Hermite + sample_traj loop (lattice_planner.py:195-198,
@@ -273,7 +292,9 @@ int f1l_front_axle_batch(f1l_handle h, const double* poses, int n_poses, double 
                          double k_path, double* front, int32_t* nearest_i);
 
 /* intersect_point (utils/utils.py:69-151) for B independent queries on the uploaded track:
- * points [B,2], radius, start parameter t [B]; out [B,4] = (p_x, p_y, t, found), out_i [B]. */
+ * points [B,2], radius, start parameter t [B]; out [B,4] = (p_x, p_y, t, found), out_i [B].
+ * Every t must lie in [0, N) (N waypoints): anything else, NaN included, is F1L_ERR_INVALID_ARG
+ * (the reference indexes waypoint int(t) unchecked). */
 int f1l_intersect_point_batch(f1l_handle h, const double* points, const double* t_start,
                               int n, double radius, int wrap, double* out, int32_t* out_i);
 

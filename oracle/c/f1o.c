@@ -745,6 +745,19 @@ int f1o_plan(const f1o_config* cfg, const f1o_world* w, const double pose[4], co
         out->steer = act[0];
         out->speed = act[1];
     }
+    if (out->best_traj_map) {
+        /* the best trajectory in the map frame with a speed column [X, Y, v, Theta],
+         * X = pose + R(theta_pose) (x, y) (B.3), v = raceline speed at the goal centre */
+        double v = pose[3];
+        if (!goals_in && w->ncols > 2) v = w->wpts[(size_t)centre_i[best_row] * w->ncols + 2];
+        for (int i = 0; i < M; ++i) {
+            const double x = best_st[4 * i], y = best_st[4 * i + 1];
+            out->best_traj_map[4 * i] = pose[0] + (ct * x - stn * y);
+            out->best_traj_map[4 * i + 1] = pose[1] + (stn * x + ct * y);
+            out->best_traj_map[4 * i + 2] = v;
+            out->best_traj_map[4 * i + 3] = best_st[4 * i + 2] + pose[2];
+        }
+    }
     free(goals); free(centre_i); free(centre_ok); free(st); free(best_st);
     return C;
 }

@@ -71,6 +71,7 @@ typedef struct {
     double* params;    /* [C,4] */
     double* states;    /* [C,M,4] */
     double* margins;   /* [C,2] opponent / map collision margins (metres, see f1o.c) */
+    double* best_traj_map; /* [M,4] (X, Y, v, Theta) map frame, SURVEY B.8 */
 } f1o_result;
 
 void f1o_default_config(f1o_config* cfg);

@@ -43,7 +43,7 @@ class Result(C.Structure):
                 ("no_feasible", C.c_int32), ("tracker_found", C.c_int32),
                 ("n_candidates", C.c_int32), ("best_cost", C.c_double), ("best_traj", _dp),
                 ("costs", _dp), ("terms", _dp), ("flags", _bp), ("goals", _dp), ("params", _dp),
-                ("states", _dp), ("margins", _dp)]
+                ("states", _dp), ("margins", _dp), ("best_traj_map", _dp)]
 
 
 _lib = None
@@ -253,7 +253,8 @@ def plan(cfg, world, pose, opp=None, goals=None, c_begin=0, c_end=0, want_states
     res = Result()
     out = dict(best_traj=np.zeros((M, 4)), costs=np.full(Cn, np.inf), terms=np.zeros((Cn, N_TERMS)),
                flags=np.zeros(Cn, np.uint8), goals=np.zeros((Cn, 3)), params=np.zeros((Cn, 4)),
-               margins=np.full((Cn, 2), np.inf))
+               margins=np.full((Cn, 2), np.inf), best_traj_map=np.zeros((M, 4)))
+    res.best_traj_map = _d(out["best_traj_map"])
     if want_states:
         out["states"] = np.zeros((Cn, M, 4))
         res.states = _d(out["states"])

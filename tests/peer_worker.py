@@ -61,6 +61,18 @@ def main():
     d = eng.plan(poses[0], opp[0, :1], update_prev=False, detail=False, shard=(lo, hi))
     assert whole_inf.no_feasible and whole_inf.best_idx == 0
     assert d.no_feasible == whole_inf.no_feasible and d.best_idx == whole_inf.best_idx, (d.no_feasible, d.best_idx)
+    # more ranks than lookahead rows (advisor r1): a rank without rows evaluates nothing, still
+    # joins the exchange and returns the global winner -- nobody times out
+    eng.configure(kappa_max=0.0)
+    eng.set_goal_grid(np.linspace(1.0, 3.0, world - 1) if world > 2 else [2.0], np.linspace(-1.2, 1.2, 21))
+    few = eng.plan(poses[2], opp[2, :n_opp[2]], update_prev=False, detail=False)
+    for graph in (True, False):
+        eng.set_graph(graph)
+        d = eng.plan(poses[2], opp[2, :n_opp[2]], update_prev=False, detail=False, rows=(rank, world))
+        assert d.best_idx == few.best_idx and np.float32(d.best_cost) == np.float32(few.best_cost), \
+            (rank, d.best_idx, few.best_idx)
+        assert np.array_equal(d.best_traj, few.best_traj) and d.steer == few.steer
+    eng.set_goal_grid(np.linspace(0.5, 3.5, 24), np.linspace(-1.2, 1.2, 21))
     eng.detach_peers()
     # detached again: plan(shard=...) is local
     eng.configure(kappa_max=0.0)

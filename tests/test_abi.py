@@ -33,7 +33,7 @@ def test_struct_layouts_match_header():
     from f1tenth_planning_b200 import _lib
     from oracle import c_oracle as co
     assert ctypes.sizeof(_lib.Config) == 10 * 4 + 5 * 8 + 7 * 8   # 9 int32 + 4 bytes of padding
-    assert ctypes.sizeof(_lib.PlanResult) == 16 + 16 + 8 + 8 * 8
+    assert ctypes.sizeof(_lib.PlanResult) == 16 + 16 + 8 + 9 * 8
     assert ctypes.sizeof(co.Config) == ctypes.sizeof(_lib.Config)
     cfg = _lib.default_config()
     oc = co.default_config()

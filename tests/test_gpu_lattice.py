@@ -56,6 +56,17 @@ def test_config3_4096_candidates(ellipse):
     assert st["n_both_valid"] > 1000
     assert st["collide_map_count"] > 0 and st["collide_opp_count"] > 0
     assert st["valid_mismatch"] <= 4 and st["collide_map_mismatch"] + st["collide_opp_mismatch"] <= 8
+    H.record_parity("c3_device_lut_seed", st)
+    # the same query with the oracle seeded from its OWN float64 LUT (nearest cell), not the
+    # device's: the converged spirals, costs, flags and the argmin must still agree
+    eng2, cfg2, world2 = H.make_pair(ellipse, la, wd, grid=synth.corridor_grid(half_width=1.0),
+                                     use_device_lut=False)
+    for seed in (1003, 1013):
+        pose, opp = H.scenario(ellipse, seed, 8)
+        d2 = eng2.plan(pose, opp, update_prev=False, want_states=True, want_map=True)
+        o2 = co.plan(cfg2, world2, pose, opp, want_states=True)
+        st2 = H.compare_plan(d2, o2, cfg2, record="c3_oracle_own_lut_seed%d" % seed)
+        assert st2["valid_mismatch"] <= 4 and st2["collide_map_mismatch"] + st2["collide_opp_mismatch"] <= 8
 
 
 def test_oracle_lut_seed_gives_same_answers(ellipse):

@@ -66,6 +66,21 @@ def test_config2_sample_vs_oracle(ellipse):
     o = co.pure_pursuit_batch(ellipse, poses[sub], 0.8, n_threads=co.max_threads())
     same = r.nearest_i[sub] == o["nearest_i"]
     assert (~same).mean() < 0.02
+    # every index mismatch is a vertex tie, (k, t=1) == (k+1, t=0): neighbouring segments, the
+    # same distance and the same projection -- a wrong block from the FP32 scan at a
+    # hairpin would differ by more than one segment or in distance
+    ties = np.nonzero(~same)[0]
+    for k in ties:
+        gi, oi = int(r.nearest_i[sub][k]), int(o["nearest_i"][k])
+        assert abs(gi - oi) == 1, (k, gi, oi)
+        assert abs(r.nearest[sub][k, 2] - o["nearest"][k, 2]) < 1e-9
+        np.testing.assert_allclose(r.nearest[sub][k, :2], o["nearest"][k, :2], rtol=0, atol=1e-9)
+        lo_t = r.nearest[sub][k, 3] if gi < oi else o["nearest"][k, 3]
+        hi_t = o["nearest"][k, 3] if gi < oi else r.nearest[sub][k, 3]
+        assert lo_t > 1.0 - 1e-7 and hi_t < 1e-7, (k, lo_t, hi_t)
+    from tests import helpers as H
+    H.record_parity("c2_nearest_index", {"poses": 4000, "index_mismatch": int(ties.size),
+                                         "index_mismatch:vertex_tie": int(ties.size)})
     np.testing.assert_allclose(r.nearest[sub][same], o["nearest"][same], rtol=1e-9, atol=1e-9)
     np.testing.assert_allclose(r.actuation[sub][same], o["actuation"][same], rtol=1e-9, atol=1e-9)
     assert (r.status[sub][same] == o["status"][same]).all()

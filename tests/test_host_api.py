@@ -82,3 +82,21 @@ def test_lqr_mirror_error_conventions():
         LQRPlanner().calc_control_points(np.zeros(4), waypoints=np.zeros((5, 4)))
     with pytest.raises(NotImplementedError):
         LQRPlanner(waypoints=np.zeros((5, 5))).plan(0.0, 0.0, 0.0, 1.0)
+
+
+def test_fingerprint_sees_every_element():
+    """raceline change detection (advisor r1): any single edited element of the array changes the
+    fingerprint -- no subsampling"""
+    from f1tenth_planning_b200.engine import fingerprint
+    rng = np.random.default_rng(0)
+    a = rng.normal(size=(2000, 5))
+    k0 = fingerprint(a)
+    assert fingerprint(a.copy()) == k0 and fingerprint(np.asfortranarray(a)) == k0
+    for i, j in [(5, 2), (1999, 4), (0, 0), (17, 3), (1001, 1)]:
+        b = a.copy()
+        b[i, j] = np.nextafter(b[i, j], np.inf)          # one ulp
+        assert fingerprint(b) != k0
+    b = a.copy()
+    b[[3, 4]] = b[[4, 3]]                                 # two rows swapped: same multiset
+    assert fingerprint(b) != k0
+    assert fingerprint(a[:1999]) != k0 and fingerprint(a.reshape(5, 2000))[0] != k0[0]
