@@ -91,14 +91,19 @@ class ClockSampler:
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
-        last = len(self.rows)
+            return
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+
+    def window(self):
+        """clocks / throttle reasons of the rows since mark() (the sampler keeps running)"""
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        last = len(self.rows)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         rows = self.rows[getattr(self, "first", 0):last] or self.rows[-3:]
@@ -119,11 +124,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def profiled_dram_bytes(path=os.path.join(ROOT, "profiles", "r1_eval_kernel.md")):
+PROFILE_MD = "profiles/r2_eval_kernel.md" if os.path.exists(os.path.join(ROOT, "profiles", "r2_eval_kernel.md")) \
+    else "profiles/r1_eval_kernel.md"
+
+
+def profiled_dram_bytes(path=None):
     """dram__bytes_read.sum + dram__bytes_write.sum of one eval_kernel launch of the bench workload,
     from the committed ncu --set full summary (bench.py cannot run under ncu itself)."""
     unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     tot, seen = 0.0, 0
+    path = path or os.path.join(ROOT, PROFILE_MD)
     try:
         for ln in open(path):
             c = [x.strip() for x in ln.split("|")]
@@ -136,11 +146,15 @@ def profiled_dram_bytes(path=os.path.join(ROOT, "profiles", "r1_eval_kernel.md")
 
 
 def workload(seed_rank, S):
+    """Scenario set of rank `seed_rank`: always drawn as the full S_PER_GPU-scenario batch of that
+    seed and then cut to its first S, so every arm (device-resident, end to end, CPU baseline,
+    --impl reference, strong-scaling shards) sees a prefix / slice of the SAME scenarios (the
+    generator's stream depends on the batch size)."""
     track = synth.ellipse_track()
     grid = synth.corridor_grid()
     la, wd = synth.goal_grid(4)
-    poses, opp, n_opp = synth.scenario_batch(track, S, K_OPP, 1004 + 7919 * seed_rank)
-    return track, grid, la, wd, poses, opp, n_opp
+    poses, opp, n_opp = synth.scenario_batch(track, max(S, S_PER_GPU), K_OPP, 1004 + 7919 * seed_rank)
+    return track, grid, la, wd, poses[:S].copy(), opp[:S].copy(), n_opp[:S].copy()
 
 
 def work_flops(flags, M, W, n_opp_mean):
@@ -194,7 +208,7 @@ def run_reference(args):
         return
     from oracle import c_oracle as co
     threads = host_threads()
-    track, grid, la, wd, poses, opp, n_opp = workload(0, 20000)
+    track, grid, la, wd, poses, opp, n_opp = workload(0, S_PER_GPU)   # the GPU arm's rank-0 scenarios
     world = co.World_(track, la, wd, grid=grid[0], grid_origin=grid[1], grid_res=grid[2])
     cfg = co.default_config(**PLAN_CFG)
     C = world.n_candidates
@@ -212,7 +226,8 @@ def run_reference(args):
         co.plan_batch(cfg, world, poses[:n], opp[:n], n_opp[:n], n_threads=threads)
     dt = time.perf_counter() - t
     value = n * C * args.steps / dt
-    sample = "%d scenarios x %d candidates per step (bounded sample of the 10^5-scenario workload)" % (n, C)
+    sample = ("the first %d of the GPU arm's %d scenarios x %d candidates per step (bounded sample of the "
+              "same workload, same seed)" % (n, S_PER_GPU, C))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -229,7 +244,7 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
-def extras(track, grid, device):
+def extras(track, grid, device, fp32_peak=None):
     """side measurements (not the headline): C3 plan() latency, C2 poses/s, C5 dense sweep."""
     import torch
     from f1tenth_planning_b200.engine import Engine
@@ -283,6 +298,16 @@ def extras(track, grid, device):
     out["c3_kernel_us"] = {"sample": 1e3 * sm, "eval": 1e3 * ev, "select": 1e3 * se}
     out["c3_eval_candidates_per_s"] = 4096 / (ev * 1e-3) if ev > 0 else None
     eng.close()
+    # the CPU oracle's plan() of the same C3 queries (one core: a single query is sequential)
+    ocfg3 = co.default_config(n_samples=100, window=128)
+    world3 = co.World_(track, la, wd, grid=grid[0], grid_origin=grid[1], grid_res=grid[2])
+    ts = []
+    for i in range(3):
+        t = time.perf_counter()
+        co.plan(ocfg3, world3, poses[i], opp[i, :n_opp[i]])
+        ts.append(time.perf_counter() - t)
+    out["c3_cpu_oracle_plan_p50_us"] = 1e6 * float(np.percentile(ts, 50))
+    out["c3_cpu_oracle_cores"] = 1
     # C5: dense sweep 65536 x 200
     la, wd = synth.goal_grid(5)
     eng = Engine(device=device, n_samples=200, window=128)
@@ -302,6 +327,17 @@ def extras(track, grid, device):
     out["c5_plan_p50_us"] = 1e6 * float(np.percentile(ts, 50))
     out["c5_eval_candidates_per_s"] = 65536 / (ev * 1e-3) if ev > 0 else None
     eng.close()
+    # CPU oracle on a bounded slice of the same C5 query (2048 of the 65536 candidates, one core),
+    # and the whole query extrapolated linearly from it
+    ocfg5 = co.default_config(n_samples=200, window=128)
+    world5 = co.World_(track, la, wd, grid=grid[0], grid_origin=grid[1], grid_res=grid[2])
+    t = time.perf_counter()
+    co.plan(ocfg5, world5, poses[0], opp[0, :n_opp[0]], c_begin=32768, c_end=32768 + 2048)
+    dt = time.perf_counter() - t
+    out["c5_cpu_oracle_candidates_per_s"] = 2048 / dt
+    out["c5_cpu_oracle_plan_extrapolated_us"] = 1e6 * dt * 65536 / 2048
+    out["c5_cpu_oracle_cores"] = 1
+    out["c5_cpu_oracle_sample"] = "candidates [32768, 34816) of query 0, %.2f s" % dt
     # C2: 10^5 poses pure pursuit, device resident
     eng = Engine(device=device)
     eng.set_track(track)
@@ -328,7 +364,21 @@ def extras(track, grid, device):
     out["c2_poses_per_s"] = 100000 / (ms * 1e-3)
     out["c2_ms"] = ms
     out["c2_fp32_tflops"] = 100000 * F.pose_flops(track.shape[0]) / (ms * 1e-3) / 1e12
+    # K1's own roofline object: F_pose = 17 (N - 1) + 60 FLOP x 10^5 poses per launch pair
+    out["c2_roofline"] = {"bound": "fp32", "achieved": out["c2_fp32_tflops"], "peak": fp32_peak,
+                          "unit": "TFLOP/s", "frac": out["c2_fp32_tflops"] / fp32_peak if fp32_peak else None,
+                          "kernel": "pp_scan_kernel + pp_finish_kernel", "ms": ms,
+                          "flops_per_launch": 100000 * F.pose_flops(track.shape[0])}
     eng.close()
+    # CPU oracle (pinned to the reference's nearest_point / pure pursuit) on a bounded sample of
+    # the same poses: one core -- the reference is single-threaded -- and all host cores
+    th = host_threads()
+    for key, nt, n in (("c2_cpu_oracle_poses_per_s_1core", 1, 4000), ("c2_cpu_oracle_poses_per_s_all_cores", th, 4000 * th)):
+        n = min(n, 100000)
+        t = time.perf_counter()
+        co.pure_pursuit_batch(track, pp[:n, :3], 0.8, n_threads=nt)
+        out[key] = n / (time.perf_counter() - t)
+    out["c2_cpu_oracle_cores"] = th
     return out
 
 
@@ -409,10 +459,81 @@ def sharded_dense_query(track, grid, device, rank, world_size, dev):
             "c5_candidates_per_rank": hi - lo, "c5_last_best": list(best_p[-1])}
 
 
+class DeviceArm:
+    """device-resident inputs / outputs of one rank for S scenarios"""
+
+    def __init__(self, torch, dev, eng, poses, opp, n_opp):
+        S, C, M = poses.shape[0], eng.n_candidates, eng.n_samples
+        self.eng, self.S = eng, S
+        self.tp = torch.from_numpy(poses).to(dev)
+        self.to = torch.from_numpy(opp).to(dev)
+        self.tn = torch.from_numpy(n_opp).to(dev)
+        self.o_idx = torch.empty(S, dtype=torch.int32, device=dev)
+        self.o_cost = torch.empty(S, dtype=torch.float32, device=dev)
+        self.o_traj = torch.empty(S, M, 4, dtype=torch.float32, device=dev)
+        self.o_costs = torch.empty(S, C, dtype=torch.float32, device=dev)
+        self.o_flags = torch.empty(S, C, dtype=torch.uint8, device=dev)
+        self.o_ss = torch.empty(S, 2, dtype=torch.float64, device=dev)
+
+    def step(self):
+        self.eng.plan_batch_dev(self.tp, self.to, self.tn, best_idx=self.o_idx, best_cost=self.o_cost,
+                                best_traj=self.o_traj, costs=self.o_costs, flags=self.o_flags,
+                                steer_speed=self.o_ss)
+
+
+class HostArm:
+    """the public API with pinned HOST buffers: every output the device-resident arm writes"""
+
+    def __init__(self, planner, pinned_empty, poses, opp, n_opp):
+        S, C, M = poses.shape[0], planner.engine.n_candidates, planner.engine.n_samples
+        self.planner = planner
+        self.h_poses = pinned_empty(poses.shape, np.float64); self.h_poses[:] = poses
+        self.h_opp = pinned_empty(opp.shape, np.float64); self.h_opp[:] = opp
+        self.h_nopp = pinned_empty(n_opp.shape, np.int32); self.h_nopp[:] = n_opp
+        self.h_out = {"best_idx": pinned_empty((S,), np.int32), "best_cost": pinned_empty((S,), np.float32),
+                      "best_traj": pinned_empty((S, M, 4), np.float32),
+                      "costs": pinned_empty((S, C), np.float32), "flags": pinned_empty((S, C), np.uint8),
+                      "steer_speed": pinned_empty((S, 2), np.float64)}
+        self.h2d = self.h_poses.nbytes + self.h_opp.nbytes + self.h_nopp.nbytes
+        self.d2h = sum(v.nbytes for v in self.h_out.values())
+
+    def step(self):
+        return self.planner.plan_batch(self.h_poses, self.h_opp, self.h_nopp, out=self.h_out, want_flags=True)
+
+
+def timed(torch, dist, dev, world_size, step, n_steps, wall=False):
+    """barrier + synchronize, n_steps of step(), synchronize + barrier; max over ranks (ms).
+    wall=False: CUDA events on torch's current stream (device-resident arm, launched there);
+    wall=True: host clock around calls that synchronise themselves (host-buffer API)."""
+    torch.cuda.synchronize(dev)
+    if world_size > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    if wall:
+        t0 = time.perf_counter()
+        for _ in range(n_steps):
+            step()
+        torch.cuda.synchronize(dev)
+        ms = 1e3 * (time.perf_counter() - t0)
+    else:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from f1tenth_planning_b200 import LatticePlanner
+    from f1tenth_planning_b200 import LatticePlanner, sharding
     from f1tenth_planning_b200.engine import Engine, pinned_empty
 
     rank = int(os.environ.get("RANK", "0"))
@@ -423,6 +544,9 @@ def run_ours(args):
                            "(use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: run on the CPUs of the GPU's NUMA node before any pinned buffer exists
+    # (first touch places the result buffers there; 8 ranks otherwise share one socket's memory)
+    numa_node = sharding.bind_host_numa(local) if world_size > 1 else None
     if world_size > 1:
         # NCCL prints its version banner on stdout at VERSION level; keep stdout to the JSON line
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -447,28 +571,16 @@ def run_ours(args):
     eng.set_grid(*grid)
     eng.set_goal_grid(la, wd)
     C, M = eng.n_candidates, eng.n_samples
-    fp32_peak, mufu_peak = eng.measure_peaks()
-
-    # ---- device-resident arm -------------------------------------------------------------------
-    tp = torch.from_numpy(poses).to(dev)
-    to = torch.from_numpy(opp).to(dev)
-    tn = torch.from_numpy(n_opp).to(dev)
-    o_idx = torch.empty(S, dtype=torch.int32, device=dev)
-    o_cost = torch.empty(S, dtype=torch.float32, device=dev)
-    o_traj = torch.empty(S, M, 4, dtype=torch.float32, device=dev)
-    o_costs = torch.empty(S, C, dtype=torch.float32, device=dev)
-    o_flags = torch.empty(S, C, dtype=torch.uint8, device=dev)
-    o_ss = torch.empty(S, 2, dtype=torch.float64, device=dev)
-
-    def step():
-        eng.plan_batch_dev(tp, to, tn, best_idx=o_idx, best_cost=o_cost, best_traj=o_traj,
-                           costs=o_costs, flags=o_flags, steer_speed=o_ss)
 
     # one nvidia-smi process on rank 0 watches every GPU of the job (eight concurrent ones on an
     # 8-GPU box took longer to start than the whole run and returned no rows)
     sampler = ClockSampler(",".join(str(i) for i in range(world_size)) if world_size > 1 else local)
     if rank == 0:
         sampler.start()
+
+    # ---- device-resident arm -------------------------------------------------------------------
+    arm = DeviceArm(torch, dev, eng, poses, opp, n_opp)
+    step = arm.step
     n_warm, t_warm = 0, time.time()
     # warm-up goes on (GPU under load) until the sampler has delivered its first row, 10 s at most
     while n_warm < max(args.warmup, 3) or (rank == 0 and sampler.proc is not None and not sampler.rows
@@ -478,65 +590,60 @@ def run_ours(args):
         if n_warm % 4 == 0:
             torch.cuda.synchronize(dev)
     torch.cuda.synchronize(dev)
-    eng.set_timing(True)
-    if world_size > 1:
-        dist.barrier()
+    # roofline denominators, measured with the GPU warm and the clock sampler running: the FFMA /
+    # MUFU microbenchmarks of the library (f1l_measure_peaks); clocks of exactly this interval
+    sampler.mark()
+    t_pk = time.time()
+    fp32_peak, mufu_peak = eng.measure_peaks()
+    while time.time() - t_pk < 0.25:      # a few 50 ms sampler rows under the microbenchmark's load
+        fp32_peak = max(fp32_peak, eng.measure_peaks()[0])
+    peak_clocks = sampler.window() if rank == 0 else None
+    step()
     torch.cuda.synchronize(dev)
+    eng.set_timing(True)
     sampler.mark()
     l0 = eng.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize(dev)
-    if world_size > 1:
-        dist.barrier()
+    ms_total = timed(torch, dist, dev, world_size, step, args.steps)
     launches = eng.launch_count - l0
-    clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.window() if rank == 0 else None
     k_sample, k_eval, k_select, n_timed = eng.mean_kernel_ms()
     eval_shape = eng.last_eval_shape()   # the template instance the timed steps launched
     eng.set_timing(False)
-    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world_size > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_total = float(t_ms.item())
     value = world_size * S * C * args.steps / (ms_total * 1e-3)
 
-    flags = o_flags.cpu().numpy()
+    flags = arm.o_flags.cpu().numpy()
     seg_steps, seg_cands = eng.stats()
     # window segments each valid candidate was tested against (= W unless --prune 1)
     w_eff = seg_steps / seg_cands if seg_cands else float(PLAN_CFG["window"])
     step_flops, valid_frac, mean_passes = work_flops(flags, M, w_eff, float(n_opp.mean()))
     achieved_tflops = step_flops / (k_eval * 1e-3) / 1e12 if k_eval > 0 else None
+    # the same without the work the kernel mostly skips: the 16 P M grid-probe FLOPs (a clearance
+    # lookup proves most footprints free) and the 6 K M opponent broad-phase FLOPs (candidate-level
+    # prune) -- the conservative reading of the roofline fraction
+    n_full = int(((flags & 1) != 0).sum())
+    skippable = n_full * M * (16.0 * F.P_PROBES + 6.0 * float(n_opp.mean()))
+    achieved_noskip = (step_flops - skippable) / (k_eval * 1e-3) / 1e12 if k_eval > 0 else None
     mufu_ops = float((flags >> 4).astype(np.float64).sum()) * (2 * F.Q_NEWTON + 1) + flags.size * 5.0 * M
 
     # ---- side measurement: the same step with prune_window = 1 (bit-identical costs) ------------
     pruned = None
     if world_size == 1 and not args.no_extras and not args.prune:
-        costs_full = o_costs.clone()
+        costs_full = arm.o_costs.clone()
         eng.configure(prune_window=1)
         for _ in range(3):
             step()
         torch.cuda.synchronize(dev)
         eng.stats()
         eng.set_timing(True)
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record()
-        for _ in range(args.steps):
-            step()
-        p1.record()
-        torch.cuda.synchronize(dev)
+        p_ms = timed(torch, dist, dev, 1, step, args.steps) / args.steps
         _, pk_eval, _, _ = eng.mean_kernel_ms()
         eng.set_timing(False)
         ps, pc = eng.stats()
-        p_ms = p0.elapsed_time(p1) / args.steps
         p_flops, _, _ = work_flops(flags, M, ps / max(pc, 1), float(n_opp.mean()))
         pruned = {"candidates_per_s": S * C / (p_ms * 1e-3), "ms_per_step": p_ms, "eval_kernel_ms": pk_eval,
                   "window_segments_tested_mean": ps / max(pc, 1),
                   "executed_tflops": p_flops / (pk_eval * 1e-3) / 1e12,
-                  "costs_bit_identical_to_full_scan": bool(torch.equal(o_costs, costs_full))}
+                  "costs_bit_identical_to_full_scan": bool(torch.equal(arm.o_costs, costs_full))}
         eng.configure(prune_window=0)
         step()
         torch.cuda.synchronize(dev)
@@ -546,31 +653,38 @@ def run_ours(args):
     planner = LatticePlanner(waypoints=track, device=local, **PLAN_CFG)
     planner.set_map(*grid)
     planner.set_goal_grid(la, wd)
-    h_poses = pinned_empty(poses.shape, np.float64); h_poses[:] = poses
-    h_opp = pinned_empty(opp.shape, np.float64); h_opp[:] = opp
-    h_nopp = pinned_empty(n_opp.shape, np.int32); h_nopp[:] = n_opp
-    h_out = {"best_idx": pinned_empty((S,), np.int32), "best_cost": pinned_empty((S,), np.float32),
-             "best_traj": pinned_empty((S, M, 4), np.float32),
-             "costs": pinned_empty((S, C), np.float32),
-             "steer_speed": pinned_empty((S, 2), np.float64)}
+    host = HostArm(planner, pinned_empty, poses, opp, n_opp)
     for _ in range(2):
-        planner.plan_batch(h_poses, h_opp, h_nopp, out=h_out)
-    if world_size > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
+        host.step()
     e2e_steps = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        r = planner.plan_batch(h_poses, h_opp, h_nopp, out=h_out)
-    torch.cuda.synchronize(dev)
-    t_e2e = time.perf_counter() - t0
-    t_e = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    t_e2e = timed(torch, dist, dev, world_size, host.step, e2e_steps, wall=True) * 1e-3
+    e2e_value = world_size * S * C * e2e_steps / t_e2e
+    assert np.array_equal(host.h_out["best_idx"], arm.o_idx.cpu().numpy()), "e2e and device-resident arms disagree"
+    assert np.array_equal(host.h_out["flags"], flags), "e2e and device-resident arms disagree (flags)"
+
+    # ---- strong scaling (BASELINE config 4 as written): the 10^5 scenarios of rank 0's set split
+    #      into contiguous blocks over the ranks, same two arms --------------------------------------
+    strong = None
     if world_size > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_value = world_size * S * C * e2e_steps / float(t_e.item())
-    assert np.array_equal(r.best_idx, o_idx.cpu().numpy()), "e2e and device-resident arms disagree"
-    h2d = h_poses.nbytes + h_opp.nbytes + h_nopp.nbytes
-    d2h = sum(v.nbytes for v in h_out.values())
+        _, _, _, _, poses0, opp0, n_opp0 = workload(0, S)
+        lo, hi = sharding.block(S, rank, world_size)
+        sarm = DeviceArm(torch, dev, eng, poses0[lo:hi].copy(), opp0[lo:hi].copy(), n_opp0[lo:hi].copy())
+        for _ in range(3):
+            sarm.step()
+        s_ms = timed(torch, dist, dev, world_size, sarm.step, args.steps) / args.steps
+        shost = HostArm(planner, pinned_empty, poses0[lo:hi], opp0[lo:hi], n_opp0[lo:hi])
+        for _ in range(2):
+            shost.step()
+        s_e2e = timed(torch, dist, dev, world_size, shost.step, e2e_steps, wall=True) * 1e-3 / e2e_steps
+        one_gpu_ms = ms_total / args.steps          # 10^5 scenarios on ONE GPU: this run's weak step
+        strong = {"scaling": "strong", "scenarios_total": S, "scenarios_per_rank": hi - lo,
+                  "value": S * C / (s_ms * 1e-3), "unit": UNIT, "ms_per_step": s_ms,
+                  "one_gpu_ms_per_step_same_run": one_gpu_ms,
+                  "efficiency_vs_one_gpu_same_run": one_gpu_ms / (world_size * s_ms),
+                  "e2e": {"value": S * C / s_e2e, "unit": UNIT, "h2d_bytes_per_step": shost.h2d,
+                          "d2h_bytes_per_step": shost.d2h,
+                          "efficiency_vs_one_gpu_same_run": (t_e2e / e2e_steps) / (world_size * s_e2e)}}
+        del sarm, shost
 
     sharded = None
     if world_size > 1 and not args.no_extras:
@@ -579,6 +693,8 @@ def run_ours(args):
         except Exception as e:   # the headline line must not depend on the side measurement
             sharded = {"c5_sharded_error": "%s: %s" % (type(e).__name__, e)}
 
+    if rank == 0:
+        sampler.stop()
     if rank != 0:
         if world_size > 1:
             dist.destroy_process_group()
@@ -596,15 +712,23 @@ def run_ours(args):
                         "kappa_max off (every converged candidate does the full cost+collision work)"
                         % (S, S * C, M, PLAN_CFG["window"], args.prune, w_eff, K_OPP),
             "track": "ellipse N=2000 a=80 b=40", "grid": "3400x1800 @0.05 m",
-            "valid_frac": valid_frac, "newton_passes_mean": mean_passes, "feasible_frac": float(np.isfinite(o_costs.cpu().numpy()).mean()),
+            "valid_frac": valid_frac, "newton_passes_mean": mean_passes,
+            "feasible_frac": float(np.isfinite(arm.o_costs.cpu().numpy()).mean()),
             "l2": "per-step working set %.0f MB > 126 MB L2 (outputs rewritten every step); no explicit flush"
                   % ((hbm_bytes + S * C * 4) / 1e6),
+            "host_numa_node": numa_node,
         },
         "roofline": {
             "bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": achieved_tflops / fp32_peak if achieved_tflops else None,
-            "peak_source": "FFMA microbenchmark measured in this run (f1l_measure_peaks); "
+            "peak_source": "FFMA microbenchmark measured in this run with the GPU warm "
+                           "(f1l_measure_peaks, best of the launches in a 0.25 s window); "
                            "MEASURED_PEAKS.json has no FP32 entry; nominal 74.4",
+            "peak_clocks": peak_clocks,
+            # conservative reading: grid-probe and opponent broad-phase FLOPs of the model left out
+            # (the clearance map / candidate-level prune skip nearly all of them)
+            "achieved_without_skippable_flops": achieved_noskip,
+            "frac_without_skippable_flops": achieved_noskip / fp32_peak if achieved_noskip else None,
             "kernel": eval_shape["name"], "kernel_plan": eval_shape, "kernel_ms": k_eval, "kernel_launches_timed": n_timed,
             "kernel_share_of_step": k_eval / (ms_total / args.steps) if k_eval else None,
             "flops_per_launch": step_flops,
@@ -615,19 +739,23 @@ def run_ours(args):
                      "frac": mufu_ops / (k_eval * 1e-3) / 1e9 / mufu_peak if (k_eval > 0 and mufu_peak) else None},
             "mufu_peak_gops": mufu_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one eval_kernel launch of this workload
-            # (ncu --set full; profiles/r1_eval_kernel.md) -- bench.py cannot run under ncu itself
+            # (ncu --set full; profiles/) -- bench.py cannot run under ncu itself
             "traffic": profiled_dram_bytes() if (S == S_PER_GPU and not args.prune) else None,
-            "traffic_source": "profiles/r1_eval_kernel.md",
+            "traffic_source": PROFILE_MD,
             "hbm": {"algorithmic_bytes_per_step": hbm_bytes,
                     "achieved_gbs": hbm_bytes / (ms_total / args.steps * 1e-3) / 1e9},
         },
         "kernels_ms": {"sample": k_sample, "eval": k_eval, "select": k_select},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "api": "LatticePlanner.plan_batch (pinned host buffers)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d,
+                "d2h_bytes_per_step": host.d2h, "steps": e2e_steps,
+                "d2h_gbs_per_gpu": host.d2h / (t_e2e / e2e_steps) / 1e9,
+                "api": "LatticePlanner.plan_batch (pinned host buffers; every output of the "
+                       "device-resident arm, flags included)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if strong is not None:
+        line["strong"] = strong
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             mp = json.load(f)
@@ -639,13 +767,13 @@ def run_ours(args):
     if world_size == 1 and not args.no_cpu_baseline:
         v, n, th, dt = cpu_reference_rate(track, grid, la, wd, poses, opp, n_opp, seconds=12.0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": th, "kind": "port",
-                                "sample": "%d of the %d scenarios (x%d candidates), %.1f s, C oracle "
+                                "sample": "the first %d of the %d scenarios (x%d candidates), %.1f s, C oracle "
                                           "(oracle/c/f1o.c) with OpenMP over scenarios" % (n, S, C, dt)}
     if sharded is not None:
         line["extra"] = sharded
     if world_size == 1 and not args.no_extras:
         try:
-            line["extra"] = extras(track, grid, local)
+            line["extra"] = extras(track, grid, local, fp32_peak)
         except Exception as ex:  # side measurements must not lose the headline
             line["extra"] = {"error": repr(ex)}
         if pruned is not None:

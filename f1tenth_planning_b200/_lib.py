@@ -98,6 +98,7 @@ SIGNATURES = {
     "f1l_set_timing": (C.c_int, [_vp, C.c_int]),
     "f1l_last_kernel_ms": (C.c_int, [_vp, _fp, _fp, _fp]),
     "f1l_mean_kernel_ms": (C.c_int, [_vp, _fp, _fp, _fp, C.POINTER(C.c_int)]),
+    "f1l_bind_host_numa": (C.c_int, [C.c_int]),
     "f1l_measure_peaks": (C.c_int, [_vp, _dp, _dp]),
     "f1l_measure_peaks_ex": (C.c_int, [_vp, _dp, C.c_int]),
     "f1l_debug_query_ctx": (C.c_int, [_vp, _fp, _ip]),

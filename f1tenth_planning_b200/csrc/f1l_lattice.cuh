@@ -545,7 +545,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
             ce.nx = ip.found ? (float)(-sp_) : 0.0f;
             ce.ny = ip.found ? (float)cp_ : 0.0f;
             ce.v = (float)a.tr.v[r];
-            ce.ok = ip.found ? 1.0f : 0.0f;
+            ce.ok = ip.found ? (float)(r + 1) : 0.0f;   // centre waypoint index + 1 (exact: < 2^24)
             a.centres[(size_t)s * a.nL + j] = ce;
         }
     }
@@ -1350,6 +1350,15 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(SelectArgs a) {
     bool have_centre;
     candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.inv_nW, a.C, s, idx,
                    a.ep.use_goal_kappa != 0, gx, gy, gth, p3, have_centre, v_ref);
+    // speed column / tracker speed: the raceline speed at the goal centre, read back in float64
+    // from the waypoint the sampler chose (pure_pursuit.py:78 returns waypoints[i, 2] itself);
+    // explicit goals have no centre: the ego speed
+    double v_goal = q->vel;
+    if (!a.goals && a.tr.ncols > 2) {
+        const int row = __float2int_rd(((float)idx + 0.5f) * a.inv_nW);
+        const int wp = (int)a.centres[(size_t)s * a.nL + row].ok - 1;
+        if (wp >= 0) v_goal = a.tr.v[wp];
+    }
     SpiralF sp;
     generate_spiral(sp, a.lut, a.ep, gx, gy, gth, p3, lane);
     float x[IPL], y[IPL], th[IPL], kp[IPL], cs[IPL], sn[IPL];
@@ -1370,7 +1379,7 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(SelectArgs a) {
         // goal centre (explicit goals: the ego speed), in float64 from the float32 states
         double sth, cth;
         sincos(q->th, &sth, &cth);
-        const double v_col = v_ref >= 0.0f ? (double)v_ref : q->vel;
+        const double v_col = v_goal;
 #pragma unroll
         for (int j = 0; j < IPL; ++j) {
             const int i = lane * IPL + j;
@@ -1426,8 +1435,7 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(SelectArgs a) {
         const double2 p0 = acc(bi), p1 = acc(bi + 1);
         double ux, uy, d, t;
         nearest_segment64(qx, qy, p0.x, p0.y, p1.x, p1.y, ux, uy, d, t);
-        const double v_track = literal ? (double)s_traj[bi].z
-                                       : (v_ref >= 0.0f ? (double)v_ref : q->vel);
+        const double v_track = literal ? (double)s_traj[bi].z : v_goal;
         double lx = 0.0, ly = 0.0;
         if (d < L) {                                        // pure_pursuit.py:70
             const Intersect64 ip = intersect_point_warp(acc, M, qx, qy, L, (double)bi + t, true,

@@ -71,3 +71,12 @@ def gather_stats(values, group=None):
     dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(m, op=dist.ReduceOp.MAX, group=group)
     return s.cpu().numpy(), m.cpu().numpy()
+
+
+def bind_host_numa(device):
+    """One process per GPU: pin this process to the CPUs of the GPU's NUMA node BEFORE allocating
+    pinned host buffers (first touch then places them on that node).  Returns the node, or None
+    when the platform exposes no placement (f1l_bind_host_numa)."""
+    from . import _lib
+    node = _lib.lib().f1l_bind_host_numa(int(device))
+    return node if node >= 0 else None

@@ -332,6 +332,13 @@ int f1l_mean_kernel_ms(f1l_handle h, float* sample_ms, float* eval_ms, float* se
                        int* n_launches);
 int f1l_last_kernel_ms(f1l_handle h, float* sample_ms, float* eval_ms, float* select_ms);
 
+/* Host placement for multi-GPU batches (one process per GPU): sets the calling thread's CPU
+ * affinity to the CPUs of the NUMA node the device's PCIe root hangs off (sysfs), so that pinned
+ * host buffers allocated afterwards are first-touched on that node and the result copies of the
+ * ranks do not all cross the socket interconnect.  Returns the node (>= 0), -100 when the platform
+ * exposes no NUMA placement (nothing changed), or F1L_ERR_NO_DEVICE.  No handle needed. */
+int f1l_bind_host_numa(int device);
+
 /* FP32 FMA / MUFU pipe peak microbenchmarks (roofline denominators):
  * returns achieved TFLOP/s (FMA = 2 FLOP) and MUFU Gop/s on the handle's device. */
 int f1l_measure_peaks(f1l_handle h, double* fp32_tflops, double* mufu_gops);
