@@ -52,6 +52,8 @@ def parse():
                          "segments, the SURVEY FLOP model; 1: provably-far segments skipped)")
     ap.add_argument("--no-extras", action="store_true", help="skip the C2/C3/C5 side measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true",
+                    help="kernel A/B runs: device-resident arm only, prints a short JSON line")
     return ap.parse_args()
 
 
@@ -611,8 +613,25 @@ def run_ours(args):
     eng.set_timing(False)
     value = world_size * S * C * args.steps / (ms_total * 1e-3)
 
+    if args.quick:
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps({"quick": True, "value": value, "ms_per_step": ms_total / args.steps,
+                              "kernels_ms": {"sample": k_sample, "eval": k_eval, "select": k_select},
+                              "kernel": eval_shape["name"], "fp32_peak": fp32_peak, "clocks": clocks,
+                              "checksum": float(arm.o_costs[torch.isfinite(arm.o_costs)].double().sum().item()),
+                              "best_idx_sum": int(arm.o_idx.long().sum().item())}), flush=True)
+        if world_size > 1:
+            dist.destroy_process_group()
+        return
     flags = arm.o_flags.cpu().numpy()
+    # work counters of the deviation pass from one extra, untimed step (counting is off in the
+    # timed ones: it costs every CTA a barrier and two global atomics)
+    eng.set_stats(True)
+    step()
+    torch.cuda.synchronize(dev)
     seg_steps, seg_cands = eng.stats()
+    eng.set_stats(False)
     # window segments each valid candidate was tested against (= W unless --prune 1)
     w_eff = seg_steps / seg_cands if seg_cands else float(PLAN_CFG["window"])
     step_flops, valid_frac, mean_passes = work_flops(flags, M, w_eff, float(n_opp.mean()))
@@ -633,12 +652,15 @@ def run_ours(args):
         for _ in range(3):
             step()
         torch.cuda.synchronize(dev)
-        eng.stats()
         eng.set_timing(True)
         p_ms = timed(torch, dist, dev, 1, step, args.steps) / args.steps
         _, pk_eval, _, _ = eng.mean_kernel_ms()
         eng.set_timing(False)
+        eng.set_stats(True)
+        step()
+        torch.cuda.synchronize(dev)
         ps, pc = eng.stats()
+        eng.set_stats(False)
         p_flops, _, _ = work_flops(flags, M, ps / max(pc, 1), float(n_opp.mean()))
         pruned = {"candidates_per_s": S * C / (p_ms * 1e-3), "ms_per_step": p_ms, "eval_kernel_ms": pk_eval,
                   "window_segments_tested_mean": ps / max(pc, 1),

@@ -87,6 +87,7 @@ SIGNATURES = {
     "f1l_intersect_point_batch": (C.c_int, [_vp, _dp, _dp, C.c_int, C.c_double, C.c_int, _dp,
                                             _ip]),
     "f1l_get_actuation_batch": (C.c_int, [_vp, _dp, C.c_int, C.c_double, _dp]),
+    "f1l_set_stats": (C.c_int, [_vp, C.c_int]),
     "f1l_get_stats": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int]),
     "f1l_last_eval_shape": (C.c_int, [_vp, _ip, C.c_int]),
     "f1l_plan_rows": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(PlanResult)]),

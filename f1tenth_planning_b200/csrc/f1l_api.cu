@@ -80,8 +80,9 @@ struct f1l_ctx {
     DevBuf q_detail;
     void* h_detail = nullptr;
     size_t h_detail_cap = 0;
-    // deviation-pass work counters (f1l_get_stats)
+    // deviation-pass work counters (f1l_set_stats / f1l_get_stats)
     DevBuf stats;
+    int stats_on = 0;
     // batch (device-pointer API) scratch
     DevBuf b_ctx, b_centres, b_best, b_near_i, b_near4;
     // batch pipeline (host-pointer API)
@@ -366,14 +367,13 @@ void launch_pp(const TrackView& tv, cudaStream_t stream, const double* poses, in
         tv, poses, pose_stride, n_poses, L, wb, max_reacquire, front_axle, k_path, key, o);
 }
 
-size_t eval_smem_bytes(int nseg_pad, int warps, int M) {
+size_t eval_smem_bytes(int nseg_pad, int warps, int M) {   // mirrors EvalSmem (f1l_lattice.cuh)
     const EvalShape sh = eval_shape(M);
-    size_t b = (size_t)(nseg_pad + EVAL_SEG_PAD) * (2 * sizeof(float4));
-    b += (size_t)warps * 2 * (((sh.s + 1) / 2) * sh.sg * 2) * sizeof(float);   // pair-layout slabs
-    b += (size_t)warps * 2 * (sh.s * sh.sg) * sizeof(float4);                  // grid-probe lists
-    b += (size_t)warps * 8 * sizeof(float4);                                   // item solutions
+    const size_t pcap = (size_t)sh.s * sh.sg, slab = (size_t)((sh.s + 1) / 2) * sh.sg * 2;
+    size_t b = (size_t)warps * (pcap * 32 + 128 + 2 * slab * 4);               // per-warp blocks
+    b += F1L_MAX_OPP * sizeof(float4) + 48;                                    // opponents, grid constants
     b += (size_t)F1L_MAX_M * sizeof(float);                                    // previous path
-    b += F1L_MAX_OPP * sizeof(float4);
+    b += (size_t)(nseg_pad + EVAL_SEG_PAD) * (2 * sizeof(float4));             // window table
     return b;
 }
 
@@ -532,7 +532,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     ea.states = o.states;
     ea.headings = o.headings;
     ea.best = best;
-    ea.stats = (unsigned long long*)h->stats.p;
+    ea.stats = h->stats_on ? (unsigned long long*)h->stats.p : nullptr;
     const long long n_ctas = (long long)S * ea.ctas_per_scn;
     if (n_ctas > 0x7fffffffLL) return F1L_ERR_TOO_LARGE;
     if (!o.empty_shard) eval_entry(M, wpc)<<<(unsigned)n_ctas, wpc * 32, smem, stream>>>(ea);
@@ -641,6 +641,13 @@ int f1l_get_stats(f1l_handle h, uint64_t* out, int n) {
     CK(cudaMemset(h->stats.p, 0, sizeof(v)));
     out[0] = v[0];
     out[1] = v[1];
+    return F1L_OK;
+}
+
+int f1l_set_stats(f1l_handle h, int on) {
+    if (!h) return F1L_ERR_INVALID_ARG;
+    h->stats_on = on != 0;
+    h->epoch++;   // a kernel argument of the captured graph
     return F1L_OK;
 }
 

@@ -414,6 +414,41 @@ __device__ __forceinline__ float fmin3(float a, float b, float c) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// shared memory through explicit 32-bit shared-space addresses.  Under register pressure nvcc
+// re-derives the address of every shared access from scratch (S2R SR_CgaCtaId + MOV + IADD3 + LEA
+// for the window base, S2R SR_TID.X + shifts for the lane part: ~250 of eval_kernel's ~1400
+// warp-instructions per candidate outside its hot loop, 4 of 135 inside it).  An address that went
+// through `opaque()` cannot be rematerialised: it stays in its register (or is spilled and comes
+// back with one LDL).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void opaque(uint32_t& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void opaque(int& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ f32x2 lds64(uint32_t a) {
+    f32x2 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 // warp helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -837,6 +837,31 @@ __device__ __forceinline__ void seg_min2(const f32x2 (&sx2)[SP], const f32x2 (&s
     }
 }
 
+// Shared-memory layout of eval_kernel (bytes; the host's eval_smem_bytes mirrors it).  Per warp one
+// contiguous block -- list of the footprints that need their nine grid probes (centre and half-axes
+// in grid-cell coordinates, two float4 per entry) | solutions of the four candidates of an item
+// ((gx, gy, gth, p3), (p1, p2, sf, have | passes)) | sample slab x | sample slab y, in the pair
+// layout of the deviation pass: element (j, sg, half) holds sample (2j + half) * SG + sg, so that
+// one 64-bit load yields a packed pair of samples -- then the CTA-wide part: opponents | grid
+// constants | previous path | window table (run-time length, last).  Everything sits at a
+// compile-time offset from two addresses, the CTA's base and the warp's block.
+template <int S, int SG, int NW>
+struct EvalSmem {
+    static constexpr int PCAP = S * SG;
+    static constexpr int SROWS = (S + 1) / 2;
+    static constexpr int SLAB = SROWS * SG * 2;                    // floats per coordinate
+    static constexpr uint32_t W_PLIST = 0;                         // [PCAP][2] float4
+    static constexpr uint32_t W_ITEM = W_PLIST + PCAP * 32;        // [4][2] float4
+    static constexpr uint32_t W_SLABX = W_ITEM + 128;              // [SLAB] float
+    static constexpr uint32_t W_SLABY = W_SLABX + SLAB * 4;
+    static constexpr uint32_t W_BYTES = W_SLABY + SLAB * 4;
+    static constexpr uint32_t C_OPP = NW * W_BYTES;                // [F1L_MAX_OPP] float4
+    static constexpr uint32_t C_GRID = C_OPP + F1L_MAX_OPP * 16;   // 3 float4: A, (fx, fy, ix0, iy0), (n_opp, has_grid)
+    static constexpr uint32_t C_PREV = C_GRID + 48;                // [F1L_MAX_M] float
+    static constexpr uint32_t C_TAB = C_PREV + F1L_MAX_M * 4;      // [ntab][2] float4
+    static_assert(W_BYTES % 16 == 0, "per-warp block keeps 16-byte alignment");
+};
+
 // One CTA per (scenario, candidate chunk).  The CTA builds the scenario's raceline window once,
 // then its NW warps pull candidates of the chunk from a shared counter until it is exhausted
 // (warps that finish an early-exit candidate immediately take the next one).
@@ -844,36 +869,30 @@ template <int IPL, int S, int SG, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
     constexpr int GG = 32 / SG;
     constexpr int kSegUnroll = EVAL_SEG_UNROLL;
+    using L = EvalSmem<S, SG, NW>;
     extern __shared__ __align__(16) unsigned char ev_smem[];
     __shared__ int s_next;
     __shared__ unsigned long long s_work;   // deviation pass: candidates << 40 | (candidate, segment) pairs
-    __shared__ float s_gf[6];
-    __shared__ int s_gi[4];
     const int M = a.ep.M;
     const int ntab = a.nseg_pad + EVAL_SEG_PAD;
-    // Dynamic shared memory.  Everything of compile-time size comes first, at constant offsets --
-    // with the window table (run-time size) in front, the addresses of all the per-warp areas
-    // were re-derived inside the candidate loop: 8 % of the kernel's instructions.
-    // per-warp list of the footprints that need their nine grid probes: centre and half-axes
-    // in grid-cell coordinates, two float4 per entry
-    constexpr int PCAP = S * SG;
-    float4* plist_all = reinterpret_cast<float4*>(ev_smem);                             // [NW][PCAP][2]
-    // per-warp solutions of the four candidates of an item: (gx, gy, gth, p3), (p1, p2, sf, have | passes)
-    float4* item_all = plist_all + NW * 2 * PCAP;                                       // [NW][4][2]
-    float4* sopp = item_all + NW * 8;                                                   // [F1L_MAX_OPP]
-    // per-warp sample slab in the pair layout of the deviation pass: element (j, sg, half) holds
-    // sample (2j + half) * SG + sg, so that one 64-bit load yields a packed pair of samples
-    constexpr int SROWS = (S + 1) / 2;
-    constexpr int SLAB = SROWS * SG * 2;                                     // floats per coordinate
-    float* slab_all = reinterpret_cast<float*>(sopp + F1L_MAX_OPP);          // [NW][2][SLAB]
-    float* sprev = slab_all + NW * 2 * SLAB;                                 // [F1L_MAX_M]
-    // window table, two float4 per segment: T0 = (ux, uy, -uy, 1/len), T1 = (-(a.u + h), -a.n, -h, 0)
-    float4* sT = reinterpret_cast<float4*>(sprev + F1L_MAX_M);               // [2 * ntab]
+    constexpr int PCAP = L::PCAP;
+    constexpr int SLAB = L::SLAB;
 
     int s, cta;
     if (a.ctas_per_scn == 1) { s = blockIdx.x; cta = 0; }
     else { s = blockIdx.x / a.ctas_per_scn; cta = blockIdx.x - s * a.ctas_per_scn; }
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int tid = threadIdx.x, wid = tid >> 5;
+    // The three values every shared access and every guard below derives from.  They go through
+    // opaque() so that the compiler keeps (or spills) them instead of re-deriving each one at
+    // every use from S2R / SR_CgaCtaId -- see f1l_common.cuh.
+    int lane = tid & 31;
+    uint32_t cbase = smem_u32(ev_smem);            // the CTA's dynamic shared memory
+    uint32_t wbase = cbase + wid * L::W_BYTES;     // this warp's block
+    int nown = min(max(M - lane * IPL, 0), IPL);   // samples [lane * IPL, lane * IPL + nown) exist
+    opaque(lane);
+    opaque(cbase);
+    opaque(wbase);
+    opaque(nown);
     const QueryCtx* __restrict__ q = a.ctx + s;
     const int cb = a.c_begin + cta * a.chunk;
     const int ce = min(cb + a.chunk, a.c_end);
@@ -912,40 +931,43 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 T1 = make_float4(-fmaf(avx, ux, avy * uy), -fmaf(avy, ux, -avx * uy), -(l2 * il), 0.0f);
 #endif
             }
-            sT[2 * k] = T0;
-            sT[2 * k + 1] = T1;
+            sts128(cbase + L::C_TAB + k * 32, T0);
+            sts128(cbase + L::C_TAB + k * 32 + 16, T1);
         }
         if (a.prev_theta) {
 #pragma unroll 1
-            for (int i = tid; i < M; i += NW * 32) sprev[i] = a.prev_theta[i];
+            for (int i = tid; i < M; i += NW * 32) sts32(cbase + L::C_PREV + i * 4, a.prev_theta[i]);
         }
-        if (tid < F1L_MAX_OPP) sopp[tid] = q->opp[tid];
+        if (tid < F1L_MAX_OPP) sts128(cbase + L::C_OPP + tid * 16, q->opp[tid]);
         if (tid == 0) { s_next = cb + NW * a.item; s_work = 0ull; }
         // per-scenario collision constants live in shared memory, not in registers, so that the
         // candidate loop does not carry them through the deviation pass
         if (tid == 32 % (NW * 32)) {
-            s_gf[0] = q->gA00; s_gf[1] = q->gA01; s_gf[2] = q->gA10; s_gf[3] = q->gA11;
-            s_gf[4] = q->gfx; s_gf[5] = q->gfy;
-            s_gi[0] = q->gix; s_gi[1] = q->giy; s_gi[2] = q->n_opp; s_gi[3] = q->has_grid;
+            sts128(cbase + L::C_GRID, make_float4(q->gA00, q->gA01, q->gA10, q->gA11));
+            sts128(cbase + L::C_GRID + 16, make_float4(q->gfx, q->gfy, __int_as_float(q->gix), __int_as_float(q->giy)));
+            sts128(cbase + L::C_GRID + 32, make_float4(__int_as_float(q->n_opp), __int_as_float(q->has_grid), 0.0f, 0.0f));
         }
     }
     __syncthreads();
 
-    float* slab_x = slab_all + (size_t)wid * (2 * SLAB);
-    float* slab_y = slab_x + SLAB;
 #pragma unroll 1
     for (int i = M + lane; i < S * SG; i += 32) {   // unused slots of the last rows: finite dummies
         const int r = i / SG, g = i - r * SG;
-        slab_x[((r >> 1) * SG + g) * 2 + (r & 1)] = 0.0f;
-        slab_y[((r >> 1) * SG + g) * 2 + (r & 1)] = 0.0f;
+        const uint32_t at = (uint32_t)(((r >> 1) * SG + g) * 2 + (r & 1)) * 4;
+        sts32(wbase + L::W_SLABX + at, 0.0f);
+        sts32(wbase + L::W_SLABY + at, 0.0f);
     }
+    // deviation pass: this lane's sample group / segment group, and how many of the group's S
+    // sample rows exist (row r holds sample r * SG + sgi; rows are valid from the front)
+    const int sgi = lane / GG, ggi = lane - sgi * GG;
+    int nrows = min(max((M - sgi + SG - 1) / SG, 0), S);
+    opaque(nrows);
 
     // A warp takes `item` consecutive candidates at a time.  With item = 4 their goals, LUT seeds
     // and Newton solves run together, one candidate per 8-lane group (spiral_newton_g8); the rest
     // of the pipeline then handles the four one after the other on the whole warp.
     const int item = a.item;
     for (int c0 = cb + wid * item; c0 < ce;) {
-      float4* isol = item_all + (size_t)wid * 8;
       if (item == 4) {   // warp-uniform
           const int cg = c0 + (lane >> 3);
           const bool active = cg < ce;
@@ -958,9 +980,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
           const int g_pass = generate_cubic_g8(gsp, a.lut, a.ep, ggx, ggy, ggth, gp3, lane, active);
           // through shared memory, not registers: nothing of this lives across the deviation pass
           if ((lane & 7) == 0) {
-              isol[2 * (lane >> 3)] = make_float4(ggx, ggy, ggth, gp3);
-              isol[2 * (lane >> 3) + 1] = make_float4(gsp.p1, gsp.p2, gsp.sf,
-                                                      __int_as_float((ghave ? 256 : 0) | g_pass));
+              const uint32_t ia = wbase + L::W_ITEM + 32 * (lane >> 3);
+              sts128(ia, make_float4(ggx, ggy, ggth, gp3));
+              sts128(ia + 16, make_float4(gsp.p1, gsp.p2, gsp.sf, __int_as_float((ghave ? 256 : 0) | g_pass)));
           }
           __syncwarp();
       }
@@ -973,7 +995,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
         SpiralF sp;
         int n_pass;
         if (item == 4) {   // the solution of candidate c, found by its 8-lane group
-            const float4 G = isol[2 * (v - c0)], Q = isol[2 * (v - c0) + 1];
+            const uint32_t ia = wbase + L::W_ITEM + 32 * (v - c0);
+            const float4 G = lds128(ia), Q = lds128(ia + 16);
             gx = G.x; gy = G.y; gth = G.z; p3 = G.w;
             v_ref = 0.0f;
             const int hp = __float_as_int(Q.w);
@@ -996,42 +1019,45 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
         const size_t cand = (size_t)s * a.C + c;
         if (a.states) {
 #pragma unroll
-            for (int j = 0; j < IPL; ++j) {
-                const int i = lane * IPL + j;
-                if (i < M) a.states[cand * M + i] = make_float4(x[j], y[j], th[j], kp[j]);
-            }
+            for (int j = 0; j < IPL; ++j)
+                if (j < nown) a.states[cand * M + lane * IPL + j] = make_float4(x[j], y[j], th[j], kp[j]);
         }
         if (a.headings) {
 #pragma unroll
-            for (int j = 0; j < IPL; ++j) {
-                const int i = lane * IPL + j;
-                if (i < M) a.headings[cand * M + i] = make_float2(cs[j], sn[j]);
-            }
+            for (int j = 0; j < IPL; ++j)
+                if (j < nown) a.headings[cand * M + lane * IPL + j] = make_float2(cs[j], sn[j]);
         }
 
         // ---- curvature terms, endpoint, validity ----
         float maxk = 0.0f, sumk = 0.0f, ex = 0.0f, ey = 0.0f, eth = 0.0f;
         __syncwarp();   // the previous candidate's deviation pass has finished reading the slab
+        {
+            // slab address of this lane's first sample; when the IPL samples of a lane cannot
+            // straddle a slab row (IPL divides SG) the others follow at 8-byte steps
+            const int i0 = lane * IPL;
+            const int r0 = i0 / SG, g0 = i0 - r0 * SG;
+            const uint32_t wa = wbase + L::W_SLABX + (uint32_t)(((r0 >> 1) * SG + g0) * 2 + (r0 & 1)) * 4;
+            const int last_lane = (M - 1) / IPL, last_j = (M - 1) - last_lane * IPL;   // uniform
 #pragma unroll
-        for (int j = 0; j < IPL; ++j) {
-            const int i = lane * IPL + j;
-            if (i < M) {
-                const float ak = fabsf(kp[j]);
-                maxk = fmaxf(maxk, ak);
-                sumk += ak;
-                {
-                    const int r = i / SG, g = i - r * SG;
-                    const int at = ((r >> 1) * SG + g) * 2 + (r & 1);
-                    slab_x[at] = x[j] * EVAL_DEV_SCALE;
-                    slab_y[at] = y[j] * EVAL_DEV_SCALE;
+            for (int j = 0; j < IPL; ++j) {
+                if (j < nown) {
+                    const float ak = fabsf(kp[j]);
+                    maxk = fmaxf(maxk, ak);
+                    sumk += ak;
+                    uint32_t at = wa + 8 * j;
+                    if constexpr (SG % IPL != 0) {
+                        const int i = i0 + j, r = i / SG, g = i - r * SG;
+                        at = wbase + L::W_SLABX + (uint32_t)(((r >> 1) * SG + g) * 2 + (r & 1)) * 4;
+                    }
+                    sts32(at, x[j] * EVAL_DEV_SCALE);
+                    sts32(at + SLAB * 4, y[j] * EVAL_DEV_SCALE);
                 }
-                if (i == M - 1) { ex = x[j]; ey = y[j]; eth = th[j]; }
+                if (j == last_j) { ex = x[j]; ey = y[j]; eth = th[j]; }   // (uniform predicate)
             }
+            ex = __shfl_sync(F1L_FULL, ex, last_lane);
+            ey = __shfl_sync(F1L_FULL, ey, last_lane);
+            eth = __shfl_sync(F1L_FULL, eth, last_lane);
         }
-        const int last_lane = (M - 1) / IPL;
-        ex = __shfl_sync(F1L_FULL, ex, last_lane);
-        ey = __shfl_sync(F1L_FULL, ey, last_lane);
-        eth = __shfl_sync(F1L_FULL, eth, last_lane);
         maxk = warp_max(maxk);
         sumk = warp_sum(sumk);
         const float gn = sqrtf(fmaf(gx, gx, fmaf(gy, gy, gth * gth)));
@@ -1070,13 +1096,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             bool hit_opp = false, hit_map = false;
             const uint8_t* occ = a.grid.occ;
             const int gw = a.grid.w, gh = a.grid.h;
-            const int n_opp = s_gi[2];
-            const bool has_grid = s_gi[3] != 0;
+            const float4 GA = lds128(cbase + L::C_GRID), GB = lds128(cbase + L::C_GRID + 16);
+            const float4 GC = lds128(cbase + L::C_GRID + 32);
+            const int n_opp = __float_as_int(GC.x);
+            const bool has_grid = __float_as_int(GC.y) != 0;
             const float hl = a.ep.half_l, hw = a.ep.half_w;
-            const float A00 = s_gf[0], A01 = s_gf[1], A10 = s_gf[2], A11 = s_gf[3];
-            const float gfx = s_gf[4], gfy = s_gf[5];
-            const int gix = s_gi[0], giy = s_gi[1];
-            const int lim = M - a.ep.n_shift - a.ep.n_cull;
+            const float A00 = GA.x, A01 = GA.y, A10 = GA.z, A11 = GA.w;
+            const float gfx = GB.x, gfy = GB.y;
+            const int gix = __float_as_int(GB.z), giy = __float_as_int(GB.w);
             const float reach_pad = sqrtf(a.ep.rc2) + 1e-3f;
             // clearance map: clear[cell] = Chebyshev distance (cells) to the nearest occupied /
             // out-of-bounds cell.  All nine probes fall within `probe_reach` cells of the
@@ -1085,9 +1112,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             int clr[IPL];
 #pragma unroll
             for (int j = 0; j < IPL; ++j) {
-                const int i = lane * IPL + j;
                 clr[j] = 0;
-                if (has_grid && a.grid.clear && i < M) {
+                if (has_grid && a.grid.clear && j < nown) {
                     const float ccx = fa(fa(fm(A00, x[j]), fm(A01, y[j])), gfx);
                     const float ccy = fa(fa(fm(A10, x[j]), fm(A11, y[j])), gfy);
                     const int ccol = gix + __float2int_rd(ccx), crow = giy + __float2int_rd(ccy);
@@ -1100,21 +1126,27 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             // farther than s_f/2 + 2 r_circ from it cannot pass the per-sample broad phase.
             unsigned opp_mask;
             {
-                const float4 o = sopp[lane & (F1L_MAX_OPP - 1)];
+                const float4 o = lds128(cbase + L::C_OPP + (lane & (F1L_MAX_OPP - 1)) * 16);
                 const float mx = o.x - 0.5f * ex, my = o.y - 0.5f * ey;
                 const float reach = 0.5f * sp.sf + reach_pad;
                 opp_mask = __ballot_sync(F1L_FULL, lane < n_opp && fmaf(mx, mx, my * my) <= reach * reach);
             }
+            if (a.prev_theta) {   // uniform
+                const int lim = M - a.ep.n_shift - a.ep.n_cull;
 #pragma unroll
-            for (int j = 0; j < IPL; ++j) {
-                const int i = lane * IPL + j;
-                if (i < M) {
-                    if (a.prev_theta && i < lim) {
-                        const float d = th[j] - sprev[i + a.ep.n_shift];
+                for (int j = 0; j < IPL; ++j) {
+                    const int i = lane * IPL + j;
+                    if (i < lim) {
+                        const float d = th[j] - lds32(cbase + L::C_PREV + (i + a.ep.n_shift) * 4);
                         sim = fmaf(d, d, sim);
                     }
-                    for (unsigned m = opp_mask; m; m &= m - 1) {
-                        const float4 o = sopp[__ffs(m) - 1];
+                }
+            }
+            for (unsigned m = opp_mask; m; m &= m - 1) {   // uniform; mostly empty
+                const float4 o = lds128(cbase + L::C_OPP + (__ffs(m) - 1) * 16);
+#pragma unroll
+                for (int j = 0; j < IPL; ++j) {
+                    if (j < nown) {
                         const float tx = fs(o.x, x[j]), ty = fs(o.y, y[j]);
                         const float d2 = fa(fm(tx, tx), fm(ty, ty));
                         if (d2 <= a.ep.rc2 && sat_collide(tx, ty, cs[j], sn[j], o.z, o.w, hl, hw))
@@ -1133,11 +1165,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 int total = 0;
 #pragma unroll
                 for (int j = 0; j < IPL; ++j) {
-                    nm[j] = __ballot_sync(F1L_FULL, lane * IPL + j < M && clr[j] <= a.grid.probe_reach);
+                    nm[j] = __ballot_sync(F1L_FULL, j < nown && clr[j] <= a.grid.probe_reach);
                     total += __popc(nm[j]);
                 }
                 if (total) {   // warp-uniform
-                    float4* pl = plist_all + (size_t)wid * (2 * PCAP);
+                    const uint32_t pl = wbase + L::W_PLIST;
                     int rank0 = 0;
 #pragma unroll
                     for (int j = 0; j < IPL; ++j) {
@@ -1148,10 +1180,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                             const float ccy = fa(fa(fm(A10, x[j]), fm(A11, y[j])), gfy);
                             const float lx = fm(cs[j], hl), ly = fm(sn[j], hl);    // body x axis * hl
                             const float wx = fm(-sn[j], hw), wy = fm(cs[j], hw);   // body y axis * hw
-                            pl[2 * r] = make_float4(ccx, ccy, fa(fm(A00, lx), fm(A01, ly)),
-                                                    fa(fm(A10, lx), fm(A11, ly)));
-                            pl[2 * r + 1] = make_float4(fa(fm(A00, wx), fm(A01, wy)),
-                                                        fa(fm(A10, wx), fm(A11, wy)), 0.0f, 0.0f);
+                            sts128(pl + 32 * r, make_float4(ccx, ccy, fa(fm(A00, lx), fm(A01, ly)),
+                                                            fa(fm(A10, lx), fm(A11, ly))));
+                            sts128(pl + 32 * r + 16, make_float4(fa(fm(A00, wx), fm(A01, wy)),
+                                                                 fa(fm(A10, wx), fm(A11, wy)), 0.0f, 0.0f));
                         }
                         rank0 += __popc(nm[j]);
                     }
@@ -1163,7 +1195,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                     const int nwork = total * 9;
                     for (int w = lane; w < nwork; w += 32) {
                         const int fp = w / 9, p = w - 9 * fp;
-                        const float4 P0 = pl[2 * fp], P1 = pl[2 * fp + 1];
+                        const float4 P0 = lds128(pl + 32 * fp), P1 = lds128(pl + 32 * fp + 16);
                         const float sa = (float)(int)((0x1520au >> (2 * p)) & 3u) - 1.0f;
                         const float sb = (float)(int)((0x12522u >> (2 * p)) & 3u) - 1.0f;
                         hit_map |= grid_hit(occ, gw, gh, gix, giy, fa(fa(P0.x, fm(sa, P0.z)), fm(sb, P1.x)),
@@ -1172,7 +1204,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                     __syncwarp();
                 }
             }
-            t_sim = warp_sum(sim);
+            if (a.prev_theta) t_sim = warp_sum(sim);
             hit_opp = __any_sync(F1L_FULL, hit_opp);
             hit_map = __any_sync(F1L_FULL, hit_map);
             if (hit_opp) flags |= F1L_FLAG_COLLIDE_OPP;
@@ -1194,20 +1226,20 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 // otherwise (1 warp-instruction per clock per scheduler, 9 per sample x segment).
                 constexpr int SP = S / 2;
                 constexpr bool ODD = (S & 1) != 0;
-                const int sgi = lane / GG, ggi = lane - sgi * GG;
                 f32x2 sx2[SP], sy2[SP];
                 float bdx[SP], bdy[SP];
                 float sxl = 0.0f, syl = 0.0f, bdl = CUDART_INF_F;
+                const uint32_t ra = wbase + L::W_SLABX + sgi * 8;
 #pragma unroll
                 for (int j = 0; j < SP; ++j) {
-                    sx2[j] = *reinterpret_cast<const f32x2*>(slab_x + (j * SG + sgi) * 2);
-                    sy2[j] = *reinterpret_cast<const f32x2*>(slab_y + (j * SG + sgi) * 2);
+                    sx2[j] = lds64(ra + j * SG * 8);
+                    sy2[j] = lds64(ra + SLAB * 4 + j * SG * 8);
                     bdx[j] = CUDART_INF_F;
                     bdy[j] = CUDART_INF_F;
                 }
                 if (ODD) {
-                    sxl = slab_x[(SP * SG + sgi) * 2];
-                    syl = slab_y[(SP * SG + sgi) * 2];
+                    sxl = lds32(ra + SP * SG * 8);
+                    syl = lds32(ra + SLAB * 4 + SP * SG * 8);
                 }
                 const int nq = a.nseg_pad;
                 // segment range [k_begin, k_end) of the window this candidate is tested against
@@ -1221,16 +1253,20 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                     // per-sample minimum, hence the cost, bit-identical.  The kept segments are
                     // covered by one index range (the raceline is a curve: normally one run).
                     const float cmx = 0.5f * ex * EVAL_DEV_SCALE, cmy = 0.5f * ey * EVAL_DEV_SCALE;
+                    const uint32_t tb = cbase + L::C_TAB;
                     float dmin = CUDART_INF_F;
                     for (int k = lane; k < nq; k += 32)
-                        dmin = fminf(dmin, seg_dist2(cmx, cmy, sT[2 * k], sT[2 * k + 1]));
+                        dmin = fminf(dmin, seg_dist2(cmx, cmy, lds128(tb + 32 * k), lds128(tb + 32 * k + 16)));
                     dmin = __uint_as_float(__reduce_min_sync(F1L_FULL, __float_as_uint(dmin)));
                     // 1 mm + 0.1 % of slack over the rounding of the FP32 distances and samples
                     const float thr = (fast_sqrt(dmin) + sp.sf * EVAL_DEV_SCALE) * 1.001f + 1e-3f * EVAL_DEV_SCALE;
                     const float thr2 = thr * thr;
                     int lo = nq, hi = -1;
                     for (int k = lane; k < nq; k += 32)
-                        if (seg_dist2(cmx, cmy, sT[2 * k], sT[2 * k + 1]) <= thr2) { lo = min(lo, k); hi = max(hi, k); }
+                        if (seg_dist2(cmx, cmy, lds128(tb + 32 * k), lds128(tb + 32 * k + 16)) <= thr2) {
+                            lo = min(lo, k);
+                            hi = max(hi, k);
+                        }
                     lo = __reduce_min_sync(F1L_FULL, lo);
                     hi = __reduce_max_sync(F1L_FULL, hi);
                     if (hi >= lo) {   // (always: the nearest segment itself passes)
@@ -1238,34 +1274,30 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                         k_end = min(nq, (hi + 2 * GG) & ~(2 * GG - 1));
                     }
                 }
-                if (lane == 0) atomicAdd(&s_work, (1ull << 40) + (unsigned long long)(k_end - k_begin));
-                float4 T0 = sT[2 * (k_begin + ggi)], T1 = sT[2 * (k_begin + ggi) + 1];
+                if (a.stats && lane == 0) atomicAdd(&s_work, (1ull << 40) + (unsigned long long)(k_end - k_begin));
+                // the walk advances the table address itself (one add per trip); the trip count is
+                // warp-uniform and lives in a uniform register
+                uint32_t ta = cbase + L::C_TAB + (k_begin + ggi) * 32;
+                float4 T0 = lds128(ta), T1 = lds128(ta + 16);
 #if EVAL_DEV_MIN3
                 // two segments per trip: the running minimum takes both distances in one
                 // three-input FMNMX3 (nseg_pad / GG is a multiple of 8)
-                for (int k = k_begin + ggi; k < k_end; k += 2 * GG) {
-                    const float4 B0 = sT[2 * (k + GG)], B1 = sT[2 * (k + GG) + 1];
-#if EVAL_DEV_MIN3 == 1
-                    const float4 N0 = sT[2 * (k + 2 * GG)];   // EVAL_SEG_PAD entries of slack
-                    const float4 N1 = sT[2 * (k + 2 * GG) + 1];
-#endif
+                for (int n = (k_end - k_begin) / (2 * GG); n > 0; --n) {
+                    const float4 B0 = lds128(ta + GG * 32), B1 = lds128(ta + GG * 32 + 16);
                     seg_min2<SP>(sx2, sy2, T0, T1, B0, B1, bdx, bdy);
                     if (ODD) bdl = fmin3(bdl, seg_dist2(sxl, syl, T0, T1), seg_dist2(sxl, syl, B0, B1));
-#if EVAL_DEV_MIN3 == 1
-                    T0 = N0;
-                    T1 = N1;
-#else
-                    T0 = sT[2 * (k + 2 * GG)];   // EVAL_SEG_PAD entries of slack
-                    T1 = sT[2 * (k + 2 * GG) + 1];
-#endif
+                    ta += 2 * GG * 32;
+                    T0 = lds128(ta);   // EVAL_SEG_PAD entries of slack
+                    T1 = lds128(ta + 16);
                 }
 #else
 #pragma unroll kSegUnroll
-                for (int k = k_begin + ggi; k < k_end; k += GG) {
-                    const float4 N0 = sT[2 * (k + GG)];       // EVAL_SEG_PAD entries of slack
-                    const float4 N1 = sT[2 * (k + GG) + 1];
+                for (int n = (k_end - k_begin) / GG; n > 0; --n) {
+                    const float4 N0 = lds128(ta + GG * 32);       // EVAL_SEG_PAD entries of slack
+                    const float4 N1 = lds128(ta + GG * 32 + 16);
                     seg_min1<SP>(sx2, sy2, T0, T1, bdx, bdy);
                     if (ODD) bdl = fminf(bdl, seg_dist2(sxl, syl, T0, T1));
+                    ta += GG * 32;
                     T0 = N0;
                     T1 = N1;
                 }
@@ -1284,11 +1316,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 float dsum = 0.0f;
 #pragma unroll
                 for (int j = 0; j < SP; ++j) {
-                    const int ia = (2 * j) * SG + sgi, ib = (2 * j + 1) * SG + sgi;
-                    dsum += (ia < M) ? fast_sqrt(bdx[j]) : 0.0f;
-                    dsum += (ib < M) ? fast_sqrt(bdy[j]) : 0.0f;
+                    dsum += (2 * j < nrows) ? fast_sqrt(bdx[j]) : 0.0f;
+                    dsum += (2 * j + 1 < nrows) ? fast_sqrt(bdy[j]) : 0.0f;
                 }
-                if (ODD) dsum += ((S - 1) * SG + sgi < M) ? fast_sqrt(bdl) : 0.0f;
+                if (ODD) dsum += (S - 1 < nrows) ? fast_sqrt(bdl) : 0.0f;
                 t_dev = warp_sum(dsum) * ((1.0f / EVAL_DEV_SCALE) / (float)GG) / (float)M;
             }
 
@@ -1316,7 +1347,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
       if (lane == 0) c_next = atomicAdd(&s_next, item);
       c0 = __shfl_sync(F1L_FULL, c_next, 0);
     }
-    if (a.stats) {   // one pair of global atomics per CTA
+    if (a.stats) {   // work counters (opt-in, f1l_set_stats): one pair of global atomics per CTA
         __syncthreads();
         if (tid == 0) {
             atomicAdd(a.stats, s_work & ((1ull << 40) - 1));

@@ -408,8 +408,13 @@ class Engine:
     def launch_count(self):
         return int(self._L.f1l_launch_count(self._h))
 
+    def set_stats(self, on):
+        """collect the deviation-pass work counters (off by default, f1l_set_stats)"""
+        self._ck(self._L.f1l_set_stats(self._h, int(bool(on))))
+
     def stats(self):
-        """(segment_steps, candidates) of the raceline-deviation pass since the last call: the
+        """(segment_steps, candidates) of the raceline-deviation pass since the last call (while
+        set_stats(True)): the
         (candidate, window segment) pairs evaluated and the valid candidates that reached the
         pass.  Resets the counters (f1l_get_stats)."""
         out = (C.c_uint64 * 2)()

@@ -304,6 +304,9 @@ int f1l_intersect_point_batch(f1l_handle h, const double* points, const double* 
 int f1l_get_actuation_batch(f1l_handle h, const double* in, int n, double wheelbase,
                             double* out);
 
+/* Work counters of the deviation pass are collected only while switched on (default off: the
+ * counting costs every CTA of eval_kernel a barrier and two global atomics). */
+int f1l_set_stats(f1l_handle h, int on);
 /* Work counters of the deviation pass since the last call (synchronises the handle's stream and
  * resets them): out[0] = (candidate, window segment) pairs evaluated, out[1] = candidates that
  * reached the pass (valid trajectories).  With prune_window = 0, out[0] / out[1] is the padded

@@ -382,6 +382,7 @@ def test_pruned_window_is_bit_identical(ellipse, corridor, config, window):
     la, wd = synth.goal_grid(config)
     eng, cfg, world = H.make_pair(ellipse, la, wd, grid=corridor, window=window, kappa_max=0.0)
     seeds = (21, 22, 23, 24) if config == 1 else (25,)
+    eng.set_stats(True)
     full, work_full = [], None
     for seed in seeds:
         pose, opp = H.scenario(ellipse, seed, 4)
