@@ -837,6 +837,36 @@ __device__ __forceinline__ void seg_min2(const f32x2 (&sx2)[SP], const f32x2 (&s
     }
 }
 
+// Deviation-pass epilogue: v[r] (r < N) is this lane's running minimum of squared distance for
+// row r of its sample group, of which the first `cnt` exist; the group's LANES lanes (consecutive,
+// LANES a power of two) hold minima over different segments.  Halving butterfly: the lane whose
+// bit is clear keeps the first half of the rows, its partner the second; after log2(LANES) steps
+// every row is reduced on exactly one lane of the group.  Returns the sum of sqrt over this
+// lane's existing rows, so that a plain warp sum gives the total over all samples.
+template <int N, int LANES>
+__device__ __forceinline__ float halve_min_sqrt_sum(float (&v)[N], int lane_in_group, int cnt) {
+    if constexpr (LANES == 1) {
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < N; ++j) s += (j < cnt) ? fast_sqrt(v[j]) : 0.0f;
+        return s;
+    } else {
+        constexpr int H = (N + 1) / 2;
+        const bool hi = (lane_in_group & (LANES / 2)) != 0;
+        float out[H];
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const float lo_v = v[j];
+            const float hi_v = (j + H < N) ? v[j + H] : CUDART_INF_F;
+            const float keep = hi ? hi_v : lo_v;
+            const float send = hi ? lo_v : hi_v;
+            out[j] = fminf(keep, __shfl_xor_sync(F1L_FULL, send, LANES / 2));
+        }
+        // rows exist from the front: the first half holds min(cnt, H) of them, the second the rest
+        return halve_min_sqrt_sum<H, LANES / 2>(out, lane_in_group, hi ? max(cnt - H, 0) : min(cnt, H));
+    }
+}
+
 // Shared-memory layout of eval_kernel (bytes; the host's eval_smem_bytes mirrors it).  Per warp one
 // contiguous block -- list of the footprints that need their nine grid probes (centre and half-axes
 // in grid-cell coordinates, two float4 per entry) | solutions of the four candidates of an item
@@ -1302,25 +1332,16 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                     T1 = N1;
                 }
 #endif
+                // Minima over the GG lanes of a sample group, by halving: at every step a lane keeps
+                // one half of its rows and hands the other half to its partner, so it ends with S / GG
+                // fully reduced rows of its own (7 + 4 shuffles and 4 square roots for S = 13, GG = 4,
+                // against 26 shuffles and 13 square roots on every lane when all lanes reduce all rows).
+                float rows[S];
 #pragma unroll
-                for (int o = 1; o < GG; o <<= 1) {
-#pragma unroll
-                    for (int j = 0; j < SP; ++j) {
-                        bdx[j] = fminf(bdx[j], __shfl_xor_sync(F1L_FULL, bdx[j], o));
-                        bdy[j] = fminf(bdy[j], __shfl_xor_sync(F1L_FULL, bdy[j], o));
-                    }
-                    if (ODD) bdl = fminf(bdl, __shfl_xor_sync(F1L_FULL, bdl, o));
-                }
-                // every lane of a sample group now holds the same S minima: sum them on all
-                // lanes (branch-free) and divide by the group size
-                float dsum = 0.0f;
-#pragma unroll
-                for (int j = 0; j < SP; ++j) {
-                    dsum += (2 * j < nrows) ? fast_sqrt(bdx[j]) : 0.0f;
-                    dsum += (2 * j + 1 < nrows) ? fast_sqrt(bdy[j]) : 0.0f;
-                }
-                if (ODD) dsum += (S - 1 < nrows) ? fast_sqrt(bdl) : 0.0f;
-                t_dev = warp_sum(dsum) * ((1.0f / EVAL_DEV_SCALE) / (float)GG) / (float)M;
+                for (int j = 0; j < SP; ++j) { rows[2 * j] = bdx[j]; rows[2 * j + 1] = bdy[j]; }
+                if (ODD) rows[S - 1] = bdl;
+                const float dsum = halve_min_sqrt_sum<S, GG>(rows, ggi, nrows);
+                t_dev = warp_sum(dsum) * (1.0f / EVAL_DEV_SCALE) / (float)M;
             }
 
             if (!(flags & (F1L_FLAG_COLLIDE_OPP | F1L_FLAG_COLLIDE_MAP))) {
