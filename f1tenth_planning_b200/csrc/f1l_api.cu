@@ -335,7 +335,13 @@ CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count, bool cubic) {
         // configuration with more resident warps on ties
         // the CTA holds its registers until its last warp finishes: about half a candidate of
         // idle tail per CTA, which weighs more the fewer candidates each warp runs
-        const double cost = waves * (rounds + 0.5) * (nw == 7 ? 0.999 : 1.0);
+        double cost = waves * (rounds + 0.5) * (nw == 7 ? 0.999 : 1.0);
+        // Throughput regime (many waves of whole-scenario CTAs sharing Newton solves): measured on
+        // the 10^5 x 28 batch, seven 4-warp CTAs per SM whose warps pull the scenario's seven items
+        // (2 + 2 + 2 + 1) beat four 7-warp CTAs with one item per warp by 0.8 % -- the once-per-warp
+        // set-up runs in 4 instead of 7 warps and idle warp slots turn over in smaller units --
+        // although the model's round count says otherwise (8 against 4 candidate-rounds per CTA).
+        if (nw == 4 && item == EVAL_ITEM && waves >= 8 && cps == 1) cost *= 0.9;
         if (cost < best_cost) { best_cost = cost; best = {nw, chunk, cps}; }
     }
     return best;

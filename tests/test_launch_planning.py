@@ -18,10 +18,13 @@ def eval_plan(n_cand, S, M, generator=0, sm=SM):
 
 
 def test_eval_plan_of_the_baseline_configs():
-    # C4: batches of the default 4x7 goal grid -> one 7-warp CTA per scenario, one item of four
-    # candidates per warp (shared Newton solve)
+    # C4: batches of the default 4x7 goal grid -> one 4-warp CTA per scenario whose warps pull the
+    # seven items of four candidates (shared Newton solve); measured faster than one 7-warp CTA
     p = eval_plan(28, 100000, 100)
-    assert p == dict(nw=7, chunk=28, ctas_per_scenario=1, item=4), p
+    assert p == dict(nw=4, chunk=28, ctas_per_scenario=1, item=4), p
+    # ... a few scenarios (less than a wave) are a latency problem: one candidate per warp
+    p = eval_plan(28, 64, 100)
+    assert p == dict(nw=7, chunk=7, ctas_per_scenario=4, item=1), p
     # C1: a single query is a latency problem -> one candidate per warp, four CTAs
     p = eval_plan(28, 1, 100)
     assert p == dict(nw=7, chunk=7, ctas_per_scenario=4, item=1), p
