@@ -317,32 +317,38 @@ CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count, bool cubic) {
 #endif
         if (nw != 8 && M > 128) continue;   // the 72-register builds of the M = 200 shapes spill
         const int resident = (nw == 4 ? EVAL_MINB4 : nw == 7 ? EVAL_MINB7 : EVAL_MINB8) * sm_count;
-        // enough CTAs for ~8 waves; batches of small queries get one CTA per scenario
+        const int full = ((n_cand + nw - 1) / nw) * nw;   // one CTA per scenario
+        // chunk sizes worth a look: enough CTAs for ~8 waves (dense single queries), the smallest
+        // chunk whose warps share Newton solves, and the whole scenario in one CTA
         long long per = (8LL * resident + S - 1) / S;
         const long long max_per = (n_cand + nw - 1) / nw;
         if (per > max_per) per = max_per;
         if (per < 1) per = 1;
-        int chunk = (int)((n_cand + per - 1) / per);
-        chunk = ((chunk + nw - 1) / nw) * nw;
-        const int cps = (n_cand + chunk - 1) / chunk;
-        const double ctas = (double)S * cps;
-        const double waves = std::ceil(ctas / resident);
-        // candidates a warp runs one after the other; with the cubic generator and at least four
-        // candidates per warp they are taken four at a time (shared Newton solve)
-        const int item = (cubic && chunk >= 4 * nw) ? EVAL_ITEM : 1;
-        const double rounds = std::ceil(std::ceil((double)chunk / item) / nw) * item;
-        // time ~ waves x rounds, in units of one candidate per warp; slightly favour the
-        // configuration with more resident warps on ties
-        // the CTA holds its registers until its last warp finishes: about half a candidate of
-        // idle tail per CTA, which weighs more the fewer candidates each warp runs
-        double cost = waves * (rounds + 0.5) * (nw == 7 ? 0.999 : 1.0);
-        // Throughput regime (many waves of whole-scenario CTAs sharing Newton solves): measured on
-        // the 10^5 x 28 batch, seven 4-warp CTAs per SM whose warps pull the scenario's seven items
-        // (2 + 2 + 2 + 1) beat four 7-warp CTAs with one item per warp by 0.8 % -- the once-per-warp
-        // set-up runs in 4 instead of 7 warps and idle warp slots turn over in smaller units --
-        // although the model's round count says otherwise (8 against 4 candidate-rounds per CTA).
-        if (nw == 4 && item == EVAL_ITEM && waves >= 8 && cps == 1) cost *= 0.9;
-        if (cost < best_cost) { best_cost = cost; best = {nw, chunk, cps}; }
+        int c8 = (int)((n_cand + per - 1) / per);
+        c8 = ((c8 + nw - 1) / nw) * nw;
+        const int options[3] = {c8, EVAL_ITEM * nw < full ? EVAL_ITEM * nw : full, full};
+        for (int chunk : options) {
+            const int cps = (n_cand + chunk - 1) / chunk;
+            const double ctas = (double)S * cps;
+            const double waves = std::ceil(ctas / resident);
+            // candidates a warp runs one after the other; with the cubic generator and at least four
+            // candidates per warp they are taken four at a time (shared Newton solve)
+            const int item = (cubic && chunk >= 4 * nw) ? EVAL_ITEM : 1;
+            const double rounds = std::ceil(std::ceil((double)chunk / item) / nw) * item;
+            // time ~ waves x (rounds + prologue) + tail, in units of one candidate per warp: a
+            // candidate whose Newton solve is not shared costs ~6 % more instructions, the CTA
+            // prologue (window table, set-up) ~0.3 candidates, and the last wave's CTAs hold their
+            // SMs until their slowest warps finish: about half a candidate.  Slightly favour the
+            // configuration with more resident warps on ties.
+            double cost = (waves * (rounds * (item == EVAL_ITEM ? 1.0 : 1.06) + 0.3) + 0.5) * (nw == 7 ? 0.999 : 1.0);
+            // Throughput regime (many waves of whole-scenario CTAs sharing Newton solves): measured
+            // on the 10^5 x 28 batch, seven 4-warp CTAs per SM whose warps pull the scenario's seven
+            // items (2 + 2 + 2 + 1) beat four 7-warp CTAs with one item per warp by 0.8 % -- the
+            // once-per-warp set-up runs in 4 instead of 7 warps and idle warp slots turn over in
+            // smaller units -- although the round count says otherwise (8 against 4 per CTA).
+            if (nw == 4 && item == EVAL_ITEM && waves >= 8 && cps == 1) cost *= 0.9;
+            if (cost < best_cost) { best_cost = cost; best = {nw, chunk, cps}; }
+        }
     }
     return best;
 }
