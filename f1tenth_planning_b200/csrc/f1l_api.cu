@@ -98,6 +98,7 @@ struct f1l_ctx {
     int eval_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // the last single query, for f1l_select_candidate: candidate count, explicit goals?, epoch
     int lastq_C = 0, lastq_goals = 0;
+    int lastq_rows[3] = {0, 1, -1};   // lookahead rows its sampler filled (row0, step, count; -1: all)
     unsigned long long lastq_epoch = ~0ull;
 };
 
@@ -315,7 +316,9 @@ CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count, bool cubic) {
 #ifdef F1L_FORCE_NW
         if (nw != F1L_FORCE_NW) continue;
 #endif
+#ifndef F1L_ALLOW_SMALL_NW_BIG_M
         if (nw != 8 && M > 128) continue;   // the 72-register builds of the M = 200 shapes spill
+#endif
         const int resident = (nw == 4 ? EVAL_MINB4 : nw == 7 ? EVAL_MINB7 : EVAL_MINB8) * sm_count;
         const int full = ((n_cand + nw - 1) / nw) * nw;   // one CTA per scenario
         // chunk sizes worth a look: enough CTAs for ~8 waves (dense single queries), the smallest
@@ -407,6 +410,7 @@ struct BatchOut {
     int row0 = 0, row_step = 1;        // row-interleaved shard (c_begin / c_end are shard-local)
     const XchgView* xc = nullptr;      // sharded single query: exchange the argmin with the peers
     int32_t* xchg_status = nullptr;
+    int s_row0 = 0, s_step = 1, s_rows = -1;   // lookahead rows the sampler must fill (-1: all)
     bool empty_shard = false;          // this rank owns no candidate of the query: it evaluates nothing
                                        // but still takes part in the exchange (key = ~0)
 };
@@ -429,6 +433,10 @@ SelectArgs select_args(f1l_handle h, const TrackView& tv, const LutView& lut, co
     se.nL = h->nL;
     se.nW = h->nW;
     se.inv_nW = 1.0f / (float)(h->nW > 0 ? h->nW : 1);
+    se.lookaheads = (const double*)h->lookaheads.p;
+    se.row0 = o.s_rows >= 0 ? o.s_row0 : 0;
+    se.row_step = o.s_rows >= 0 ? o.s_step : 1;
+    se.n_rows = o.s_rows >= 0 ? o.s_rows : h->nL;
     se.goals = goals;
     se.C = C;
     se.c_begin = first_cand < C ? first_cand : 0;   // (a rank without rows)
@@ -481,6 +489,9 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     sa.max_opp = max_opp;
     sa.lookaheads = (const double*)h->lookaheads.p;
     sa.nL = goals ? 0 : h->nL;
+    sa.row0 = o.s_rows >= 0 ? o.s_row0 : 0;
+    sa.row_step = o.s_rows >= 0 ? o.s_step : 1;
+    sa.n_rows = o.s_rows >= 0 ? o.s_rows : h->nL;
     sa.ctx = ctx;
     sa.centres = centres;
     sa.best = best;
@@ -504,8 +515,8 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     } else {
         // a lone dense query: one warp per ~2 lookahead rows; small batches: 8 warps each
         int st_threads = SAMPLE_THREADS;
-        if (S <= 4 && sa.nL > 8) {
-            st_threads = ((sa.nL + 1) / 2) * 32;
+        if (S <= 4 && sa.n_rows > 8) {
+            st_threads = ((sa.n_rows + 1) / 2) * 32;
             if (st_threads > SAMPLE_THREADS_MAX) st_threads = SAMPLE_THREADS_MAX;
             if (st_threads < SAMPLE_THREADS) st_threads = SAMPLE_THREADS;
         }
@@ -1113,6 +1124,17 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
         o.row_step = row_step;
         c_begin = 0;
         c_end = n_rows * h->nW;
+        o.s_row0 = row0 < h->nL ? row0 : 0;   // the sampler fills this shard's rows only
+        o.s_step = row_step;
+        o.s_rows = n_rows > 0 ? n_rows : 0;
+    } else if (!goals && h->nW > 0 && (c_begin > 0 || (c_end > 0 && c_end < C))) {
+        // contiguous candidate block: the lookahead rows it touches
+        const int cb = c_begin > 0 ? c_begin : 0, ce = (c_end > 0 && c_end < C) ? c_end : C;
+        if (cb < ce) {
+            o.s_row0 = cb / h->nW;
+            o.s_step = 1;
+            o.s_rows = (ce - 1) / h->nW - o.s_row0 + 1;
+        }
     }
     exchange = exchange && h->xview.world > 1;
     if (exchange) {   // the ranks' minima meet inside select_kernel (peer memory over NVLink)
@@ -1196,6 +1218,9 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     if (exchange && hd->pad != 0) return F1L_ERR_PEER_TIMEOUT;
     h->lastq_C = C;
     h->lastq_goals = goals != nullptr;
+    h->lastq_rows[0] = o.s_row0;
+    h->lastq_rows[1] = o.s_step;
+    h->lastq_rows[2] = o.s_rows;
     h->lastq_epoch = h->epoch;
     out->steer = hd->steer;
     out->speed = hd->speed;
@@ -1257,6 +1282,9 @@ int f1l_select_candidate(f1l_handle h, int idx, float cost, int update_prev, f1l
     o.best_traj = (float4*)(dres + Q_OFF_TRAJ);
     o.best_traj_map = out->best_traj_map ? (double*)(dres + Q_OFF_MAP) : nullptr;
     o.prev_out = update_prev ? (float*)h->prev.p : nullptr;
+    o.s_row0 = h->lastq_rows[0];
+    o.s_step = h->lastq_rows[1];
+    o.s_rows = h->lastq_rows[2];
     const SelectArgs se = select_args(h, track_view(h), lut_view(h), eval_params(h),
                                       (const QueryCtx*)h->q_ctx.p, (const Centre*)h->q_centres.p,
                                       h->lastq_goals ? (const float4*)h->q_goals.p : nullptr, C, 0,

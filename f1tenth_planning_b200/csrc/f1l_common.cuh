@@ -66,6 +66,8 @@ struct EvalParams {
 // per-scenario context written by the sampler kernel, read by eval / select
 struct __align__(16) QueryCtx {
     double px, py, th, vel;
+    double t_ego;          // parameter of the nearest point on segment i_ego (utils.py:58-60)
+    double pad1;
     float cth, sth;        // cos / sin of the pose heading
     int i_ego;             // nearest open-polyline segment (utils.py:66)
     int seg0, nseg;        // cyclic raceline window [seg0, seg0+nseg) over the n-1 segments

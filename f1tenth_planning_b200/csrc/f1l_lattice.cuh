@@ -322,6 +322,8 @@ struct SampleArgs {
     int max_opp;
     const double* lookaheads;  // [nL] device
     int nL;                    // 0 in explicit-goal mode
+    int row0, row_step, n_rows;  // the lookahead rows this launch needs: row0 + k * row_step, k < n_rows
+                                 // (a shard of a dense query samples only the rows it evaluates)
     QueryCtx* ctx;             // [S]
     Centre* centres;           // [S,nL]
     unsigned long long* best;  // [S]
@@ -426,6 +428,8 @@ struct SelectArgs {
     const float* widths;
     int nL, nW;
     float inv_nW;
+    const double* lookaheads;   // [nL] (the winner's centre is recomputed when its row is not ours)
+    int row0, row_step, n_rows; // the lookahead rows this rank's sampler filled (see SampleArgs)
     const float4* goals;
     int C, c_begin;
     const unsigned long long* best;
@@ -495,6 +499,29 @@ __device__ __forceinline__ double wrap_to_pi64(double a) {
     return r - pi;
 }
 
+// goal centre of one lookahead row from its intersect_point result (lattice_planner.py:251: the
+// segment-start waypoint's x, y, psi), in the vehicle frame
+__device__ __forceinline__ Centre centre_from_hit(const TrackView& tr, const Intersect64& ip, double px,
+                                                  double py, double pth, double cth, double sth) {
+    Centre ce;
+    const int r = ip.found ? pymod(ip.i, tr.n) : 0;
+    const double2 c = tr.xy[r];
+    const double psi = tr.psi[r];
+    const double dx = c.x - px, dy = c.y - py;
+    const double prel = wrap_to_pi64(psi - pth);
+    ce.cx = ip.found ? (float)(cth * dx + sth * dy) : 0.0f;
+    ce.cy = ip.found ? (float)(-sth * dx + cth * dy) : 0.0f;
+    ce.psi_rel = ip.found ? (float)prel : 0.0f;
+    ce.kappa_g = (float)tr.kappa[r];
+    double sp_, cp_;
+    sincos(prel, &sp_, &cp_);
+    ce.nx = ip.found ? (float)(-sp_) : 0.0f;
+    ce.ny = ip.found ? (float)cp_ : 0.0f;
+    ce.v = (float)tr.v[r];
+    ce.ok = ip.found ? (float)(r + 1) : 0.0f;   // centre waypoint index + 1 (exact: < 2^24)
+    return ce;
+}
+
 // everything after the nearest-point search, shared by the two sampler kernels.  `lt` / `nt`:
 // this thread's index / the number of threads working on scenario s.
 __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, int nt, int i_ego,
@@ -509,10 +536,12 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
     // four rows per warp at a time
     XYTrack acc{a.tr.xy};
     const int lane = lt & 31;
-    for (int j0 = (lt >> 5) * 4; j0 < a.nL; j0 += (nt >> 5) * 4) {
-        const int j = j0 + (lane >> 3);
-        const bool active = j < a.nL;
-        const double L = a.lookaheads[active ? j : j0];
+    const int n_rows = a.nL > 0 ? a.n_rows : 0;
+    for (int j0 = (lt >> 5) * 4; j0 < n_rows; j0 += (nt >> 5) * 4) {
+        const int jj = j0 + (lane >> 3);
+        const bool active = jj < n_rows;
+        const int j = a.row0 + (active ? jj : j0) * a.row_step;   // lookahead row
+        const double L = a.lookaheads[j];
         const float rr = (float)L + 1e-3f;
         const TrackPrefilter pf{a.tr, px, py, rr * rr};
         bool pending;
@@ -529,25 +558,8 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
                 intersect_point_warp(acc, a.tr.n, px, py, Ls, (double)i_ego + t_ego, true, lane, pfs);
             if ((lane & ~7) == src) ip = full;
         }
-        if (active && (lane & 7) == 0) {
-            Centre ce;
-            const int r = ip.found ? pymod(ip.i, a.tr.n) : 0;
-            const double2 c = a.tr.xy[r];
-            const double psi = a.tr.psi[r];
-            const double dx = c.x - px, dy = c.y - py;
-            const double prel = wrap_to_pi64(psi - pth);
-            ce.cx = ip.found ? (float)(cth * dx + sth * dy) : 0.0f;
-            ce.cy = ip.found ? (float)(-sth * dx + cth * dy) : 0.0f;
-            ce.psi_rel = ip.found ? (float)prel : 0.0f;
-            ce.kappa_g = (float)a.tr.kappa[r];
-            double sp_, cp_;
-            sincos(prel, &sp_, &cp_);
-            ce.nx = ip.found ? (float)(-sp_) : 0.0f;
-            ce.ny = ip.found ? (float)cp_ : 0.0f;
-            ce.v = (float)a.tr.v[r];
-            ce.ok = ip.found ? (float)(r + 1) : 0.0f;   // centre waypoint index + 1 (exact: < 2^24)
-            a.centres[(size_t)s * a.nL + j] = ce;
-        }
+        if (active && (lane & 7) == 0)
+            a.centres[(size_t)s * a.nL + j] = centre_from_hit(a.tr, ip, px, py, pth, cth, sth);
     }
 
     QueryCtx* q = a.ctx + s;
@@ -568,6 +580,8 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
         q->px = px; q->py = py; q->th = pth; q->vel = pv;
         q->cth = (float)cth; q->sth = (float)sth;
         q->i_ego = i_ego;
+        q->t_ego = t_ego;
+        q->pad1 = 0.0;
         int ns = a.ep.window;
         if (ns <= 0 || ns > nseg) ns = nseg;
         q->nseg = ns;
@@ -1400,16 +1414,44 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(SelectArgs a) {
 
     float gx, gy, gth, p3, v_ref;
     bool have_centre;
-    candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.inv_nW, a.C, s, idx,
-                   a.ep.use_goal_kappa != 0, gx, gy, gth, p3, have_centre, v_ref);
     // speed column / tracker speed: the raceline speed at the goal centre, read back in float64
     // from the waypoint the sampler chose (pure_pursuit.py:78 returns waypoints[i, 2] itself);
     // explicit goals have no centre: the ego speed
     double v_goal = q->vel;
-    if (!a.goals && a.tr.ncols > 2) {
-        const int row = __float2int_rd(((float)idx + 0.5f) * a.inv_nW);
-        const int wp = (int)a.centres[(size_t)s * a.nL + row].ok - 1;
-        if (wp >= 0) v_goal = a.tr.v[wp];
+    if (a.goals) {
+        candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.inv_nW, a.C, s, idx,
+                       a.ep.use_goal_kappa != 0, gx, gy, gth, p3, have_centre, v_ref);
+    } else {
+        const int row = __float2int_rd(((float)idx + 0.5f) * a.inv_nW), k = idx - row * a.nW;
+        // A shard's sampler fills only the lookahead rows the shard evaluates.  The global winner
+        // of a sharded query may sit in a row of another rank: its centre is recomputed here, by
+        // the same float64 intersect_point the owner ran (same operations, same result).
+        const int rel = row - a.row0;
+        const bool mine = rel >= 0 && rel < a.n_rows * a.row_step && (a.row_step == 1 || rel % a.row_step == 0);
+        Centre ce;
+        if (mine) {   // warp-uniform
+            ce = a.centres[(size_t)s * a.nL + row];
+        } else {
+            const double px = q->px, py = q->py, pth = q->th;
+            double sth, cth;
+            sincos(pth, &sth, &cth);
+            const double L = a.lookaheads[row];
+            const float rr = (float)L + 1e-3f;
+            const TrackPrefilter pf{a.tr, px, py, rr * rr};
+            XYTrack acc{a.tr.xy};
+            const Intersect64 ip = intersect_point_warp(acc, a.tr.n, px, py, L, (double)q->i_ego + q->t_ego,
+                                                        true, lane, pf);
+            ce = centre_from_hit(a.tr, ip, px, py, pth, cth, sth);
+        }
+        const float wk = __ldg(a.widths + k);
+        gx = fmaf(wk, ce.nx, ce.cx);
+        gy = fmaf(wk, ce.ny, ce.cy);
+        gth = ce.psi_rel;
+        p3 = a.ep.use_goal_kappa != 0 ? ce.kappa_g : 0.0f;
+        have_centre = ce.ok != 0.0f;
+        v_ref = ce.v;
+        const int wp = (int)ce.ok - 1;
+        if (a.tr.ncols > 2 && wp >= 0) v_goal = a.tr.v[wp];
     }
     SpiralF sp;
     generate_spiral(sp, a.lut, a.ep, gx, gy, gth, p3, lane);
