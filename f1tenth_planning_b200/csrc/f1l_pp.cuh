@@ -33,7 +33,9 @@
 #pragma once
 #include "f1l_common.cuh"
 
+#ifndef PP_LANE_POSES
 #define PP_LANE_POSES 4        // poses per lane (two packed pairs)
+#endif
 #define PP_CTA_POSES (32 * PP_LANE_POSES)   // poses of a scan task
 #define PP_THREADS 128         // finish kernel
 
