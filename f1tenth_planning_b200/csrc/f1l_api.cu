@@ -433,7 +433,6 @@ SelectArgs select_args(f1l_handle h, const TrackView& tv, const LutView& lut, co
     se.nL = h->nL;
     se.nW = h->nW;
     se.inv_nW = 1.0f / (float)(h->nW > 0 ? h->nW : 1);
-    se.lookaheads = (const double*)h->lookaheads.p;
     se.row0 = o.s_rows >= 0 ? o.s_row0 : 0;
     se.row_step = o.s_rows >= 0 ? o.s_step : 1;
     se.n_rows = o.s_rows >= 0 ? o.s_rows : h->nL;
@@ -1319,7 +1318,7 @@ int f1l_xchg_export(f1l_handle h, uint8_t* handle_out, int n) {
     // a whole 2 MB allocation granule of its own: the IPC handle maps exactly this block
     ENS(h->xchg, (size_t)2 << 20);
     unsigned long long init[F1L_XCHG_WORDS];
-    for (int i = 0; i < F1L_XCHG_WORDS; ++i) init[i] = i < 4 ? ~0ull : 0ull;
+    for (int i = 0; i < F1L_XCHG_WORDS; ++i) init[i] = 0ull;
     CK(cudaMemcpy(h->xchg.p, init, sizeof(init), cudaMemcpyHostToDevice));
     cudaIpcMemHandle_t mh;
     CK(cudaIpcGetMemHandle(&mh, h->xchg.p));

@@ -363,11 +363,17 @@ struct EvalArgs {
 };
 
 // Peer-memory exchange of a candidate-sharded query (the one exchange step of the
-// path).  Every rank owns a 128-byte block in its HBM, mapped into the other ranks' address
-// spaces with CUDA IPC (NVLink P2P): u64 words [0..3] argmin-key slots, [4..7] arrival counters,
-// [8] call sequence number (local), [9] sticky timeout flag (local).
+// path).  Every rank owns a block of u64 words in its HBM, mapped into the other ranks' address
+// spaces with CUDA IPC (NVLink P2P):
+//   [0] call sequence number (local)     [1] sticky timeout flag (local)
+//   [2..5] arrival counters of the four round-robin slots
+//   [8 + (slot * F1L_MAX_RANKS + r) * 6 ...] entry of rank r in that slot: the rank's packed
+//        (cost, index) key and the goal centre (Centre, 32 bytes) of its winner -- the winner's
+//        lookahead row was sampled by its owner only, so the centre travels with the key.
 #define F1L_MAX_RANKS 16
-#define F1L_XCHG_WORDS 16
+#define F1L_XCHG_ENTRY 6                                         // words per entry (key, Centre, pad)
+#define F1L_XCHG_ENTRY0 8
+#define F1L_XCHG_WORDS (F1L_XCHG_ENTRY0 + 4 * F1L_MAX_RANKS * F1L_XCHG_ENTRY)
 #ifndef F1L_XCHG_TIMEOUT_CYCLES
 #define F1L_XCHG_TIMEOUT_CYCLES 4000000000ll   // ~2 s at 1.965 GHz: a dead peer must not hang the GPU
 #endif
@@ -376,45 +382,67 @@ struct XchgView {
     unsigned long long* peer[F1L_MAX_RANKS];        // peer[rank] is the local block
 };
 
-// Lanes r < world each push this rank's packed (cost, index) key into rank r's slot with a
-// system-scope atomicMin over NVLink, fence, then bump rank r's arrival counter; lane 0 waits until
-// all `world` arrivals are visible in the local block and reads the global minimum -- every rank
-// ends with the same key, the first minimum of the concatenated cost vector (np.argmin).  Slots
-// are used round-robin by call number and a call resets the slot two calls ahead: a peer can only
-// be one call ahead of the slowest rank (it waits for everybody's arrival), so a slot is never
-// reset while somebody may still write or read it.  Returns the global key; *timed_out is set
-// when a peer did not arrive within F1L_XCHG_TIMEOUT_CYCLES.
+// Lanes r < world each store this rank's (key, centre) entry into rank r's block over NVLink,
+// fence, then bump rank r's arrival counter; lane 0 waits until all `world` arrivals are visible in
+// the local block, then the lanes read the `world` keys and the warp takes their minimum -- every
+// rank ends with the same key, the first minimum of the concatenated cost vector (np.argmin), and
+// the centre its owner sent along.  Slots are used round-robin by call number and a call resets
+// the counter of the slot two calls ahead: a peer can only be one call ahead of the slowest rank
+// (it waits for everybody's arrival), so a slot is never reset while somebody may still write or
+// read it.  Returns the global key and overwrites `ce` with the winner's centre; *timed_out is
+// set when a peer did not arrive within F1L_XCHG_TIMEOUT_CYCLES.
 __device__ __forceinline__ unsigned long long xchg_global_min(const XchgView& xc, unsigned long long key,
-                                                              int lane, int* timed_out) {
+                                                              Centre& ce, int lane, int* timed_out) {
     unsigned long long* mine = xc.peer[xc.rank];
-    const unsigned seq = (unsigned)(*(volatile unsigned long long*)(mine + 8));
+    const unsigned seq = (unsigned)(*(volatile unsigned long long*)(mine + 0));
     const int slot = (int)(seq & 3u);
     if (lane < xc.world) {
-        unsigned long long* dst = xc.peer[lane];
-        atomicMin_system(dst + slot, key);
+        volatile unsigned long long* dst =
+            xc.peer[lane] + F1L_XCHG_ENTRY0 + (slot * F1L_MAX_RANKS + xc.rank) * F1L_XCHG_ENTRY;
+        const unsigned long long* cw = reinterpret_cast<const unsigned long long*>(&ce);
+        dst[0] = key;
+        dst[1] = cw[0]; dst[2] = cw[1]; dst[3] = cw[2]; dst[4] = cw[3];
         __threadfence_system();
-        atomicAdd_system(dst + 4 + slot, 1ull);
+        atomicAdd_system(xc.peer[lane] + 2 + slot, 1ull);
     }
     __syncwarp();
-    unsigned long long g = key;
     int bad = 0;
     if (lane == 0) {
         const long long t0 = clock64();
-        volatile unsigned long long* cnt = mine + 4 + slot;
+        volatile unsigned long long* cnt = mine + 2 + slot;
         while (*cnt < (unsigned long long)xc.world) {
             if (clock64() - t0 > F1L_XCHG_TIMEOUT_CYCLES) { bad = 1; break; }
         }
         __threadfence_system();
-        g = *(volatile unsigned long long*)(mine + slot);
+    }
+    __syncwarp();
+    // the world keys, one per lane; 64-bit minimum over the warp, the lowest rank on ties (keys of
+    // different ranks differ in their index part unless both are ~0)
+    const volatile unsigned long long* ent = mine + F1L_XCHG_ENTRY0 + (size_t)slot * F1L_MAX_RANKS * F1L_XCHG_ENTRY;
+    unsigned long long k = lane < xc.world ? ent[lane * F1L_XCHG_ENTRY] : ~0ull;
+    unsigned long long g = k;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(F1L_FULL, g, o);
+        g = other < g ? other : g;
+    }
+    const unsigned who = __ballot_sync(F1L_FULL, lane < xc.world && k == g);
+    const int wr = who ? __ffs(who) - 1 : xc.rank;
+    if (wr != xc.rank) {   // warp-uniform
+        unsigned long long* cw = reinterpret_cast<unsigned long long*>(&ce);
+        const volatile unsigned long long* src = ent + wr * F1L_XCHG_ENTRY;
+        cw[0] = src[1]; cw[1] = src[2]; cw[2] = src[3]; cw[3] = src[4];
+    }
+    __syncwarp();
+    if (lane == 0) {
         const int nxt = (slot + 2) & 3;
-        mine[nxt] = ~0ull;
-        mine[4 + nxt] = 0ull;
-        mine[8] = (unsigned long long)(seq + 1u);
-        if (bad) mine[9] = 1ull;
-        bad |= (int)(*(volatile unsigned long long*)(mine + 9));
+        mine[2 + nxt] = 0ull;
+        mine[0] = (unsigned long long)(seq + 1u);
+        if (bad) mine[1] = 1ull;
+        bad |= (int)(*(volatile unsigned long long*)(mine + 1));
     }
     *timed_out = __shfl_sync(F1L_FULL, bad, 0);
-    return __shfl_sync(F1L_FULL, g, 0);
+    return g;
 }
 
 struct SelectArgs {
@@ -428,7 +456,6 @@ struct SelectArgs {
     const float* widths;
     int nL, nW;
     float inv_nW;
-    const double* lookaheads;   // [nL] (the winner's centre is recomputed when its row is not ours)
     int row0, row_step, n_rows; // the lookahead rows this rank's sampler filled (see SampleArgs)
     const float4* goals;
     int C, c_begin;
@@ -1402,9 +1429,21 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(SelectArgs a) {
     const int M = a.ep.M;
     const QueryCtx* __restrict__ q = a.ctx + s;
     unsigned long long key = a.best[s];
+    // goal centre of the winner's lookahead row.  A shard's sampler fills only the rows the shard
+    // evaluates, which contain its own winner; in a sharded query the global winner's centre
+    // arrives with its key through the exchange.
+    Centre ce;
+    ce.cx = 0.f; ce.cy = 0.f; ce.psi_rel = 0.f; ce.kappa_g = 0.f; ce.nx = 0.f; ce.ny = 0.f; ce.v = 0.f; ce.ok = 0.f;
+    if (!a.goals) {
+        const int lidx = key == ~0ull ? a.c_begin : (int)(key & 0xffffffffu);
+        const int lrow = __float2int_rd(((float)lidx + 0.5f) * a.inv_nW);
+        const int rel = lrow - a.row0;
+        if (rel >= 0 && rel < a.n_rows * a.row_step && (a.row_step == 1 || rel % a.row_step == 0))
+            ce = a.centres[(size_t)s * a.nL + lrow];   // (a rank without rows has nothing to offer)
+    }
     if (a.xc.world > 1) {   // (S == 1) the ranks' local minima meet over NVLink peer memory
         int timed_out = 0;
-        key = xchg_global_min(a.xc, key, lane, &timed_out);
+        key = xchg_global_min(a.xc, key, ce, lane, &timed_out);
         if (lane == 0 && a.xchg_status) *a.xchg_status = timed_out;
     }
     int idx = (int)(key & 0xffffffffu);
@@ -1423,26 +1462,6 @@ __global__ void __launch_bounds__(SELECT_THREADS) select_kernel(SelectArgs a) {
                        a.ep.use_goal_kappa != 0, gx, gy, gth, p3, have_centre, v_ref);
     } else {
         const int row = __float2int_rd(((float)idx + 0.5f) * a.inv_nW), k = idx - row * a.nW;
-        // A shard's sampler fills only the lookahead rows the shard evaluates.  The global winner
-        // of a sharded query may sit in a row of another rank: its centre is recomputed here, by
-        // the same float64 intersect_point the owner ran (same operations, same result).
-        const int rel = row - a.row0;
-        const bool mine = rel >= 0 && rel < a.n_rows * a.row_step && (a.row_step == 1 || rel % a.row_step == 0);
-        Centre ce;
-        if (mine) {   // warp-uniform
-            ce = a.centres[(size_t)s * a.nL + row];
-        } else {
-            const double px = q->px, py = q->py, pth = q->th;
-            double sth, cth;
-            sincos(pth, &sth, &cth);
-            const double L = a.lookaheads[row];
-            const float rr = (float)L + 1e-3f;
-            const TrackPrefilter pf{a.tr, px, py, rr * rr};
-            XYTrack acc{a.tr.xy};
-            const Intersect64 ip = intersect_point_warp(acc, a.tr.n, px, py, L, (double)q->i_ego + q->t_ego,
-                                                        true, lane, pf);
-            ce = centre_from_hit(a.tr, ip, px, py, pth, cth, sth);
-        }
         const float wk = __ldg(a.widths + k);
         gx = fmaf(wk, ce.nx, ce.cx);
         gy = fmaf(wk, ce.ny, ce.cy);

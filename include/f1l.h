@@ -196,7 +196,7 @@ int f1l_plan_rows(f1l_handle h, const double pose[4], const double* opp, int n_o
  * Peer-memory exchange for f1l_plan_shard ("final step = gather of G (cost, idx)
  * pairs"; replaces an 8-byte NCCL all-gather plus host min).  Each rank (one PROCESS per rank --
  * CUDA IPC handles cannot be opened by the process that exported them; ranks may share a GPU)
- * exports a 128-byte block of its HBM as a CUDA IPC handle
+ * exports a 3 KB block of its HBM (per-rank key + goal-centre entries, arrival counters) as a CUDA IPC handle
  * (f1l_xchg_export, 64 bytes), the caller gathers the `world` handles by any means (the Python
  * layer uses torch.distributed) and attaches them in rank order (f1l_xchg_attach: maps the peers'
  * blocks over NVLink P2P).  From then on f1l_plan_shard / f1l_plan_rows are collective: every rank calls it for
