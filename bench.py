@@ -684,6 +684,15 @@ def run_ours(args):
     assert np.array_equal(host.h_out["best_idx"], arm.o_idx.cpu().numpy()), "e2e and device-resident arms disagree"
     assert np.array_equal(host.h_out["flags"], flags), "e2e and device-resident arms disagree (flags)"
 
+    # ---- what the host link gives: every rank copies 128 MB device -> pinned host at the same time
+    #      (the e2e arm's result copy is 176 MB per step per GPU) ----------------------------------
+    probe_dev = torch.empty(128 << 20, dtype=torch.uint8, device=dev)
+    probe_host = torch.empty(128 << 20, dtype=torch.uint8, pin_memory=True)
+    probe_host.copy_(probe_dev)
+    probe_ms = timed(torch, dist, dev, world_size, lambda: probe_host.copy_(probe_dev, non_blocking=True), 4)
+    d2h_probe_gbs = 4 * (128 << 20) / (probe_ms * 1e-3) / 1e9
+    del probe_dev, probe_host
+
     # ---- strong scaling (BASELINE config 4 as written): the 10^5 scenarios of rank 0's set split
     #      into contiguous blocks over the ranks, same two arms --------------------------------------
     strong = None
@@ -771,6 +780,8 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": host.h2d,
                 "d2h_bytes_per_step": host.d2h, "steps": e2e_steps,
                 "d2h_gbs_per_gpu": host.d2h / (t_e2e / e2e_steps) / 1e9,
+                # plain 128 MB device -> pinned-host copies issued by all ranks at the same time
+                "d2h_link_probe_gbs_per_gpu": d2h_probe_gbs,
                 "api": "LatticePlanner.plan_batch (pinned host buffers; every output of the "
                        "device-resident arm, flags included)"},
         "gpu_launches": int(launches),

@@ -31,7 +31,7 @@ class Config(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("n_newton", C.c_int32), ("window", C.c_int32),
                 ("n_shift", C.c_int32), ("n_cull", C.c_int32), ("literal_tracker", C.c_int32),
                 ("use_goal_kappa", C.c_int32), ("generator", C.c_int32),
-                ("prune_window", C.c_int32),
+                ("prune_window", C.c_int32), ("collision_mode", C.c_int32),
                 ("weights", C.c_double * N_TERMS), ("kappa_max", C.c_double),
                 ("car_length", C.c_double), ("car_width", C.c_double),
                 ("converge_tol", C.c_double), ("tracker_lookahead", C.c_double),
@@ -62,6 +62,7 @@ SIGNATURES = {
     "f1l_set_track": (C.c_int, [_vp, _dp, C.c_int, C.c_int]),
     "f1l_set_grid": (C.c_int, [_vp, _bp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]),
     "f1l_clear_grid": (C.c_int, [_vp]),
+    "f1l_get_edt": (C.c_int, [_vp, _vp]),
     "f1l_set_goal_grid": (C.c_int, [_vp, _dp, C.c_int, _dp, C.c_int]),
     "f1l_get_lut_shape": (C.c_int, [_vp, _ip, _dp]),
     "f1l_get_lut": (C.c_int, [_vp, _fp]),

@@ -11,12 +11,23 @@
 #include <sched.h>
 #include <unistd.h>
 
+// NVTX ranges around the stages of the path (profiling hooks): sampler / eval / select
+// launches, the H2D / D2H legs of the host-buffer calls.  Header-only NVTX3: a few tens of
+// nanoseconds per call with no tool attached.
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 #include "f1l_common.cuh"
 #include "f1l_lattice.cuh"
 #include "f1l_peaks.cuh"
 #include "f1l_pp.cuh"
 
+#ifndef N_PIPE
 #define N_PIPE 3  // streams of the host-buffer batch pipeline
+#endif
 
 namespace {
 
@@ -55,7 +66,7 @@ struct f1l_ctx {
     int n = 0, ncols = 0;
     DevBuf xy, v, psi, kappa, segA, segB, blk;
     // grid
-    DevBuf grid, clear, clear_tmp;
+    DevBuf grid, clear, clear_tmp, edt;
     int use_clearance = 1;
     int gh = 0, gw = 0;
     double gox = 0, goy = 0, gres = 1;
@@ -160,12 +171,33 @@ TrackView track_view(f1l_handle h) {
 GridView grid_view(f1l_handle h) {
     GridView g;
     g.occ = (const uint8_t*)h->grid.p;
-    g.clear = h->use_clearance ? (const uint8_t*)h->clear.p : nullptr;
-    // all nine probes fall within ceil(r_circ / res) cells of the centre cell (+1 for rounding)
-    const double rc = 0.5 * std::sqrt(h->cfg.car_length * h->cfg.car_length +
-                                      h->cfg.car_width * h->cfg.car_width);
-    g.probe_reach = (int)std::ceil(rc / h->gres) + 1;
-    if (g.probe_reach > CLEAR_R) g.clear = nullptr;  // map too fine for the clearance radius
+    // three covering discs (collision_mode 1): centres -L/3, 0, +L/3 on the body axis, radius
+    // sqrt((L/6)^2 + (W/2)^2); thresholds on the squared cell distance of the transform
+    const double L = h->cfg.car_length, W = h->cfg.car_width;
+    const double r_cells = std::sqrt(L * L / 36.0 + W * W / 4.0) / h->gres;
+    const double off_cells = (L / 3.0) / h->gres;
+    g.edt2 = (const uint16_t*)h->edt.p;
+    // centre-to-centre cell distances: the disc centre lies within half a cell diagonal of its
+    // cell's centre and an occupied cell reaches half a diagonal beyond its own, so the discs
+    // (hence the rectangle they cover) are clear of every occupied cell iff d > r + sqrt(2)
+    const double t = r_cells + 1.4142135623730951;
+    g.disc_t2 = (int)std::floor(t * t) + 1;
+    g.disc_off = (float)(L / 3.0);
+    if (h->cfg.collision_mode == 1) {
+        // the outer discs' cells lie within off + sqrt(2) (+1 for FP32 cell rounding) cells of the
+        // centre's cell and the transform is 1-Lipschitz: at this distance no disc can collide
+        const double far = std::sqrt((double)g.disc_t2) + off_cells + 2.5;
+        g.near_map = g.edt2;
+        g.near_free = (int)std::ceil(far * far);
+    } else {
+        // all nine probes fall within ceil(r_circ / res) cells of the centre cell (+1 for
+        // rounding): a larger Chebyshev clearance proves them free
+        const double rc = 0.5 * std::sqrt(L * L + W * W);
+        const int probe_reach = (int)std::ceil(rc / h->gres) + 1;
+        g.near_map = h->use_clearance ? (const uint16_t*)h->clear.p : nullptr;
+        g.near_free = probe_reach + 1;
+        if (probe_reach > CLEAR_R) g.near_map = nullptr;   // map too fine for the clearance radius
+    }
     g.h = h->gh;
     g.w = h->gw;
     g.ox = h->gox;
@@ -201,6 +233,7 @@ EvalParams eval_params(f1l_handle h) {
     e.use_goal_kappa = c.use_goal_kappa;
     e.generator = c.generator;
     e.prune = c.prune_window != 0;
+    e.collision_mode = c.collision_mode;
     for (int i = 0; i < F1L_N_TERMS; ++i) e.w[i] = (float)c.weights[i];
     e.kappa_max = (float)c.kappa_max;
     e.half_l = (float)(0.5 * c.car_length);
@@ -220,6 +253,7 @@ int check_config(const f1l_config* c) {
     if (c->n_newton < 0 || c->n_newton > 64) return F1L_ERR_INVALID_ARG;
     if (c->n_shift < 0 || c->n_cull < 0) return F1L_ERR_INVALID_ARG;
     if (c->generator < 0 || c->generator > 1) return F1L_ERR_INVALID_ARG;
+    if (c->collision_mode < 0 || c->collision_mode > 1) return F1L_ERR_INVALID_ARG;
     if (!(c->car_length > 0) || !(c->car_width > 0)) return F1L_ERR_INVALID_ARG;
     return F1L_OK;
 }
@@ -468,6 +502,11 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     if (max_opp > F1L_MAX_OPP || max_opp < 0) return F1L_ERR_INVALID_ARG;
     const int M = h->cfg.n_samples;
     const EvalParams ep = eval_params(h);
+    if (ep.collision_mode == 1 && h->grid.p) {
+        // the distance transform is exact up to CLEAR_R cells: a finer map needs a larger radius
+        const GridView gv = grid_view(h);
+        if (gv.near_free > CLEAR_R * CLEAR_R) return F1L_ERR_TOO_LARGE;
+    }
     const int nsegs = h->n - 1;
     int nseg = h->cfg.window;
     if (nseg <= 0 || nseg > nsegs) nseg = nsegs;
@@ -496,6 +535,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     sa.best = best;
     cudaEvent_t* ev = h->ev + 4 * h->ev_next;
     if (time_it) cudaEventRecord(ev[0], stream);
+    nvtxRangePushA("f1l.sample");
     if (near_i && near4 && S >= 32) {
         // batch: nearest_point of all scenarios by the thread-per-pose scan kernel (K1), then one
         // warp per scenario for the lookahead intersections / context
@@ -521,8 +561,10 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
         }
         sample_kernel<<<S, st_threads, 0, stream>>>(sa);
     }
+    nvtxRangePop();
     if (time_it) cudaEventRecord(ev[1], stream);
 
+    NvtxRange nvtx_eval_select("f1l.eval+select");
     EvalArgs ea;
     ea.tr = sa.tr;
     ea.grid = sa.grid;
@@ -845,7 +887,7 @@ int f1l_destroy(f1l_handle h) {
     cudaDeviceSynchronize();
     f1l_xchg_detach(h);
     release(h->xchg);
-    DevBuf* bufs[] = {&h->xy, &h->v, &h->psi, &h->kappa, &h->segA, &h->segB, &h->blk, &h->grid, &h->clear, &h->clear_tmp,
+    DevBuf* bufs[] = {&h->xy, &h->v, &h->psi, &h->kappa, &h->segA, &h->segB, &h->blk, &h->grid, &h->clear, &h->clear_tmp, &h->edt,
                       &h->lut, &h->lookaheads, &h->widths, &h->prev, &h->q_res, &h->q_in, &h->q_goals,
                       &h->q_ctx, &h->q_centres, &h->q_best, &h->q_detail, &h->q_params, &h->q_flags, &h->q_states, &h->q_headings, &h->b_ctx, &h->b_centres,
                       &h->b_best, &h->b_near_i, &h->b_near4, &h->stats, &h->m_in, &h->m_in2, &h->m_o0, &h->m_o1, &h->m_o2, &h->m_o3,
@@ -931,15 +973,18 @@ int f1l_set_grid(f1l_handle h, const uint8_t* occ, int height, int width, double
     ENS(h->grid, (size_t)height * width);
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaMemcpy(h->grid.p, occ, (size_t)height * width, cudaMemcpyHostToDevice));
-    ENS(h->clear, (size_t)height * width);
+    ENS(h->clear, (size_t)height * width * sizeof(uint16_t));
     ENS(h->clear_tmp, (size_t)height * width);
+    ENS(h->edt, (size_t)height * width * sizeof(uint16_t));
     {
         dim3 blk(256), grd((width + 255) / 256, height);
         clearance_h_kernel<<<grd, blk, 0, h->stream>>>((const uint8_t*)h->grid.p, height, width,
                                                        (uint8_t*)h->clear_tmp.p);
         clearance_v_kernel<<<grd, blk, 0, h->stream>>>((const uint8_t*)h->clear_tmp.p, height, width,
-                                                       (uint8_t*)h->clear.p);
-        h->launches += 2;
+                                                       (uint16_t*)h->clear.p);
+        edt_v_kernel<<<grd, blk, 0, h->stream>>>((const uint8_t*)h->clear_tmp.p, height, width,
+                                                 (uint16_t*)h->edt.p);
+        h->launches += 3;
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(h->stream));
     }
@@ -959,8 +1004,17 @@ int f1l_clear_grid(f1l_handle h) {
     release(h->grid);
     release(h->clear);
     release(h->clear_tmp);
+    release(h->edt);
     h->epoch++;
     h->gh = h->gw = 0;
+    return F1L_OK;
+}
+
+int f1l_get_edt(f1l_handle h, uint16_t* out) {
+    if (!h || !out || !h->edt.p || h->gh <= 0) return F1L_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out, h->edt.p, (size_t)h->gh * h->gw * sizeof(uint16_t), cudaMemcpyDeviceToHost));
     return F1L_OK;
 }
 
@@ -1043,6 +1097,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     const int M = h->cfg.n_samples;
     cudaStream_t st = h->stream;
 
+    NvtxRange nvtx_plan("f1l.plan (single query)");
     // stage inputs (pinned)
     QInput* hin = (QInput*)h->h_in;
     memcpy(hin->pose, pose, 4 * sizeof(double));
@@ -1442,15 +1497,23 @@ int f1l_plan_batch(f1l_handle h, const double* poses, const double* opp, const i
     const int M = h->cfg.n_samples;
     // chunked 3-stream pipeline: H2D(i+1) | kernels(i) | D2H(i-1)
     // 8192-scenario chunks (0.23 M candidates: 1 ms of kernels against ~30 us of launches) for
-    // large batches; smaller batches are cut into about eight chunks, down to 1024 scenarios, so
-    // that the first H2D and the last D2H -- the only copies nothing overlaps -- stay short
+    // large batches; smaller batches are cut into about eight chunks, down to 1024 scenarios.  The
+    // last chunks taper (half, quarter, ... of a chunk, down to 1024): the result copy of the final
+    // chunk is the one transfer nothing overlaps, 14 MB at full size but under 2 MB tapered.
     int chunk = 8192;
-    if (const char* e = getenv("F1L_PIPE_CHUNK")) { const int v = atoi(e); if (v > 0) chunk = v; }
+    bool taper = true;
+    if (const char* e = getenv("F1L_PIPE_CHUNK")) { const int v = atoi(e); if (v > 0) { chunk = v; taper = false; } }
     else if (S < 8 * chunk) { chunk = (S + 7) / 8; if (chunk < 1024) chunk = 1024; }
     if (chunk > S) chunk = S;
     int slot = 0;
-    for (int s0 = 0; s0 < S; s0 += chunk, slot = (slot + 1) % N_PIPE) {
-        const int n = (S - s0 < chunk) ? (S - s0) : chunk;
+    for (int s0 = 0, n = 0; s0 < S; s0 += n, slot = (slot + 1) % N_PIPE) {
+        n = (S - s0 < chunk) ? (S - s0) : chunk;
+        if (taper) {
+            // rest = what is left after this chunk: keep halving while the tail is short
+            const int rest = S - s0;
+            if (rest < 2 * chunk && rest > 1024) { n = rest / 2; if (n < 1024) n = 1024; if (n > rest) n = rest; }
+        }
+        NvtxRange nvtx_chunk("f1l.plan_batch.chunk (H2D, kernels, D2H)");
         PipeSlot& p = h->pipe[slot];
         cudaStream_t st = p.stream;
         CK(cudaStreamSynchronize(st));  // slot buffers free again (grow-only ensure below)
@@ -1508,6 +1571,7 @@ int f1l_pure_pursuit_batch_dev(f1l_handle h, const double* poses_dev, int n_pose
     if (!h || !poses_dev || n_poses <= 0) return F1L_ERR_INVALID_ARG;
     if (h->n < 2) return F1L_ERR_NO_TRACK;
     CK(cudaSetDevice(h->device));
+    NvtxRange nvtx_pp("f1l.pure_pursuit_batch (K1 scan + finish)");
     PPOut o;
     o.nearest = nearest_dev;
     o.nearest_i = nearest_i_dev;

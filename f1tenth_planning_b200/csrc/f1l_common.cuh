@@ -33,10 +33,18 @@ struct TrackView {
 
 struct GridView {
     const uint8_t* occ;    // [h, w] row-major, 0 free
-    const uint8_t* clear;  // [h, w] Chebyshev clearance in cells (0 = occupied), or null
+    // [h, w] uint16 "how far is the nearest occupied / out-of-bounds cell" map the footprint test
+    // looks up first (or null): collision_mode 0 -- Chebyshev clearance in cells (0 = occupied);
+    // collision_mode 1 -- squared Euclidean cell distance (edt2).  A sample whose value is at least
+    // near_free cannot collide and skips the per-footprint test.
+    const uint16_t* near_map;
+    int near_free;
     int h, w;
-    int probe_reach;       // probes lie within this many cells of the footprint-centre cell
     double ox, oy, inv_res;
+    // collision_mode 1: three discs on the Euclidean distance transform
+    const uint16_t* edt2;  // [h, w] squared cell distance to the nearest occupied / out-of-bounds cell
+    int disc_t2;           // a disc collides iff edt2[its centre's cell] < disc_t2 = ceil((r_disc / res)^2)
+    float disc_off;        // disc spacing along the body axis, L / 3 (metres)
 };
 
 struct LutView {
@@ -55,6 +63,7 @@ struct EvalParams {
     int literal_tracker, use_goal_kappa;
     int generator;    // 0 cubic spiral, 1 G1 clothoid
     int prune;        // deviation pass: skip window segments that cannot be nearest
+    int collision_mode;  // 0 nine probes, 1 three discs on the distance transform
     float w[F1L_N_TERMS];
     float kappa_max;  // <= 0: off
     float half_l, half_w;

@@ -1180,16 +1180,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             // out-of-bounds cell.  All nine probes fall within `probe_reach` cells of the
             // footprint-centre cell, so a larger clearance proves them free without touching
             // them.  The loads are issued first, the opponent tests cover their latency.
+            // (collision_mode 1, three discs on the Euclidean distance transform, works the same
+            // way: the squared distance at the footprint centre's cell, when at least near_free,
+            // proves all three discs free.)
             int clr[IPL];
 #pragma unroll
             for (int j = 0; j < IPL; ++j) {
                 clr[j] = 0;
-                if (has_grid && a.grid.clear && j < nown) {
+                if (has_grid && a.grid.near_map && j < nown) {
                     const float ccx = fa(fa(fm(A00, x[j]), fm(A01, y[j])), gfx);
                     const float ccy = fa(fa(fm(A10, x[j]), fm(A11, y[j])), gfy);
                     const int ccol = gix + __float2int_rd(ccx), crow = giy + __float2int_rd(ccy);
                     if ((unsigned)ccol < (unsigned)gw && (unsigned)crow < (unsigned)gh)
-                        clr[j] = __ldg(a.grid.clear + (size_t)crow * gw + ccol);
+                        clr[j] = __ldg(a.grid.near_map + (size_t)crow * gw + ccol);
                 }
             }
             // candidate-level opponent pruning: every point of a curve of length s_f from the
@@ -1236,12 +1239,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 int total = 0;
 #pragma unroll
                 for (int j = 0; j < IPL; ++j) {
-                    nm[j] = __ballot_sync(F1L_FULL, j < nown && clr[j] <= a.grid.probe_reach);
+                    nm[j] = __ballot_sync(F1L_FULL, j < nown && clr[j] < a.grid.near_free);
                     total += __popc(nm[j]);
                 }
                 if (total) {   // warp-uniform
                     const uint32_t pl = wbase + L::W_PLIST;
                     int rank0 = 0;
+                    const bool discs = a.ep.collision_mode == 1;     // uniform
+                    const float al = discs ? a.grid.disc_off : hl;   // extent along the body axis
 #pragma unroll
                     for (int j = 0; j < IPL; ++j) {
                         if ((nm[j] >> lane) & 1u) {
@@ -1249,7 +1254,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                             // footprint centre and half-axes in grid-cell coordinates
                             const float ccx = fa(fa(fm(A00, x[j]), fm(A01, y[j])), gfx);
                             const float ccy = fa(fa(fm(A10, x[j]), fm(A11, y[j])), gfy);
-                            const float lx = fm(cs[j], hl), ly = fm(sn[j], hl);    // body x axis * hl
+                            const float lx = fm(cs[j], al), ly = fm(sn[j], al);    // body x axis * extent
                             const float wx = fm(-sn[j], hw), wy = fm(cs[j], hw);   // body y axis * hw
                             sts128(pl + 32 * r, make_float4(ccx, ccy, fa(fm(A00, lx), fm(A01, ly)),
                                                             fa(fm(A10, lx), fm(A11, ly))));
@@ -1259,18 +1264,33 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                         rank0 += __popc(nm[j]);
                     }
                     __syncwarp();
-                    // 4 corners, 4 edge mid-points, centre (SURVEY B.6, P = 9): probe p sits at
-                    // centre + sa * l-axis + sb * w-axis with (sa, sb) in {-1, 0, 1}, two bits each.
-                    // x + (+-1) * e and x + 0 * e round like x +- e and x, so the cells are the
-                    // ones the oracle's float32 mirror visits.
-                    const int nwork = total * 9;
-                    for (int w = lane; w < nwork; w += 32) {
-                        const int fp = w / 9, p = w - 9 * fp;
-                        const float4 P0 = lds128(pl + 32 * fp), P1 = lds128(pl + 32 * fp + 16);
-                        const float sa = (float)(int)((0x1520au >> (2 * p)) & 3u) - 1.0f;
-                        const float sb = (float)(int)((0x12522u >> (2 * p)) & 3u) - 1.0f;
-                        hit_map |= grid_hit(occ, gw, gh, gix, giy, fa(fa(P0.x, fm(sa, P0.z)), fm(sb, P1.x)),
-                                            fa(fa(P0.y, fm(sa, P0.w)), fm(sb, P1.y)));
+                    if (discs) {
+                        // the three discs of every listed footprint: centre and +- L/3 along the
+                        // body axis, one distance-transform lookup each (out of bounds = collision)
+                        const int nwork = total * 3;
+                        for (int w = lane; w < nwork; w += 32) {
+                            const int fp = w / 3;
+                            const float sa = (float)(w - 3 * fp) - 1.0f;
+                            const float4 P0 = lds128(pl + 32 * fp);
+                            const int col = gix + __float2int_rd(fa(P0.x, fm(sa, P0.z)));
+                            const int row = giy + __float2int_rd(fa(P0.y, fm(sa, P0.w)));
+                            if ((unsigned)col >= (unsigned)gw || (unsigned)row >= (unsigned)gh) hit_map = true;
+                            else if ((int)__ldg(a.grid.edt2 + (size_t)row * gw + col) < a.grid.disc_t2) hit_map = true;
+                        }
+                    } else {
+                        // 4 corners, 4 edge mid-points, centre (SURVEY B.6, P = 9): probe p sits at
+                        // centre + sa * l-axis + sb * w-axis with (sa, sb) in {-1, 0, 1}, two bits each.
+                        // x + (+-1) * e and x + 0 * e round like x +- e and x, so the cells are the
+                        // ones the oracle's float32 mirror visits.
+                        const int nwork = total * 9;
+                        for (int w = lane; w < nwork; w += 32) {
+                            const int fp = w / 9, p = w - 9 * fp;
+                            const float4 P0 = lds128(pl + 32 * fp), P1 = lds128(pl + 32 * fp + 16);
+                            const float sa = (float)(int)((0x1520au >> (2 * p)) & 3u) - 1.0f;
+                            const float sb = (float)(int)((0x12522u >> (2 * p)) & 3u) - 1.0f;
+                            hit_map |= grid_hit(occ, gw, gh, gix, giy, fa(fa(P0.x, fm(sa, P0.z)), fm(sb, P1.x)),
+                                                fa(fa(P0.y, fm(sa, P0.w)), fm(sb, P1.y)));
+                        }
                     }
                     __syncwarp();
                 }
@@ -1593,7 +1613,7 @@ __global__ void clearance_h_kernel(const uint8_t* __restrict__ occ, int h, int w
     hd[(size_t)row * w + col] = (uint8_t)d;
 }
 __global__ void clearance_v_kernel(const uint8_t* __restrict__ hd, int h, int w,
-                                   uint8_t* __restrict__ clear) {
+                                   uint16_t* __restrict__ clear) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
     if (col >= w) return;
     int best = hd[(size_t)row * w + col];
@@ -1605,7 +1625,27 @@ __global__ void clearance_v_kernel(const uint8_t* __restrict__ hd, int h, int w,
         const int m = max(k, min(da, db));
         best = min(best, m);
     }
-    clear[(size_t)row * w + col] = (uint8_t)best;
+    clear[(size_t)row * w + col] = (uint16_t)best;
+}
+
+// Exact Euclidean distance transform up to CLEAR_R cells, second (vertical) pass over the
+// horizontal distances `hd` of clearance_h_kernel (0 = occupied, out of bounds counts as
+// occupied, CLEAR_R + 1 = farther):  d^2(r, c) = min over dr of dr^2 + hd(r + dr, c)^2.  A nearest
+// occupied cell within Euclidean distance CLEAR_R has |dr|, |dc| <= CLEAR_R, so every value up to
+// CLEAR_R^2 is exact; larger ones are stored as the sentinel CLEAR_R^2 + 1.
+#define EDT_FAR (CLEAR_R * CLEAR_R + 1)
+__global__ void edt_v_kernel(const uint8_t* __restrict__ hd, int h, int w, uint16_t* __restrict__ edt2) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+    if (col >= w) return;
+    int best = EDT_FAR;
+    for (int dr = -CLEAR_R; dr <= CLEAR_R; ++dr) {
+        const int r = row + dr;
+        int d = 0;                                            // a row outside the grid is occupied
+        if (r >= 0 && r < h) d = hd[(size_t)r * w + col];
+        if (d > CLEAR_R) continue;                            // nothing within reach in that row
+        best = min(best, dr * dr + d * d);
+    }
+    edt2[(size_t)row * w + col] = (uint16_t)min(best, EDT_FAR);
 }
 
 __global__ void fill_f32_kernel(float* __restrict__ p, size_t n, float v) {

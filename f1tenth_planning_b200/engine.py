@@ -124,6 +124,13 @@ class Engine:
         self._ck(self._L.f1l_set_grid(self._h, _ptr(g, _bp), g.shape[0], g.shape[1],
                                       float(origin[0]), float(origin[1]), float(resolution)))
 
+    def get_edt(self, shape):
+        """[H, W] uint16 squared cell distance to the nearest occupied / out-of-bounds cell (exact
+        to 576, 577 = farther): the transform collision_mode=1 looks up (f1l_get_edt)."""
+        out = np.zeros(shape, np.uint16)
+        self._ck(self._L.f1l_get_edt(self._h, _vp(out)))
+        return out
+
     def clear_grid(self):
         self._ck(self._L.f1l_clear_grid(self._h))
 

@@ -76,6 +76,17 @@ typedef struct {
                                 (default); 1 = skip the window segments that provably cannot be
                                 nearest to any sample of the candidate (chord-midpoint bound).
                                 Same minima, hence bit-identical costs, fewer segment tests. */
+    int32_t collision_mode;  /* occupancy-grid collision test of a footprint (map_collision stub,
+                                utils/utils.py:297-301): 0 = nine probe points (corners, edge
+                                mid-points, centre; default); 1 = three discs along the body axis
+                                (centres -L/3, 0, +L/3, radius sqrt((L/6)^2 + (W/2)^2): they cover
+                                the rectangle), ONE lookup each in a Euclidean distance transform of
+                                the grid built at f1l_set_grid -- a disc collides iff the distance
+                                (in cells, between cell centres) from its centre's cell to the
+                                nearest occupied / out-of-bounds cell is at most radius/res + sqrt 2
+                                (half a cell diagonal for the centre within its cell, half for the
+                                extent of the occupied cell): strictly conservative, every
+                                nine-probe collision is a disc collision */
     double weights[F1L_N_TERMS]; /* cost weights (lattice_planner.py:130-156) */
     double kappa_max;        /* candidates with max|kappa| above it are invalid; <=0 disables */
     double car_length;       /* 0.58 */
@@ -112,6 +123,10 @@ int f1l_set_track(f1l_handle h, const double* wpts, int n, int ncols);
 int f1l_set_grid(f1l_handle h, const uint8_t* occ, int height, int width,
                  double origin_x, double origin_y, double resolution);
 int f1l_clear_grid(f1l_handle h);
+/* The Euclidean distance transform collision_mode = 1 looks up: out [H, W] uint16 = squared
+ * distance in cells from each cell to the nearest occupied or out-of-bounds cell, exact up to
+ * 24^2 = 576, 577 = farther.  Built on the device by f1l_set_grid. */
+int f1l_get_edt(f1l_handle h, uint16_t* out);
 
 /* Goal grid of the built-in sampler: lookahead distances x lateral widths.
  * Replaces the kwargs of sample_lookahead_square (lattice_planner.py:228-229).

@@ -338,9 +338,12 @@ void f1o_spiral_sample(const double q[3], double p0, double p3, int m, double* s
 /* Bertolazzi & Frego, "G1 fitting with clothoids" (2015): with the chord as x axis,
  * phi0 = theta0 - phi, phi1 = theta1 - phi, delta = phi1 - phi0, find A with
  *   g(A) = int_0^1 sin(A t^2 + (delta - A) t + phi0) dt = 0          (1-D Newton from 3(phi0+phi1))
- * then L = r / int_0^1 cos(...), kappa0 = (delta - A)/L, dkappa = 2A/L^2.  Integrals by the same
- * composite Simpson rule (Q = 32) as the cubic-spiral Newton.  pyclothoids is absent here, so
- * this stage is parity-unpinned; tests check it against scipy.integrate. */
+ * then L = r / int_0^1 cos(...), kappa0 = (delta - A)/L, dkappa = 2A/L^2.  pyclothoids (absent
+ * here) evaluates these Fresnel-type integrals in closed form, so the oracle integrates them to
+ * float64 accuracy -- composite Simpson on 4096 intervals, error ~1e-15 -- and the tests pin the
+ * result to the closed-form Fresnel solution (scipy.special.fresnel) at 1e-12.  (The device uses
+ * 32 intervals in FP32: ~4e-7 relative, inside the 1e-4 tolerance.) */
+#define F1O_QC 4096
 static double normalize_angle(double a) {
     while (a > PI) a -= 2.0 * PI;
     while (a <= -PI) a += 2.0 * PI;
@@ -358,15 +361,15 @@ int f1o_clothoid_g1(const double goal[3], int n_newton, double out[3]) {
     for (int it = 0; it <= n_newton; ++it) {
         double g = 0.0, dg = 0.0;
         X = 0.0;
-        for (int j = 0; j <= F1O_Q; ++j) {
-            const double t = (double)j / F1O_Q;
-            const double w = ((j == 0 || j == F1O_Q) ? 1.0 : ((j & 1) ? 4.0 : 2.0)) / (3.0 * F1O_Q);
+        for (int j = 0; j <= F1O_QC; ++j) {
+            const double t = (double)j / F1O_QC;
+            const double w = ((j == 0 || j == F1O_QC) ? 1.0 : ((j & 1) ? 4.0 : 2.0)) / (3.0 * F1O_QC);
             const double ph = A * t * t + (delta - A) * t + phi0;
             const double c = cos(ph), s = sin(ph);
             g += w * s; X += w * c; dg += w * c * (t * t - t);
         }
-        if (fabs(g) < 1e-12) { ok = 1; break; }
-        if (it == n_newton) break;
+        if (fabs(g) < 1e-15) { ok = 1; break; }
+        if (it == n_newton) { ok = fabs(g) < 1e-12; break; }
         A -= g / dg;
     }
     const double L = r / X;
@@ -377,10 +380,28 @@ int f1o_clothoid_g1(const double goal[3], int n_newton, double out[3]) {
 }
 
 void f1o_clothoid_sample(const double kdl[3], int m, double* st) {
-    /* a clothoid is the cubic spiral with linear curvature: knots on the line kappa0 + dkappa s */
-    const double L = kdl[2], k0 = kdl[0], k1 = kdl[0] + kdl[1] * L;
-    const double q[3] = {k0 + (k1 - k0) / 3.0, k0 + 2.0 * (k1 - k0) / 3.0, L};
-    f1o_spiral_sample(q, k0, k1, m, st);
+    /* theta(s) = kappa0 s + dkappa s^2 / 2; x, y by Simpson on 32 sub-intervals of every sample
+     * interval (error ~1e-16 per interval: float64-exact against the Fresnel closed form) */
+    const double L = kdl[2], k0 = kdl[0], dk = kdl[1];
+    const double h = L / (double)(m > 1 ? m - 1 : 1);
+    const int sub = 32;
+    double x = 0.0, y = 0.0;
+    for (int i = 0; i < m; ++i) {
+        if (i > 0) {
+            const double s0 = (i - 1) * h, hs = h / sub;
+            double ax = 0.0, ay = 0.0;
+            for (int j = 0; j <= sub; ++j) {
+                const double sj = s0 + j * hs, th = k0 * sj + 0.5 * dk * sj * sj;
+                const double w = (j == 0 || j == sub) ? 1.0 : ((j & 1) ? 4.0 : 2.0);
+                ax += w * cos(th); ay += w * sin(th);
+            }
+            x += ax * hs / 3.0; y += ay * hs / 3.0;
+        }
+        const double si = i * h;
+        st[4 * i] = x; st[4 * i + 1] = y;
+        st[4 * i + 2] = k0 * si + 0.5 * dk * si * si;
+        st[4 * i + 3] = k0 + dk * si;
+    }
 }
 
 /* heuristic seed */
@@ -558,6 +579,35 @@ static int grid_probe(const f1o_world* w, double X, double Y, double* margin) {
     return occ;
 }
 
+/* collision_mode 1: does the disc centred at (X, Y) collide?  status of a cell = out of bounds or
+ * edt2 < t2; *margin = distance (m) from the centre to the nearest neighbouring cell of different
+ * status (the only place where the FP32 device path may legitimately decide differently) */
+static int edt_status(const f1o_world* w, long col, long row, int t2) {
+    if (col < 0 || row < 0 || col >= w->gw || row >= w->gh) return 1;
+    return (int)w->edt2[(size_t)row * w->gw + col] < t2;
+}
+
+static int edt_probe(const f1o_world* w, double X, double Y, int t2, double* margin) {
+    const double fx = (X - w->gox) / w->gres, fy = (Y - w->goy) / w->gres;
+    const long col = (long)floor(fx), row = (long)floor(fy);
+    const int st = edt_status(w, col, row, t2);
+    if (margin) {
+        const double ax = fx - (double)col, ay = fy - (double)row;
+        double best = INFINITY;
+        for (int dy = -1; dy <= 1; ++dy)
+            for (int dx = -1; dx <= 1; ++dx) {
+                if (!dx && !dy) continue;
+                if (edt_status(w, col + dx, row + dy, t2) == st) continue;
+                const double ex = dx < 0 ? ax : (dx > 0 ? 1.0 - ax : 0.0);
+                const double ey = dy < 0 ? ay : (dy > 0 ? 1.0 - ay : 0.0);
+                const double d = sqrt(ex * ex + ey * ey) * w->gres;
+                if (d < best) best = d;
+            }
+        *margin = best;
+    }
+    return st;
+}
+
 /* ------------------------------------------------------------------------- */
 /* one query                                                                  */
 /* ------------------------------------------------------------------------- */
@@ -661,7 +711,25 @@ int f1o_plan(const f1o_config* cfg, const f1o_world* w, const double pose[4], co
                     if (tx * tx + ty * ty > rc2) continue; /* broad phase */
                     if (sep < 0.0) hit_opp = 1;
                 }
-                if (w->grid) {
+                if (w->grid && cfg->collision_mode == 1 && w->edt2) {
+                    /* three covering discs on the body axis at -L/3, 0, +L/3 (radius
+                     * sqrt((L/6)^2 + (W/2)^2)), one distance-transform lookup each: a disc
+                     * collides iff the squared cell distance at its centre's cell is at most
+                     * (radius / res + sqrt 2)^2; out of bounds = collision */
+                    const double cth = cos(TH), sth = sin(TH);
+                    const double rc = sqrt(cfg->car_length * cfg->car_length / 36.0 +
+                                           cfg->car_width * cfg->car_width / 4.0) / w->gres;
+                    /* cell-centre distances: + half a cell diagonal for the disc centre within its
+                     * cell, + half for the extent of the occupied cell: strictly conservative */
+                    const double tc = rc + 1.4142135623730951;
+                    const int t2 = (int)floor(tc * tc) + 1;
+                    for (int d = -1; d <= 1; ++d) {
+                        const double off = d * cfg->car_length / 3.0;
+                        double mg;
+                        if (edt_probe(w, X + cth * off, Y + sth * off, t2, &mg)) hit_map = 1;
+                        if (mg < m_map) m_map = mg;
+                    }
+                } else if (w->grid) {
                     const double cth = cos(TH), sth = sin(TH);
                     for (int p = 0; p < 9; ++p) {
                         const double bx = PROBE[p][0] * hl, by = PROBE[p][1] * hw;

@@ -38,6 +38,7 @@ extern "C" {
 typedef struct {
     int32_t n_samples, n_newton, window, n_shift, n_cull, literal_tracker, use_goal_kappa, generator;
     int32_t prune_window; /* layout parity with f1l_config only: the oracle always scans the whole window */
+    int32_t collision_mode; /* 0: nine probes; 1: three discs on the Euclidean distance transform (world.edt2) */
     double weights[F1O_N_TERMS];
     double kappa_max, car_length, car_width, converge_tol, tracker_lookahead, wheelbase,
         max_reacquire;
@@ -57,6 +58,8 @@ typedef struct {
     const double* widths;
     int32_t n_lookaheads, n_widths;
     const float* prev_theta; /* [M] or NULL */
+    const uint16_t* edt2;    /* [gh, gw] squared cell distance to the nearest occupied / out-of-bounds
+                                cell (exact to 576, 577 = farther), collision_mode 1; or NULL */
 } f1o_world;
 
 typedef struct {

@@ -22,7 +22,7 @@ class Config(C.Structure):
     _fields_ = [("n_samples", C.c_int32), ("n_newton", C.c_int32), ("window", C.c_int32),
                 ("n_shift", C.c_int32), ("n_cull", C.c_int32), ("literal_tracker", C.c_int32),
                 ("use_goal_kappa", C.c_int32), ("generator", C.c_int32),
-                ("prune_window", C.c_int32),
+                ("prune_window", C.c_int32), ("collision_mode", C.c_int32),
                 ("weights", C.c_double * N_TERMS), ("kappa_max", C.c_double),
                 ("car_length", C.c_double), ("car_width", C.c_double),
                 ("converge_tol", C.c_double), ("tracker_lookahead", C.c_double),
@@ -35,7 +35,7 @@ class World(C.Structure):
                 ("gres", C.c_double), ("lut", _fp), ("lut_dims", C.c_int32 * 3),
                 ("pad0", C.c_int32), ("lut_ranges", C.c_double * 6), ("lookaheads", _dp),
                 ("widths", _dp), ("n_lookaheads", C.c_int32), ("n_widths", C.c_int32),
-                ("prev_theta", _fp)]
+                ("prev_theta", _fp), ("edt2", C.POINTER(C.c_uint16))]
 
 
 class Result(C.Structure):
@@ -194,6 +194,24 @@ def spiral(goal, p0=0.0, p3=0.0, n_newton=8, seed=None, m=100):
     return q, st
 
 
+_edt_cache = {}
+EDT_R = 24   # the transform is exact up to this many cells (CLEAR_R of the device library)
+
+
+def edt2_of(grid):
+    """Squared Euclidean distance, in cells between cell centres, from every cell to the nearest
+    occupied or out-of-bounds cell (uint16; exact up to EDT_R^2, EDT_R^2 + 1 = farther) -- by
+    scipy.ndimage.distance_transform_edt, independent of the device's separable two-pass build."""
+    from scipy import ndimage
+    g = np.asarray(grid) != 0
+    pad = EDT_R + 1
+    big = np.ones((g.shape[0] + 2 * pad, g.shape[1] + 2 * pad), bool)
+    big[pad:-pad, pad:-pad] = g
+    d = ndimage.distance_transform_edt(~big)[pad:-pad, pad:-pad]
+    d2 = np.rint(d * d).astype(np.int64)
+    return np.ascontiguousarray(np.minimum(d2, EDT_R * EDT_R + 1).astype(np.uint16))
+
+
 class World_:
     """Keeps the numpy buffers alive behind a C f1o_world."""
 
@@ -227,7 +245,17 @@ class World_:
         w.n_widths = self.widths.shape[0]
         if self.prev_theta is not None:
             w.prev_theta = self.prev_theta.ctypes.data_as(_fp)
+        self.edt2 = None   # built on first use by a collision_mode = 1 query (need_edt)
         self.c = w
+
+    def need_edt(self):
+        if self.edt2 is None and self.grid is not None:
+            import zlib
+            key = (self.grid.shape, zlib.crc32(self.grid))
+            if key not in _edt_cache:
+                _edt_cache[key] = edt2_of(self.grid)
+            self.edt2 = _edt_cache[key]
+            self.c.edt2 = self.edt2.ctypes.data_as(C.POINTER(C.c_uint16))
 
     def set_prev(self, prev_theta):
         self.prev_theta = (None if prev_theta is None
@@ -241,6 +269,8 @@ class World_:
 
 
 def plan(cfg, world, pose, opp=None, goals=None, c_begin=0, c_end=0, want_states=False):
+    if cfg.collision_mode == 1:
+        world.need_edt()
     pose = _as_f64(pose)
     M = cfg.n_samples
     if goals is not None:
@@ -276,6 +306,8 @@ def plan(cfg, world, pose, opp=None, goals=None, c_begin=0, c_end=0, want_states
 
 def plan_batch(cfg, world, poses, opp=None, n_opp=None, n_threads=1, want_traj=True,
                want_costs=True):
+    if cfg.collision_mode == 1:
+        world.need_edt()
     poses = _as_f64(poses).reshape(-1, 4)
     S = poses.shape[0]
     Cn = world.n_candidates

@@ -37,7 +37,7 @@ def record_parity(name, stats):
         pass
 
 CFG_FIELDS = ["n_samples", "n_newton", "window", "n_shift", "n_cull", "literal_tracker",
-              "use_goal_kappa", "generator", "kappa_max", "car_length", "car_width", "converge_tol",
+              "use_goal_kappa", "generator", "collision_mode", "kappa_max", "car_length", "car_width", "converge_tol",
               "tracker_lookahead", "wheelbase", "max_reacquire"]
 
 

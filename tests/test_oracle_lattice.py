@@ -272,3 +272,44 @@ def test_spiral_known_answer_straight_line_and_mirror():
         q2, s2 = co.spiral((g[0], -g[1], -g[2]), n_newton=12, m=64)
         np.testing.assert_allclose(q2, [-q1[0], -q1[1], q1[2]], rtol=1e-9, atol=1e-10)
         np.testing.assert_allclose(s2, s1 * np.array([1.0, -1.0, -1.0, -1.0]), atol=1e-9)
+
+
+def _clothoid_closed_form(k0, dk, s):
+    """(x, y) of the clothoid theta(t) = k0 t + dk t^2 / 2 from the origin, at arc lengths s, in
+    closed form through the Fresnel integrals S, C (scipy.special.fresnel; their argument
+    convention is int cos(pi t^2 / 2)).  Completing the square: theta = a (t + b)^2 - a b^2 with
+    a = dk / 2, b = k0 / dk."""
+    from scipy.special import fresnel
+    s = np.asarray(s, dtype=np.float64)
+    if abs(dk) < 1e-14:
+        if abs(k0) < 1e-14:
+            return s.copy(), np.zeros_like(s)
+        return np.sin(k0 * s) / k0, (1.0 - np.cos(k0 * s)) / k0
+    a, b = 0.5 * dk, k0 / dk
+    sg = 1.0 if a > 0 else -1.0
+    scale = np.sqrt(np.pi / (2.0 * abs(a)))
+    S1, C1 = fresnel((s + b) / scale)
+    S0, C0 = fresnel(b / scale)
+    Ic, Is = scale * (C1 - C0), sg * scale * (S1 - S0)     # int cos / sin of a (t + b)^2
+    ph = -a * b * b
+    return np.cos(ph) * Ic - np.sin(ph) * Is, np.sin(ph) * Ic + np.cos(ph) * Is
+
+
+@pytest.mark.parametrize("goal", [(1.0, 1.0, 0.0), (2.0, 0.5, 0.3), (3.0, -1.0, -0.4), (0.8, 0.6, 1.2),
+                                  (4.0, 0.0, 0.0), (2.5, 1.5, 1.0), (1.5, -1.2, -1.3), (3.5, 0.2, -0.2)])
+def test_g1_clothoid_pinned_to_fresnel_closed_form(goal):
+    """pyclothoids' Clothoid.G1Hermite evaluates the clothoid through Fresnel
+    integrals; the oracle's generator=1 path is pinned to that closed form at 1e-12 -- both the
+    solved (kappa0, dkappa, L), whose exact endpoint must be the goal, and every sampled state."""
+    kdl, st, ok = co.clothoid(goal, n_newton=12, m=100)
+    assert ok
+    k0, dk, L = kdl
+    s = np.linspace(0.0, L, 100)
+    x, y = _clothoid_closed_form(k0, dk, s)
+    scale = max(1.0, L)
+    assert np.abs(st[:, 0] - x).max() < 1e-12 * scale and np.abs(st[:, 1] - y).max() < 1e-12 * scale
+    np.testing.assert_allclose(st[:, 2], k0 * s + 0.5 * dk * s * s, rtol=0, atol=1e-13)
+    # the G1 interpolation conditions, evaluated in closed form
+    assert abs(x[-1] - goal[0]) < 1e-12 * scale and abs(y[-1] - goal[1]) < 1e-12 * scale
+    end_th = k0 * L + 0.5 * dk * L * L
+    assert abs(np.angle(np.exp(1j * (end_th - goal[2])))) < 1e-12
