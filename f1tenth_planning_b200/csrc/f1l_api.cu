@@ -1714,8 +1714,9 @@ int f1l_debug_query_ctx(f1l_handle h, float* out_f, int32_t* out_i) {
     out_f[2] = q.gA00; out_f[3] = q.gA01; out_f[4] = q.gA10; out_f[5] = q.gA11;
     out_f[6] = q.gfx; out_f[7] = q.gfy;
     for (int k = 0; k < F1L_MAX_OPP; ++k) {
-        out_f[8 + 4 * k] = q.opp[k].x; out_f[9 + 4 * k] = q.opp[k].y;
-        out_f[10 + 4 * k] = q.opp[k].z; out_f[11 + 4 * k] = q.opp[k].w;
+        const float4 o = k < q.n_opp ? q.opp[k] : make_float4(1e9f, 1e9f, 1.0f, 0.0f);   // unused: far away
+        out_f[8 + 4 * k] = o.x; out_f[9 + 4 * k] = o.y;
+        out_f[10 + 4 * k] = o.z; out_f[11 + 4 * k] = o.w;
     }
     out_i[0] = q.gix; out_i[1] = q.giy; out_i[2] = q.i_ego; out_i[3] = q.seg0;
     out_i[4] = q.nseg; out_i[5] = q.n_opp;

@@ -591,17 +591,15 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
 
     QueryCtx* q = a.ctx + s;
     const int n_opp = a.opp ? (a.n_opp ? min(a.n_opp[s], a.max_opp) : a.max_opp) : 0;
-    for (int k = lt; k < F1L_MAX_OPP; k += nt) {
-        float4 o = make_float4(1e9f, 1e9f, 1.0f, 0.0f);
-        if (k < n_opp) {
-            const double* op = a.opp + 3 * ((size_t)s * a.max_opp + k);
-            const double dx = op[0] - px, dy = op[1] - py, ph = op[2] - pth;
-            double so_, co_;
-            sincos(ph, &so_, &co_);
-            o = make_float4((float)(cth * dx + sth * dy), (float)(-sth * dx + cth * dy), (float)co_,
-                            (float)so_);
-        }
-        q->opp[k] = o;
+    // only the n_opp entries in use are written (and read back by eval_kernel): the other slots of
+    // the 16-entry table would be 2 x 256 bytes of HBM traffic per scenario for nothing
+    for (int k = lt; k < n_opp; k += nt) {
+        const double* op = a.opp + 3 * ((size_t)s * a.max_opp + k);
+        const double dx = op[0] - px, dy = op[1] - py, ph = op[2] - pth;
+        double so_, co_;
+        sincos(ph, &so_, &co_);
+        q->opp[k] = make_float4((float)(cth * dx + sth * dy), (float)(-sth * dx + cth * dy), (float)co_,
+                                (float)so_);
     }
     if (lt == nt - 1) {
         q->px = px; q->py = py; q->th = pth; q->vel = pv;
@@ -1009,7 +1007,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
 #pragma unroll 1
             for (int i = tid; i < M; i += NW * 32) sts32(cbase + L::C_PREV + i * 4, a.prev_theta[i]);
         }
-        if (tid < F1L_MAX_OPP) sts128(cbase + L::C_OPP + tid * 16, q->opp[tid]);
+        if (tid < F1L_MAX_OPP)   // unused slots: an opponent far away
+            sts128(cbase + L::C_OPP + tid * 16,
+                   tid < q->n_opp ? q->opp[tid] : make_float4(1e9f, 1e9f, 1.0f, 0.0f));
         if (tid == 0) { s_next = cb + NW * a.item; s_work = 0ull; }
         // per-scenario collision constants live in shared memory, not in registers, so that the
         // candidate loop does not carry them through the deviation pass
