@@ -240,6 +240,8 @@ EvalParams eval_params(f1l_handle h) {
     e.half_w = (float)(0.5 * c.car_width);
     const double hl = 0.5 * c.car_length, hw = 0.5 * c.car_width;
     e.rc2 = (float)(4.0 * (hl * hl + hw * hw));
+    e.reach_pad = sqrtf(e.rc2) + 1e-3f;
+    e.inv_M = 1.0f / (float)c.n_samples;
     e.tol = (float)c.converge_tol;
     e.tracker_lookahead = c.tracker_lookahead;
     e.wheelbase = c.wheelbase;
@@ -345,6 +347,13 @@ struct CtaPlan {
 CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count, bool cubic) {
     CtaPlan best{8, 8, 1};
     double best_cost = 1e300;
+    // tuning hook for experiments: F1L_EVAL_PLAN="<warps>,<candidates per CTA>"
+    if (const char* e = getenv("F1L_EVAL_PLAN")) {
+        int nw = 0, chunk = 0;
+        if (sscanf(e, "%d,%d", &nw, &chunk) == 2 && (nw == 4 || nw == 7 || nw == 8) && chunk >= nw &&
+            chunk % nw == 0 && !(nw != 8 && M > 128))
+            return CtaPlan{nw, chunk, (n_cand + chunk - 1) / chunk};
+    }
     const int nws[3] = {4, 7, 8};
     for (int nw : nws) {
 #ifdef F1L_FORCE_NW

@@ -68,6 +68,8 @@ struct EvalParams {
     float kappa_max;  // <= 0: off
     float half_l, half_w;
     float rc2;        // (2 r_circ)^2 broad-phase radius
+    float reach_pad;  // 2 r_circ + 1 mm: candidate-level opponent prune
+    float inv_M;      // 1 / M
     float tol;
     double tracker_lookahead, wheelbase, max_reacquire;
 };

@@ -686,8 +686,10 @@ sample_warp_kernel(SampleArgs a, const int32_t* __restrict__ near_i,
 // ---------------------------------------------------------------------------------------------
 #define EVAL_MAX_WARPS 8
 
-// collision predicate pieces use explicitly rounded FP32 ops (no FMA contraction) so that the
-// float32 mirror in the oracle reproduces the flags bit for bit on identical inputs.
+// collision predicate pieces use explicitly rounded FP32 ops (no implicit FMA contraction; the
+// sample -> grid-cell transform is written as explicit fused multiply-adds, fmaf in the mirror) so
+// that the float32 mirror in the oracle reproduces the flags bit for bit on identical inputs.
+__device__ __forceinline__ float ffm(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 __device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
@@ -1159,7 +1161,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
         if (valid) {  // warp-uniform
             const float t_len = __fdividef(1.0f, sp.sf);       // lattice_planner.py:271
             const float t_maxk = maxk;                         // :277
-            const float t_meank = sumk / (float)M;             // :284
+            const float t_meank = sumk * a.ep.inv_M;           // :284
             float t_sim = 0.0f;
 
             // ---- similarity (lattice_planner.py:287-296), collision ----
@@ -1175,7 +1177,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             const float A00 = GA.x, A01 = GA.y, A10 = GA.z, A11 = GA.w;
             const float gfx = GB.x, gfy = GB.y;
             const int gix = __float_as_int(GB.z), giy = __float_as_int(GB.w);
-            const float reach_pad = sqrtf(a.ep.rc2) + 1e-3f;
             // clearance map: clear[cell] = Chebyshev distance (cells) to the nearest occupied /
             // out-of-bounds cell.  All nine probes fall within `probe_reach` cells of the
             // footprint-centre cell, so a larger clearance proves them free without touching
@@ -1188,8 +1189,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             for (int j = 0; j < IPL; ++j) {
                 clr[j] = 0;
                 if (has_grid && a.grid.near_map && j < nown) {
-                    const float ccx = fa(fa(fm(A00, x[j]), fm(A01, y[j])), gfx);
-                    const float ccy = fa(fa(fm(A10, x[j]), fm(A11, y[j])), gfy);
+                    const float ccx = ffm(A00, x[j], ffm(A01, y[j], gfx));
+                    const float ccy = ffm(A10, x[j], ffm(A11, y[j], gfy));
                     const int ccol = gix + __float2int_rd(ccx), crow = giy + __float2int_rd(ccy);
                     if ((unsigned)ccol < (unsigned)gw && (unsigned)crow < (unsigned)gh)
                         clr[j] = __ldg(a.grid.near_map + (size_t)crow * gw + ccol);
@@ -1202,7 +1203,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             {
                 const float4 o = lds128(cbase + L::C_OPP + (lane & (F1L_MAX_OPP - 1)) * 16);
                 const float mx = o.x - 0.5f * ex, my = o.y - 0.5f * ey;
-                const float reach = 0.5f * sp.sf + reach_pad;
+                const float reach = 0.5f * sp.sf + a.ep.reach_pad;
                 opp_mask = __ballot_sync(F1L_FULL, lane < n_opp && fmaf(mx, mx, my * my) <= reach * reach);
             }
             if (a.prev_theta) {   // uniform
@@ -1252,8 +1253,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                         if ((nm[j] >> lane) & 1u) {
                             const int r = rank0 + __popc(nm[j] & ((1u << lane) - 1u));
                             // footprint centre and half-axes in grid-cell coordinates
-                            const float ccx = fa(fa(fm(A00, x[j]), fm(A01, y[j])), gfx);
-                            const float ccy = fa(fa(fm(A10, x[j]), fm(A11, y[j])), gfy);
+                            const float ccx = ffm(A00, x[j], ffm(A01, y[j], gfx));
+                            const float ccy = ffm(A10, x[j], ffm(A11, y[j], gfy));
                             const float lx = fm(cs[j], al), ly = fm(sn[j], al);    // body x axis * extent
                             const float wx = fm(-sn[j], hw), wy = fm(cs[j], hw);   // body y axis * hw
                             sts128(pl + 32 * r, make_float4(ccx, ccy, fa(fm(A00, lx), fm(A01, ly)),
@@ -1402,7 +1403,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 for (int j = 0; j < SP; ++j) { rows[2 * j] = bdx[j]; rows[2 * j + 1] = bdy[j]; }
                 if (ODD) rows[S - 1] = bdl;
                 const float dsum = halve_min_sqrt_sum<S, GG>(rows, ggi, nrows);
-                t_dev = warp_sum(dsum) * (1.0f / EVAL_DEV_SCALE) / (float)M;
+                t_dev = warp_sum(dsum) * ((1.0f / EVAL_DEV_SCALE) * a.ep.inv_M);
             }
 
             if (!(flags & (F1L_FLAG_COLLIDE_OPP | F1L_FLAG_COLLIDE_MAP))) {

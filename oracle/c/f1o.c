@@ -859,7 +859,8 @@ int64_t f1o_plan_batch(const f1o_config* cfg, const f1o_world* w, const double* 
 /* ------------------------------------------------------------------------- */
 /* Same operations in the same order and rounding as eval_kernel's collision block
  * (f1tenth_planning_b200/csrc/f1l_lattice.cuh: sat_collide / grid_hit and the explicitly
- * rounded fm/fa/fs arithmetic); compiled with -ffp-contract=off so that no FMA is formed.
+ * rounded fm/fa/fs arithmetic and the explicitly fused sample -> grid-cell transform); compiled
+ * with -ffp-contract=off so that no other FMA is formed.
  * Inputs are the device's own float32 states, footprint headings and per-query constants, so
  * the flags must agree bit for bit. */
 static int sat_collide_f32(float tx, float ty, float c, float s, float oc, float os, float hl,
@@ -900,8 +901,8 @@ void f1o_collide_f32(const float* states, const float* headings, int c, int m,
             }
             if (grid) {
                 const float A00 = grid_xf[0], A01 = grid_xf[1], A10 = grid_xf[2], A11 = grid_xf[3];
-                const float ccx = (A00 * x + A01 * y) + grid_xf[4];
-                const float ccy = (A10 * x + A11 * y) + grid_xf[5];
+                const float ccx = fmaf(A00, x, fmaf(A01, y, grid_xf[4]));   /* fused like the device */
+                const float ccy = fmaf(A10, x, fmaf(A11, y, grid_xf[5]));
                 const float lx = cs * hl, ly = sn * hl;
                 const float wx = -sn * hw, wy = cs * hw;
                 const float elx = A00 * lx + A01 * ly, ely = A10 * lx + A11 * ly;

@@ -39,7 +39,7 @@ seq = launch_table(launches)
 big = [i for i, (n, g, v) in enumerate(seq) if n.startswith("eval_kernel") and g.startswith("(100000")]
 lines = ["# ncu launch list, %s" % tag, "",
          "Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py "
-         "--steps 2 --warmup 1 --scenarios 100000 --no-extras --no-cpu-baseline` (cold-cache, serialised "
+         "--steps 2 --warmup 1 --quick` (cold-cache, serialised "
          "launches: compare shares, not absolutes).", "",
          "%d launches captured; the device-resident steps (eval grid = 100000 CTAs):" % len(seq), "",
          "| step | kernel | grid | ms | share of step |", "|---|---|---|---|---|"]
@@ -48,8 +48,7 @@ for si, i in enumerate(big):
     tot = sum(v for _, _, v in grp)
     for n, g, v in grp:
         lines.append("| %d | %s | %s | %.4f | %.1f %% |" % (si, n, g, v, 100 * v / tot))
-lines += ["", "Other launches: LUT build, clearance map (2), peak microbenchmarks (6), and the chunked "
-          "end-to-end arm (8192-scenario chunks of the same five kernels)."]
+lines += ["", "Other launches: LUT build, clearance map + distance transform (3), peak microbenchmarks."]
 open(os.path.join(out_dir, "%s_launches.md" % tag), "w").write("\n".join(lines) + "\n")
 
 

@@ -34,8 +34,8 @@ marks = [("prologue (window table)", k0),
          ("curvature / validity / slab", find("// ---- curvature terms", k0)),
          ("similarity + collision", find("// ---- similarity", k0)),
          ("deviation: setup + pruning bound", find("// ---- raceline deviation", k0)),
-         ("deviation: segment loop", find("float4 T0 = sT[2 * (k_begin + ggi)]", k0)),
-         ("deviation: reduce", find("for (int o = 1; o < GG; o <<= 1)", k0) - 1),
+         ("deviation: segment loop", find("uint32_t ta = cbase + L::C_TAB + (k_begin + ggi) * 32;", k0)),
+         ("deviation: reduce", find("float rows[S];", k0) - 3),
          ("cost + output + next candidate", find("if (!(flags & (F1L_FLAG_COLLIDE_OPP", k0)),
          ("end", find("// K5: select", k0))]
 
