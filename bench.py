@@ -449,6 +449,15 @@ def sharded_dense_query(track, grid, device, rank, world_size, dev):
     ts_q, _, best_q = run(32, False, True)
     eng.configure(prune_window=0)
     eng.detach_peers()
+    # where a rank's local time goes: device time of its three kernels (plain launches, CUDA events)
+    eng.set_timing(True)
+    for i in range(24):
+        eng.plan(poses[i % 16], opp[i % 16], update_prev=False, detail=False, rows=(rank, world_size))
+    k_ms = eng.mean_kernel_ms()[:3]
+    eng.set_timing(False)
+    tk = torch.tensor(k_ms, dtype=torch.float64, device=dev)
+    dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+    k_us = [1e3 * float(v) for v in tk.cpu().numpy()]
     eng.close()
     tl = torch.tensor([np.percentile(tp_n, 50), np.percentile(tp_r, 50)], dtype=torch.float64, device=dev)
     dist.all_reduce(tl, op=dist.ReduceOp.MAX)   # the slowest rank's local plan
@@ -466,6 +475,7 @@ def sharded_dense_query(track, grid, device, rank, world_size, dev):
             "c5_sharded_pruned_plan_p50_us": 1e6 * float(np.percentile(ts_q, 50)),
             "c5_sharded_pruned_note": "prune_window=1: provably-irrelevant window segments skipped, "
                                       "bit-identical costs and winner (c5_sharded_paths_agree covers it)",
+            "c5_sharded_kernel_us_slowest_rank": {"sample": k_us[0], "eval": k_us[1], "select": k_us[2]},
             "c5_sharded_paths_agree": best_n == best_p and best_c == best_p and best_q == best_p,
             "c5_candidates_per_rank": hi - lo, "c5_last_best": list(best_p[-1])}
 

@@ -51,7 +51,24 @@ assert np.array_equal(b.best_idx[:7], b2.best_idx)
 eng.configure(prune_window=1)
 bp = eng.plan_batch(poses, opp, n_opp)
 assert np.array_equal(bp.costs, b.costs)
-eng.configure(prune_window=0, generator=1)                      # G1 clothoid generator
+eng.configure(prune_window=0, collision_mode=1)                 # three discs on the distance transform
+check(eng.plan(poses[10], opp[10, :n_opp[10]], want_map=True))
+eng.plan_batch(poses[:40], opp[:40], n_opp[:40], want_flags=True)
+assert eng.get_edt(occ.shape).shape == occ.shape
+d = eng.plan(poses[11], opp[11, :1], want_states=True)
+t = eng.select_candidate(int(np.argmax(np.isfinite(d.costs))), 0.5, want_map=True)   # user selection
+assert t.best_traj_map.shape == (100, 4)
+check(eng.plan(poses[12], opp[12, :2], rows=(1, 3)))            # row-interleaved shard (own rows sampled)
+try:
+    eng.plan(poses[12], opp[12, :2], rows=(5, 8))               # a shard without rows is an error alone
+    raise SystemExit("expected an error")
+except RuntimeError:
+    pass
+eng.set_stats(True)
+check(eng.plan(poses[13], opp[13, :2]))
+assert eng.stats()[1] > 0
+eng.set_stats(False)
+eng.configure(collision_mode=0, generator=1)                    # G1 clothoid generator
 check(eng.plan(poses[6], opp[6, :n_opp[6]]))
 eng.plan_batch(poses[:40], opp[:40], n_opp[:40])
 eng.clear_grid()
