@@ -1329,9 +1329,21 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                     bdx[j] = CUDART_INF_F;
                     bdy[j] = CUDART_INF_F;
                 }
+                // Odd S: the last sample row is unpacked.  When it holds at most SG / 2 samples
+                // (M = 100: 4 of 8, M = 200: 8 of 16) the lanes of the upper half of the sample
+                // groups would only carry dummies; instead both halves take the SAME samples and
+                // split the two segments of a trip between them -- the lower half tests segment A,
+                // the upper half segment B, each from its own table address (one extra LDS.128
+                // pair per trip instead of a second 7-instruction scalar chain), and the two
+                // halves' minima meet in one shuffle after the loop.
+#ifndef EVAL_SPLIT_ODD
+#define EVAL_SPLIT_ODD 1
+#endif
+                const bool split_odd = EVAL_SPLIT_ODD && ODD && EVAL_DEV_MIN3 && (M - (S - 1) * SG) <= SG / 2;   // uniform
                 if (ODD) {
-                    sxl = lds32(ra + SP * SG * 8);
-                    syl = lds32(ra + SLAB * 4 + SP * SG * 8);
+                    const uint32_t ro = split_odd ? wbase + L::W_SLABX + (sgi & (SG / 2 - 1)) * 8 : ra;
+                    sxl = lds32(ro + SP * SG * 8);
+                    syl = lds32(ro + SLAB * 4 + SP * SG * 8);
                 }
                 const int nq = a.nseg_pad;
                 // segment range [k_begin, k_end) of the window this candidate is tested against
@@ -1374,6 +1386,19 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
 #if EVAL_DEV_MIN3
                 // two segments per trip: the running minimum takes both distances in one
                 // three-input FMNMX3 (nseg_pad / GG is a multiple of 8)
+                if (split_odd) {
+                    const uint32_t off = (sgi >= SG / 2) ? GG * 32 : 0;   // this lane's segment of the trip
+                    for (int n = (k_end - k_begin) / (2 * GG); n > 0; --n) {
+                        const float4 B0 = lds128(ta + GG * 32), B1 = lds128(ta + GG * 32 + 16);
+                        seg_min2<SP>(sx2, sy2, T0, T1, B0, B1, bdx, bdy);
+                        const uint32_t to = ta + off;
+                        bdl = fminf(bdl, seg_dist2(sxl, syl, lds128(to), lds128(to + 16)));
+                        ta += 2 * GG * 32;
+                        T0 = lds128(ta);   // EVAL_SEG_PAD entries of slack
+                        T1 = lds128(ta + 16);
+                    }
+                    bdl = fminf(bdl, __shfl_xor_sync(F1L_FULL, bdl, (SG / 2) * GG));
+                } else
                 for (int n = (k_end - k_begin) / (2 * GG); n > 0; --n) {
                     const float4 B0 = lds128(ta + GG * 32), B1 = lds128(ta + GG * 32 + 16);
                     seg_min2<SP>(sx2, sy2, T0, T1, B0, B1, bdx, bdy);
