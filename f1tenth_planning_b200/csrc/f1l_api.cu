@@ -456,6 +456,7 @@ struct BatchOut {
     int s_row0 = 0, s_step = 1, s_rows = -1;   // lookahead rows the sampler must fill (-1: all)
     bool empty_shard = false;          // this rank owns no candidate of the query: it evaluates nothing
                                        // but still takes part in the exchange (key = ~0)
+    int* work_next = nullptr;          // single query: device counter for the persistent-grid schedule
 };
 
 // select_kernel arguments of a pipeline over S scenarios (first_cand: the first evaluated candidate,
@@ -525,6 +526,14 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     const int wpc = cp.nw;
     const size_t smem = eval_smem_bytes(nseg_pad, wpc, M);
     if (smem > 226 * 1024) return F1L_ERR_TOO_LARGE;
+    // A lone dense query that needs more than one wave of CTAs runs on a PERSISTENT grid instead: one
+    // wave of CTAs whose warps pull single candidates from a device-wide counter, far lookahead rows
+    // (the expensive candidates) first.  No wave quantisation, one window-table prologue per
+    // resident CTA, and the cheap early-exit candidates fill the tail.
+    const int resident_ctas = (wpc == 4 ? EVAL_MINB4 : wpc == 7 ? EVAL_MINB7 : EVAL_MINB8) * h->sm_count;
+    static const bool dyn_off = getenv("F1L_EVAL_DYNAMIC") && atoi(getenv("F1L_EVAL_DYNAMIC")) == 0;
+    const bool dyn = S == 1 && wpc != 4 && o.work_next && !o.empty_shard && !dyn_off &&
+                     (long long)cp.ctas_per_scn > resident_ctas;
 
     SampleArgs sa;
     sa.tr = track_view(h);
@@ -542,6 +551,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     sa.ctx = ctx;
     sa.centres = centres;
     sa.best = best;
+    sa.work_next = dyn ? o.work_next : nullptr;
     cudaEvent_t* ev = h->ev + 4 * h->ev_next;
     if (time_it) cudaEventRecord(ev[0], stream);
     nvtxRangePushA("f1l.sample");
@@ -595,6 +605,14 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     ea.ctas_per_scn = cp.ctas_per_scn;
     // four candidates per warp at a time (shared Newton) when every warp has at least four
     ea.item = (ep.generator == 0 && cp.chunk >= 4 * cp.nw) ? EVAL_ITEM : 1;
+    ea.work_next = nullptr;
+    ea.v_last = 0;
+    if (dyn) {
+        ea.work_next = o.work_next;
+        ea.v_last = c_begin + c_end - 1;
+        ea.item = 1;
+        ea.ctas_per_scn = resident_ctas;
+    }
     ea.inv_nW = 1.0f / (float)(h->nW > 0 ? h->nW : 1);
     ea.nseg_pad = nseg_pad;
     ea.costs = o.costs;
@@ -1116,7 +1134,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     ENS(h->q_in, sizeof(QInput));
     ENS(h->q_ctx, sizeof(QueryCtx));
     ENS(h->q_centres, sizeof(Centre) * (size_t)(h->nL > 0 ? h->nL : 1));
-    ENS(h->q_best, 8);
+    ENS(h->q_best, 16);   // argmin key | work counter of the persistent-grid schedule
     ENS(h->prev, F1L_MAX_M * sizeof(float));
     // detail block layout (every region 16-byte aligned)
     const size_t c16 = ((size_t)C + 3) & ~(size_t)3;
@@ -1199,6 +1217,7 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
             o.s_rows = (ce - 1) / h->nW - o.s_row0 + 1;
         }
     }
+    o.work_next = (int*)((char*)h->q_best.p + 8);
     exchange = exchange && h->xview.world > 1;
     if (exchange) {   // the ranks' minima meet inside select_kernel (peer memory over NVLink)
         o.xc = &h->xview;

@@ -207,16 +207,53 @@ struct Intersect64 {
     int found;
 };
 
-// intersect_point (utils/utils.py:69-151), sequential early-exit scan by one thread
-template <class P>
+// prefilter on the uploaded track, FP32 on the block-local line form of segment i.  A root of the
+// reference's quadratic in [0,1] is a point of the (1e-6-shifted) segment at distance r from the
+// query, so a segment (a) farther than r + 1 mm from the query, or (b) whose FARTHER endpoint is
+// closer than r - 2 mm -- the whole segment lies strictly inside the circle -- cannot be accepted
+// and needs no float64 test.  (b) is what makes long lookaheads cheap: every segment between the
+// query and the crossing is of that kind.  The closing segment (i = -1) has no line form and is
+// always tested.
+struct TrackPrefilter {
+    const TrackView& tr;
+    double qx, qy;
+    float rr2;   // (radius + 1 mm)^2 in metres^2
+    float ri2;   // (max(radius - 2 mm, 0))^2
+    __device__ __forceinline__ bool operator()(int i) const {
+        if (i < 0) return true;
+        const double2 o = tr.blk_origin[i >> 5];
+        const float prx = (float)(qx - o.x) * TRACK_SCALE, pry = (float)(qy - o.y) * TRACK_SCALE;
+        const float4 A = __ldg(tr.segA + i);
+        const float2 Bv = __ldg(tr.segB + i);
+        const float q = fmaf(prx, A.x, fmaf(pry, A.y, A.z));
+        const float nn = fmaf(pry, A.x, fmaf(-prx, A.y, A.w));
+        const float n2 = nn * nn;
+        const float e = __saturatef(fabsf(q) + Bv.x);   // beyond the nearer end (Bv.x = -h)
+        const float f = fabsf(q) - Bv.x;                // along-axis distance to the farther end
+        return fmaf(e, e, n2) <= rr2 * (TRACK_SCALE * TRACK_SCALE) &&
+               fmaf(f, f, n2) >= ri2 * (TRACK_SCALE * TRACK_SCALE);
+    }
+};
+__device__ __forceinline__ TrackPrefilter track_prefilter(const TrackView& tr, double qx, double qy, double r) {
+    const float ro = (float)r + 1e-3f, ri = fmaxf((float)r - 2e-3f, 0.0f);
+    return TrackPrefilter{tr, qx, qy, ro * ro, ri * ri};
+}
+struct NoPrefilter {
+    __device__ __forceinline__ bool operator()(int) const { return true; }
+};
+
+// intersect_point (utils/utils.py:69-151), sequential early-exit scan by one thread; `maybe(i)` as
+// in intersect_point_warp below (false only for a segment the reference cannot accept)
+template <class P, class F = NoPrefilter>
 __device__ inline Intersect64 intersect_point64(const P& pts, int n, double qx, double qy,
-                                                double r, double t, bool wrap) {
+                                                double r, double t, bool wrap, const F& maybe = F()) {
     Intersect64 o;
     o.px = 0.0; o.py = 0.0; o.t = 0.0; o.i = 0; o.found = 0;
     const int start_i = (int)t;                 // :78
     const double start_t = t - (double)start_i;  // == t % 1.0 for t >= 0, exactly        // :79
     double t1, t2, vx, vy;
     for (int i = start_i; i < n - 1; ++i) {     // :84
+        if (!maybe(i)) continue;
         const double2 s = pts(i);
         if (!intersect_segment64(qx, qy, r, s, pts(i + 1), t1, t2, vx, vy)) continue;
         double tt = -1.0;
@@ -233,6 +270,7 @@ __device__ inline Intersect64 intersect_point64(const P& pts, int n, double qx, 
     }
     if (wrap) {                                 // :124
         for (int i = -1; i < start_i; ++i) {    // :125
+            if (!maybe(i)) continue;
             const double2 s = pts(pymod(i, n));
             if (!intersect_segment64(qx, qy, r, s, pts(pymod(i + 1, n)), t1, t2, vx, vy)) continue;
             double tt = -1.0;
@@ -355,26 +393,6 @@ __device__ inline Intersect64 intersect_point_group(const P& pts, int n, double 
     }
     return o;
 }
-
-// prefilter on the uploaded track: FP32 distance of the query point to segment i (block-local
-// line form) against radius + 1 mm.  A root of the reference's quadratic in [0,1] is a point of
-// the (1e-6-shifted) segment at distance r from the query, so a segment farther than that cannot
-// be accepted; the closing segment (i = -1) has no line form and is always tested.
-struct TrackPrefilter {
-    const TrackView& tr;
-    double qx, qy;
-    float rr2;   // (radius + 1 mm)^2 in metres^2
-    __device__ __forceinline__ bool operator()(int i) const {
-        if (i < 0) return true;
-        const double2 o = tr.blk_origin[i >> 5];
-        const float prx = (float)(qx - o.x) * TRACK_SCALE, pry = (float)(qy - o.y) * TRACK_SCALE;
-        return track_seg_d2(prx, pry, __ldg(tr.segA + i), __ldg(tr.segB + i)) <=
-               rr2 * (TRACK_SCALE * TRACK_SCALE);
-    }
-};
-struct NoPrefilter {
-    __device__ __forceinline__ bool operator()(int) const { return true; }
-};
 
 // get_actuation (utils/utils.py:153-161): returns steer, passes speed through
 __device__ __forceinline__ double actuation_steer64(double pose_theta, double lx, double ly,

@@ -327,6 +327,7 @@ struct SampleArgs {
     QueryCtx* ctx;             // [S]
     Centre* centres;           // [S,nL]
     unsigned long long* best;  // [S]
+    int* work_next;            // dense single query: the eval kernel's work counter, reset here (or null)
 };
 
 struct EvalArgs {
@@ -360,6 +361,10 @@ struct EvalArgs {
     float2* headings;        // [S,C,M] (cos, sin) used by the footprint (teacher-forced tests)
     unsigned long long* best;  // [S]
     unsigned long long* stats; // [2] deviation-pass work counters (segment steps, candidates) or null
+    int* work_next;          // dense single query on a persistent grid: every warp pulls its next
+                             // candidate from this device-wide counter (null: the CTA's own chunk)
+    int v_last;              // with work_next: the walk is reversed, v -> v_last - v (far lookahead
+                             // rows, the expensive candidates, first; the cheap ones fill the tail)
 };
 
 // Peer-memory exchange of a candidate-sharded query (the one exchange step of the
@@ -569,8 +574,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
         const bool active = jj < n_rows;
         const int j = a.row0 + (active ? jj : j0) * a.row_step;   // lookahead row
         const double L = a.lookaheads[j];
-        const float rr = (float)L + 1e-3f;
-        const TrackPrefilter pf{a.tr, px, py, rr * rr};
+        const TrackPrefilter pf = track_prefilter(a.tr, px, py, L);
         bool pending;
         Intersect64 ip = intersect_point_group<8>(acc, a.tr.n, px, py, L, (double)i_ego + t_ego,
                                                   true, lane, pf, active, 4, pending);
@@ -579,8 +583,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
         for (unsigned open = __ballot_sync(F1L_FULL, pending) & 0x01010101u; open; open &= open - 1) {
             const int src = __ffs(open) - 1;
             const double Ls = __shfl_sync(F1L_FULL, L, src);
-            const float rs = (float)Ls + 1e-3f;
-            const TrackPrefilter pfs{a.tr, px, py, rs * rs};
+            const TrackPrefilter pfs = track_prefilter(a.tr, px, py, Ls);
             const Intersect64 full =
                 intersect_point_warp(acc, a.tr.n, px, py, Ls, (double)i_ego + t_ego, true, lane, pfs);
             if ((lane & ~7) == src) ip = full;
@@ -641,6 +644,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS_MAX) sample_kernel(SampleArgs a
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const double px = a.poses[4 * (size_t)s], py = a.poses[4 * (size_t)s + 1];
     const int nseg = a.tr.n - 1;
+    if (a.work_next && s == 0 && tid == 0) *a.work_next = 0;
 
     float bd = CUDART_INF_F;
     int bi = 0x7fffffff;
@@ -950,7 +954,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
     constexpr int SLAB = L::SLAB;
 
     int s, cta;
+    // persistent grid over one dense query (never with the 4-warp CTAs of the batch regime: the
+    // compile-time false keeps that instance's candidate loop free of the extra state)
+    const bool dyn = NW != 4 && a.work_next != nullptr;
     if (a.ctas_per_scn == 1) { s = blockIdx.x; cta = 0; }
+    else if (dyn) { s = 0; cta = 0; }
     else { s = blockIdx.x / a.ctas_per_scn; cta = blockIdx.x - s * a.ctas_per_scn; }
     const int tid = threadIdx.x, wid = tid >> 5;
     // The three values every shared access and every guard below derives from.  They go through
@@ -966,7 +974,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
     opaque(nown);
     const QueryCtx* __restrict__ q = a.ctx + s;
     const int cb = a.c_begin + cta * a.chunk;
-    const int ce = min(cb + a.chunk, a.c_end);
+    const int ce = dyn ? a.c_end : min(cb + a.chunk, a.c_end);
 
     // ---- prologue: raceline window -> vehicle frame -> line form in shared memory.  Only the
     //      subtraction of the pose happens in float64 (|coordinates| reach 85 m, the window is
@@ -1040,14 +1048,20 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
     // and Newton solves run together, one candidate per 8-lane group (spiral_newton_g8); the rest
     // of the pipeline then handles the four one after the other on the whole warp.
     const int item = a.item;
-    for (int c0 = cb + wid * item; c0 < ce;) {
+    int c_first = cb + wid * item;
+    if (dyn) {
+        if (lane == 0) c_first = cb + atomicAdd(a.work_next, item);
+        c_first = __shfl_sync(F1L_FULL, c_first, 0);
+    }
+    for (int c0 = c_first; c0 < ce;) {
       if (item == 4) {   // warp-uniform
           const int cg = c0 + (lane >> 3);
           const bool active = cg < ce;
           float ggx, ggy, ggth, gp3, gv_ref;
           bool ghave;
+          const int cgv = active ? cg : c0;
           candidate_goal(a.centres, a.widths, a.goals, a.nL, a.nW, a.inv_nW, a.C, s,
-                         shard_candidate(active ? cg : c0, a.nW, a.inv_nW, a.row0, a.row_step),
+                         shard_candidate(dyn ? a.v_last - cgv : cgv, a.nW, a.inv_nW, a.row0, a.row_step),
                          a.ep.use_goal_kappa != 0, ggx, ggy, ggth, gp3, ghave, gv_ref);
           SpiralF gsp;
           const int g_pass = generate_cubic_g8(gsp, a.lut, a.ep, ggx, ggy, ggth, gp3, lane, active);
@@ -1061,7 +1075,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
       }
       const int c_last = min(c0 + item, ce);
       for (int v = c0; v < c_last; ++v) {
-        const int c = shard_candidate(v, a.nW, a.inv_nW, a.row0, a.row_step);
+        const int c = shard_candidate(dyn ? a.v_last - v : v, a.nW, a.inv_nW, a.row0, a.row_step);
         // ---- goal, seed, Newton ----
         float gx, gy, gth, p3, v_ref;
         bool have_centre;
@@ -1312,7 +1326,9 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             //      group gg); each lane keeps S samples in registers and walks every GG-th
             //      segment, the next segment's table entry already in flight.
             __syncwarp();
-            {
+            // prune mode also drops the whole pass for a candidate that collided when nobody asked
+            // for its per-term costs: its cost is +inf whatever the deviation (same outputs)
+            if (!(a.ep.prune && !a.terms && (flags & (F1L_FLAG_COLLIDE_OPP | F1L_FLAG_COLLIDE_MAP)))) {
                 // samples are processed in pairs with packed FP32x2 instructions (FFMA2 / FMUL2,
                 // sm_100): the same FMA-pipe work in half the issue slots -- the loop is issue-bound
                 // otherwise (1 warp-instruction per clock per scheduler, 9 per sample x segment).
@@ -1452,7 +1468,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
       }
       __syncwarp();   // all lanes have read the item's solutions
       int c_next = 0;
-      if (lane == 0) c_next = atomicAdd(&s_next, item);
+      if (lane == 0) c_next = dyn ? cb + atomicAdd(a.work_next, item) : atomicAdd(&s_next, item);
       c0 = __shfl_sync(F1L_FULL, c_next, 0);
     }
     if (a.stats) {   // work counters (opt-in, f1l_set_stats): one pair of global atomics per CTA

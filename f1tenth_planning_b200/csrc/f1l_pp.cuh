@@ -264,7 +264,8 @@ pp_finish_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride
     double lx = 0.0, ly = 0.0, speed = 0.0;
     if (nr.dist < L) {                                            // :70
         XYTrack acc{tr.xy};
-        ip = intersect_point64(acc, tr.n, qx, qy, L, (double)nr.i + nr.t, true);  // :71-75
+        ip = intersect_point64(acc, tr.n, qx, qy, L, (double)nr.i + nr.t, true,
+                               track_prefilter(tr, qx, qy, L));                  // :71-75
         if (ip.found) {                                           // :78
             const int r = pymod(ip.i, tr.n);
             lx = tr.xy[r].x; ly = tr.xy[r].y; speed = tr.v[nr.i];

@@ -75,7 +75,9 @@ typedef struct {
     int32_t prune_window;    /* raceline deviation: 0 = every sample against every window segment
                                 (default); 1 = skip the window segments that provably cannot be
                                 nearest to any sample of the candidate (chord-midpoint bound).
-                                Same minima, hence bit-identical costs, fewer segment tests. */
+                                Same minima, hence bit-identical costs, fewer segment tests.
+                                A candidate that collided (cost +inf) skips the deviation pass
+                                altogether unless the per-term costs were requested. */
     int32_t collision_mode;  /* occupancy-grid collision test of a footprint (map_collision stub,
                                 utils/utils.py:297-301): 0 = nine probe points (corners, edge
                                 mid-points, centre; default); 1 = three discs along the body axis

@@ -14,7 +14,7 @@ from f1tenth_planning_b200.engine import Engine  # noqa: E402
 W = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 track = synth.ellipse_track()
 la, wd = synth.goal_grid(5)
-eng = Engine(n_samples=200, window=128)
+eng = Engine(n_samples=200, window=128, prune_window=int(os.environ.get("PRUNE", "0")))
 eng.set_track(track)
 eng.set_grid(*synth.corridor_grid())
 eng.set_goal_grid(la, wd)
