@@ -159,18 +159,21 @@ def workload(seed_rank, S):
     return track, grid, la, wd, poses[:S].copy(), opp[:S].copy(), n_opp[:S].copy()
 
 
-def work_flops(flags, M, W, n_opp_mean):
-    """algorithmic FLOPs of one step (appendix D) from the flags it produced: a candidate that
-    failed validation stops after generation; the Newton term counts the quadrature passes the
-    candidate actually used (flag bits 4..7) instead of the nominal 8."""
+def work_flops(flags, M, seg_steps, n_opp_mean):
+    """algorithmic FLOPs of one step (appendix D) from the flags it produced and the kernel's own
+    work counter: a candidate that failed validation stops after generation; the Newton term counts
+    the quadrature passes the candidate actually used (flag bits 4..7) instead of the nominal 8;
+    the deviation term is 17 M per (candidate, window segment) pair the kernel actually tested
+    (`seg_steps`, f1l_get_stats) -- W = 128 for every valid candidate in the headline run, fewer
+    with prune_window = 1, which also drops the pass for collided candidates."""
     valid = (flags & 1) != 0
     passes = (flags >> 4).astype(np.float64)
     n_full = int(valid.sum())
     n_short = int(valid.size - n_full)
-    base = (n_full * F.candidate_flops(M=M, W=W, K=n_opp_mean, I=0, full=True) +
-            n_short * F.candidate_flops(M=M, W=W, K=n_opp_mean, I=0, full=False))
+    base = (n_full * F.candidate_flops(M=M, W=0, K=n_opp_mean, I=0, full=True) +
+            n_short * F.candidate_flops(M=M, W=0, K=n_opp_mean, I=0, full=False))
     newton = float(passes.sum()) * (44 * (F.Q_NEWTON + 1) + 110)
-    return base + newton, n_full / valid.size, float(passes.mean())
+    return base + 17.0 * M * float(seg_steps) + newton, n_full / valid.size, float(passes.mean())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -521,6 +524,11 @@ class HostArm:
     def step(self):
         return self.planner.plan_batch(self.h_poses, self.h_opp, self.h_nopp, out=self.h_out, want_flags=True)
 
+    def step_no_traj(self):
+        """the same call without the [S,M,4] best trajectories (91 % of the result bytes)"""
+        return self.planner.plan_batch(self.h_poses, self.h_opp, self.h_nopp, out=self.h_out, want_flags=True,
+                                       want_traj=False)
+
 
 def timed(torch, dist, dev, world_size, step, n_steps, wall=False):
     """barrier + synchronize, n_steps of step(), synchronize + barrier; max over ranks (ms).
@@ -654,7 +662,7 @@ def run_ours(args):
     eng.set_stats(False)
     # window segments each valid candidate was tested against (= W unless --prune 1)
     w_eff = seg_steps / seg_cands if seg_cands else float(PLAN_CFG["window"])
-    step_flops, valid_frac, mean_passes = work_flops(flags, M, w_eff, float(n_opp.mean()))
+    step_flops, valid_frac, mean_passes = work_flops(flags, M, seg_steps, float(n_opp.mean()))
     achieved_tflops = step_flops / (k_eval * 1e-3) / 1e12 if k_eval > 0 else None
     # the same without the work the kernel mostly skips: the 16 P M grid-probe FLOPs (a clearance
     # lookup proves most footprints free) and the 6 K M opponent broad-phase FLOPs (candidate-level
@@ -681,9 +689,11 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         ps, pc = eng.stats()
         eng.set_stats(False)
-        p_flops, _, _ = work_flops(flags, M, ps / max(pc, 1), float(n_opp.mean()))
+        p_flops, _, _ = work_flops(flags, M, ps, float(n_opp.mean()))
         pruned = {"candidates_per_s": S * C / (p_ms * 1e-3), "ms_per_step": p_ms, "eval_kernel_ms": pk_eval,
                   "window_segments_tested_mean": ps / max(pc, 1),
+                  "candidates_in_deviation_pass": int(pc),
+                  "valid_candidates": int(((flags & 1) != 0).sum()),
                   "executed_tflops": p_flops / (pk_eval * 1e-3) / 1e12,
                   "costs_bit_identical_to_full_scan": bool(torch.equal(arm.o_costs, costs_full))}
         eng.configure(prune_window=0)
@@ -703,6 +713,12 @@ def run_ours(args):
     e2e_value = world_size * S * C * e2e_steps / t_e2e
     assert np.array_equal(host.h_out["best_idx"], arm.o_idx.cpu().numpy()), "e2e and device-resident arms disagree"
     assert np.array_equal(host.h_out["flags"], flags), "e2e and device-resident arms disagree (flags)"
+    # side measurement: the same call with want_traj=False -- what the end-to-end rate is when the
+    # host link does not have to carry the best trajectories (it is the bound at N = 8 on this box)
+    host.step_no_traj()
+    t_nt = timed(torch, dist, dev, world_size, host.step_no_traj, e2e_steps, wall=True) * 1e-3
+    e2e_no_traj = {"value": world_size * S * C * e2e_steps / t_nt, "unit": UNIT,
+                   "d2h_bytes_per_step": host.d2h - host.h_out["best_traj"].nbytes}
 
     # ---- what the host link gives: every rank copies 128 MB device -> pinned host at the same time
     #      (the e2e arm's result copy is 176 MB per step per GPU) ----------------------------------
@@ -800,6 +816,8 @@ def run_ours(args):
                 "d2h_gbs_per_gpu": host.d2h / (t_e2e / e2e_steps) / 1e9,
                 # plain 128 MB device -> pinned-host copies issued by all ranks at the same time
                 "d2h_link_probe_gbs_per_gpu": d2h_probe_gbs,
+                # side measurement, not the headline: want_traj=False
+                "without_best_traj": e2e_no_traj,
                 "api": "LatticePlanner.plan_batch (pinned host buffers; every output of the "
                        "device-resident arm, flags included)"},
         "gpu_launches": int(launches),

@@ -292,10 +292,12 @@ __device__ inline Intersect64 intersect_point64(const P& pts, int n, double qx, 
 // lowest accepting lane wins (== first hit of the sequential loop).  `maybe(i)` is a cheap
 // conservative prefilter (false only if segment i cannot reach the circle).  Call with the whole
 // warp converged; every lane returns the same result.
+// `skip`: the first `skip` segments of the forward scan are known not to hit (a caller that has
+// already tested them) and are not visited again.
 template <class P, class F>
 __device__ inline Intersect64 intersect_point_warp(const P& pts, int n, double qx, double qy,
                                                    double r, double t, bool wrap, int lane,
-                                                   const F& maybe) {
+                                                   const F& maybe, int skip = 0) {
     Intersect64 o;
     o.px = 0.0; o.py = 0.0; o.t = 0.0; o.i = 0; o.found = 0;
     const int start_i = (int)t;                 // :78
@@ -303,7 +305,7 @@ __device__ inline Intersect64 intersect_point_warp(const P& pts, int n, double q
     for (int phase = 0; phase < (wrap ? 2 : 1); ++phase) {
         const int lo = phase == 0 ? start_i : -1;          // :84 / :125
         const int hi = phase == 0 ? n - 1 : start_i;       // exclusive
-        for (int base = lo; base < hi; base += 32) {
+        for (int base = lo + (phase == 0 ? skip : 0); base < hi; base += 32) {
             const int i = base + lane;
             double tt = -1.0, vx = 0.0, vy = 0.0;
             double2 s = make_double2(0.0, 0.0);
@@ -330,6 +332,29 @@ __device__ inline Intersect64 intersect_point_warp(const P& pts, int n, double q
                 return o;
             }
         }
+    }
+    return o;
+}
+
+// intersect_point for a circle that is known to stay clear of every open segment (the nearest
+// distance to the raceline exceeds the radius): the only segment the reference's scan can still
+// accept is the closing one, i = -1 of the wrap loop (utils.py:125-150), from the last waypoint to
+// the first.  One float64 segment test instead of a scan of the whole track.
+template <class P>
+__device__ inline Intersect64 intersect_closing_only(const P& pts, int n, double qx, double qy,
+                                                     double r, bool wrap) {
+    Intersect64 o;
+    o.px = 0.0; o.py = 0.0; o.t = 0.0; o.i = 0; o.found = 0;
+    if (!wrap) return o;
+    double t1, t2, vx, vy;
+    const double2 s = pts(n - 1);
+    if (!intersect_segment64(qx, qy, r, s, pts(0), t1, t2, vx, vy)) return o;
+    double tt = -1.0;
+    if (t1 >= 0.0 && t1 <= 1.0) tt = t1;        // :140
+    else if (t2 >= 0.0 && t2 <= 1.0) tt = t2;   // :145
+    if (tt >= 0.0) {
+        o.t = tt; o.i = -1; o.found = 1;
+        o.px = xadd(s.x, xmul(tt, vx)); o.py = xadd(s.y, xmul(tt, vy));
     }
     return o;
 }

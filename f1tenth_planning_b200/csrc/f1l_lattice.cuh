@@ -556,8 +556,10 @@ __device__ __forceinline__ Centre centre_from_hit(const TrackView& tr, const Int
 
 // everything after the nearest-point search, shared by the two sampler kernels.  `lt` / `nt`:
 // this thread's index / the number of threads working on scenario s.
+// `d_ego`: the float64 distance of the pose to its nearest raceline point (nearest_point's third
+// result).
 __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, int nt, int i_ego,
-                                            double t_ego) {
+                                            double t_ego, double d_ego) {
     const double px = a.poses[4 * (size_t)s], py = a.poses[4 * (size_t)s + 1];
     const double pth = a.poses[4 * (size_t)s + 2], pv = a.poses[4 * (size_t)s + 3];
     const int nseg = a.tr.n - 1;
@@ -575,17 +577,26 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
         const int j = a.row0 + (active ? jj : j0) * a.row_step;   // lookahead row
         const double L = a.lookaheads[j];
         const TrackPrefilter pf = track_prefilter(a.tr, px, py, L);
+        // A circle that stays clear of the raceline -- the pose is farther from its nearest
+        // raceline point than the lookahead (2 mm of slack over the FP32 pre-scan behind d_ego) --
+        // cannot cross any open segment: no scan, only the closing segment's test.  (18 % of the
+        // benchmark's scenarios at L = 0.4 m; the scan would walk the whole track to find nothing.)
+        const bool clear = active && d_ego > L + 2e-3;
         bool pending;
         Intersect64 ip = intersect_point_group<8>(acc, a.tr.n, px, py, L, (double)i_ego + t_ego,
-                                                  true, lane, pf, active, 4, pending);
-        // rows whose hit is not within the first 32 segments (mostly: no hit at all): the full
-        // 32-lane scan, one row after the other
+                                                  true, lane, pf, active && !clear, 4, pending);
+        if (__any_sync(F1L_FULL, clear)) {
+            const Intersect64 co = intersect_closing_only(acc, a.tr.n, px, py, L, true);
+            if (clear) ip = co;
+        }
+        // rows whose hit is not within the first 32 segments: the full 32-lane scan from there on,
+        // one row after the other
         for (unsigned open = __ballot_sync(F1L_FULL, pending) & 0x01010101u; open; open &= open - 1) {
             const int src = __ffs(open) - 1;
             const double Ls = __shfl_sync(F1L_FULL, L, src);
             const TrackPrefilter pfs = track_prefilter(a.tr, px, py, Ls);
             const Intersect64 full =
-                intersect_point_warp(acc, a.tr.n, px, py, Ls, (double)i_ego + t_ego, true, lane, pfs);
+                intersect_point_warp(acc, a.tr.n, px, py, Ls, (double)i_ego + t_ego, true, lane, pfs, 32);
             if ((lane & ~7) == src) ip = full;
         }
         if (active && (lane & 7) == 0)
@@ -637,7 +648,7 @@ __device__ __forceinline__ void sample_body(const SampleArgs& a, int s, int lt, 
 __global__ void __launch_bounds__(SAMPLE_THREADS_MAX) sample_kernel(SampleArgs a) {
     __shared__ float s_d[SAMPLE_THREADS_MAX / 32];
     __shared__ int s_i[SAMPLE_THREADS_MAX / 32];
-    __shared__ double s_t;
+    __shared__ double s_t, s_dist;
     __shared__ int s_best;
     const int s = blockIdx.x;
     const int nthreads = blockDim.x;
@@ -669,9 +680,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS_MAX) sample_kernel(SampleArgs a
         const Nearest64 nr = refine_nearest64(a.tr.xy, nseg, px, py, bi);
         s_best = nr.i;
         s_t = nr.t;
+        s_dist = nr.dist;
     }
     __syncthreads();
-    sample_body(a, s, tid, nthreads, s_best, s_t);
+    sample_body(a, s, tid, nthreads, s_best, s_t, s_dist);
 }
 
 // batches: the nearest-point search of all scenarios is done by pp_scan_kernel + pp_finish_kernel (K1, lane per pose,
@@ -682,7 +694,7 @@ sample_warp_kernel(SampleArgs a, const int32_t* __restrict__ near_i,
                    const double* __restrict__ near4, int n_scenarios) {
     const int s = blockIdx.x * SAMPLE_WARPS + (threadIdx.x >> 5);
     if (s >= n_scenarios) return;
-    sample_body(a, s, threadIdx.x & 31, 32, near_i[s], near4[4 * (size_t)s + 3]);
+    sample_body(a, s, threadIdx.x & 31, 32, near_i[s], near4[4 * (size_t)s + 3], near4[4 * (size_t)s + 2]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1326,9 +1338,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
             //      group gg); each lane keeps S samples in registers and walks every GG-th
             //      segment, the next segment's table entry already in flight.
             __syncwarp();
-            // prune mode also drops the whole pass for a candidate that collided when nobody asked
-            // for its per-term costs: its cost is +inf whatever the deviation (same outputs)
-            if (!(a.ep.prune && !a.terms && (flags & (F1L_FLAG_COLLIDE_OPP | F1L_FLAG_COLLIDE_MAP)))) {
+            {
                 // samples are processed in pairs with packed FP32x2 instructions (FFMA2 / FMUL2,
                 // sm_100): the same FMA-pipe work in half the issue slots -- the loop is issue-bound
                 // otherwise (1 warp-instruction per clock per scheduler, 9 per sample x segment).
@@ -1364,7 +1374,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                 const int nq = a.nseg_pad;
                 // segment range [k_begin, k_end) of the window this candidate is tested against
                 int k_begin = 0, k_end = nq;
-                if (a.ep.prune) {
+                if (a.ep.prune && !a.terms && (flags & (F1L_FLAG_COLLIDE_OPP | F1L_FLAG_COLLIDE_MAP))) {
+                    // prune mode also drops the scan for a candidate that collided when nobody
+                    // asked for its per-term costs: its cost is +inf whatever the deviation
+                    k_end = 0;
+                } else if (a.ep.prune) {
                     // Every point of a curve of length s_f from the origin to (ex, ey) lies
                     // within rho = s_f / 2 of the chord midpoint c.  With D = the distance of c
                     // to the window, every sample's nearest distance is <= D + rho, and a
@@ -1394,7 +1408,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                         k_end = min(nq, (hi + 2 * GG) & ~(2 * GG - 1));
                     }
                 }
-                if (a.stats && lane == 0) atomicAdd(&s_work, (1ull << 40) + (unsigned long long)(k_end - k_begin));
+                if (a.stats && lane == 0 && k_end > k_begin) atomicAdd(&s_work, (1ull << 40) + (unsigned long long)(k_end - k_begin));
                 // the walk advances the table address itself (one add per trip); the trip count is
                 // warp-uniform and lives in a uniform register
                 uint32_t ta = cbase + L::C_TAB + (k_begin + ggi) * 32;
