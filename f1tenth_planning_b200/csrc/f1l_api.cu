@@ -84,7 +84,11 @@ struct f1l_ctx {
     DevBuf q_res, q_in, q_goals, q_ctx, q_centres, q_best, q_states, q_headings, q_params, q_flags;
     // pinned staging for the single query
     void* h_in = nullptr;   // pose + opponents
+    void* h_in_dev = nullptr;   // the same block as the device sees it (mapped): the sampler of a single
+                                // query reads its 416 bytes of input straight from it
     void* h_out = nullptr;  // header + best trajectory
+    void* h_out_dev = nullptr;  // the same block as the device sees it (mapped pinned memory): the
+                                // select kernel of a single query writes its results straight into it
     size_t h_out_cap = 0;
     // per-candidate detail block of a single query (costs | terms | goals | params | flags): one
     // device block, one D2H into pinned staging, then plain copies into the caller's arrays
@@ -870,10 +874,26 @@ int f1l_create(f1l_handle* out, int device, const f1l_config* cfg) {
         e = cudaStreamCreateWithFlags(&h->pipe[i].stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->pipe[i].done, cudaEventDisableTiming);
     }
-    if (e == cudaSuccess) e = cudaHostAlloc(&h->h_in, 1024, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc(&h->h_in, 1024, cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+        memset(h->h_in, 0, 1024);
+        static const bool in_off = !getenv("F1L_DIRECT_IN") || atoi(getenv("F1L_DIRECT_IN")) == 0;
+        if (in_off || cudaHostGetDevicePointer(&h->h_in_dev, h->h_in, 0) != cudaSuccess) {
+            h->h_in_dev = nullptr;
+            cudaGetLastError();
+        }
+    }
     if (e == cudaSuccess) {
         h->h_out_cap = Q_RES_BYTES;
-        e = cudaHostAlloc(&h->h_out, h->h_out_cap, cudaHostAllocDefault);
+        e = cudaHostAlloc(&h->h_out, h->h_out_cap, cudaHostAllocMapped);
+        if (e == cudaSuccess) {
+            memset(h->h_out, 0, h->h_out_cap);
+            static const bool direct_off = getenv("F1L_DIRECT_OUT") && atoi(getenv("F1L_DIRECT_OUT")) == 0;
+            if (direct_off || cudaHostGetDevicePointer(&h->h_out_dev, h->h_out, 0) != cudaSuccess) {
+                h->h_out_dev = nullptr;   // fall back to the device block + D2H copy
+                cudaGetLastError();
+            }
+        }
     }
     if (e == cudaSuccess) {
         int sm = 0;
@@ -1175,7 +1195,11 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
         // the header's padding words travel with the D2H copy: defined bytes (initcheck-clean)
         CK(cudaMemsetAsync(h->q_res.p, 0, sizeof(QHeader), st));
     }
-    char* dres = (char*)h->q_res.p;
+    // Results of a single query: the select kernel writes header and best trajectory straight into
+    // the mapped pinned block (posted writes over the host link, 3-10 KB) -- no D2H copy node on the
+    // latency path; without a mapping they go to the device block and one D2H copy.
+    const bool direct = h->h_out_dev != nullptr;
+    char* dres = direct ? (char*)h->h_out_dev : (char*)h->q_res.p;
     BatchOut o;
     o.steer_speed = (double*)(dres + offsetof(QHeader, steer));
     o.best_idx = (int32_t*)(dres + offsetof(QHeader, best_idx));
@@ -1226,12 +1250,13 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
     const bool sharded = exchange || row_step > 1 || c_begin != 0 || (c_end > 0 && c_end < C);
     QHeader* hd = (QHeader*)h->h_out;
     float* htraj = (float*)((char*)h->h_out + sizeof(QHeader));
-    const QInput* din = (const QInput*)h->q_in.p;
+    const bool direct_in = h->h_in_dev != nullptr;
+    const QInput* din = direct_in ? (const QInput*)h->h_in_dev : (const QInput*)h->q_in.p;
     // H2D of the input block, the three kernels, D2H of header + best trajectory.  The
     // similarity term reads the previous path while select overwrites it: eval reads it before
     // select runs (stream order), so one buffer suffices.
     auto enqueue = [&](bool time_it) -> int {
-        CK(cudaMemcpyAsync(h->q_in.p, hin, sizeof(QInput), cudaMemcpyHostToDevice, st));
+        if (!direct_in) CK(cudaMemcpyAsync(h->q_in.p, hin, sizeof(QInput), cudaMemcpyHostToDevice, st));
         if (sharded && want_detail) {
             // sharded evaluation: untouched candidates keep +inf / zero flags (only when the
             // per-candidate arrays travel back at all)
@@ -1244,10 +1269,12 @@ static int plan_internal(f1l_handle h, const double pose[4], const double* opp, 
                                 (unsigned long long*)h->q_best.p, nullptr, nullptr,
                                 h->has_prev ? (const float*)h->prev.p : nullptr, o, time_it);
         if (r != F1L_OK) return r;
-        CK(cudaMemcpyAsync(hd, h->q_res.p, sizeof(QHeader) + (size_t)M * 16, cudaMemcpyDeviceToHost, st));
-        if (o.best_traj_map)
-            CK(cudaMemcpyAsync((char*)h->h_out + Q_OFF_MAP, dres + Q_OFF_MAP, (size_t)M * 32,
-                               cudaMemcpyDeviceToHost, st));
+        if (!direct) {
+            CK(cudaMemcpyAsync(hd, h->q_res.p, sizeof(QHeader) + (size_t)M * 16, cudaMemcpyDeviceToHost, st));
+            if (o.best_traj_map)
+                CK(cudaMemcpyAsync((char*)h->h_out + Q_OFF_MAP, dres + Q_OFF_MAP, (size_t)M * 32,
+                                   cudaMemcpyDeviceToHost, st));
+        }
         if (want_detail)
             CK(cudaMemcpyAsync(h->h_detail, ddet, detail_bytes, cudaMemcpyDeviceToHost, st));
         return F1L_OK;

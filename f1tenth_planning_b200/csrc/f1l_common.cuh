@@ -155,6 +155,34 @@ __device__ __forceinline__ Nearest64 refine_nearest64(const double2* __restrict_
     return b;
 }
 
+// The same with the (up to) five segments on five lanes of a converged warp: one float64 segment
+// evaluation deep instead of five; the first-minimum rule is replayed in segment order over the
+// shuffled distances.  Every lane returns the result.
+__device__ __forceinline__ Nearest64 refine_nearest64_warp(const double2* __restrict__ xy, int nseg,
+                                                           double qx, double qy, int k, int lane) {
+    const int lo = max(k - 2, 0), hi = min(k + 2, nseg - 1);
+    const int s = lo + lane;
+    double px = 0.0, py = 0.0, d = CUDART_INF, t = 0.0;
+    if (s <= hi) {
+        const double2 a = xy[s], c = xy[s + 1];
+        nearest_segment64(qx, qy, a.x, a.y, c.x, c.y, px, py, d, t);
+    }
+    double bd = CUDART_INF;
+    int bj = -1;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const double dj = __shfl_sync(0xffffffffu, d, j);
+        if (lo + j <= hi && dj < bd) { bd = dj; bj = j; }
+    }
+    Nearest64 b;
+    b.dist = CUDART_INF; b.i = 0; b.px = 0.0; b.py = 0.0; b.t = 0.0;
+    const int src = bj < 0 ? 0 : bj;
+    const double wpx = __shfl_sync(0xffffffffu, px, src), wpy = __shfl_sync(0xffffffffu, py, src);
+    const double wt = __shfl_sync(0xffffffffu, t, src);
+    if (bj >= 0) { b.dist = bd; b.i = lo + bj; b.px = wpx; b.py = wpy; b.t = wt; }
+    return b;
+}
+
 // lexicographic (dist, index) minimum == np.argmin first-minimum rule (utils.py:66)
 __device__ __forceinline__ bool nearest_better(double d, int i, double bd, int bi) {
     return d < bd || (d == bd && i < bi);

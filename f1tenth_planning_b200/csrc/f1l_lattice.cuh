@@ -673,14 +673,23 @@ __global__ void __launch_bounds__(SAMPLE_THREADS_MAX) sample_kernel(SampleArgs a
     }
     if (lane == 0) { s_d[wid] = bd; s_i[wid] = bi; }
     __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < (nthreads >> 5); ++w)
-            if (s_d[w] < bd || (s_d[w] == bd && s_i[w] < bi)) { bd = s_d[w]; bi = s_i[w]; }
+    if (wid == 0) {   // warp 0: the warps' minima (one per lane), then the float64 neighbours on five lanes
+        const int nw = nthreads >> 5;
+        bd = lane < nw ? s_d[lane] : CUDART_INF_F;
+        bi = lane < nw ? s_i[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float od = __shfl_xor_sync(F1L_FULL, bd, o);
+            const int oi = __shfl_xor_sync(F1L_FULL, bi, o);
+            if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+        }
         if (bi == 0x7fffffff) bi = 0;
-        const Nearest64 nr = refine_nearest64(a.tr.xy, nseg, px, py, bi);
-        s_best = nr.i;
-        s_t = nr.t;
-        s_dist = nr.dist;
+        const Nearest64 nr = refine_nearest64_warp(a.tr.xy, nseg, px, py, bi, lane);
+        if (lane == 0) {
+            s_best = nr.i;
+            s_t = nr.t;
+            s_dist = nr.dist;
+        }
     }
     __syncthreads();
     sample_body(a, s, tid, nthreads, s_best, s_t, s_dist);
