@@ -614,7 +614,9 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     if (dyn) {
         ea.work_next = o.work_next;
         ea.v_last = c_begin + c_end - 1;
-        ea.item = 1;
+        // single candidates per pull, unless every warp has at least four 4-candidate items to go
+        // through: then the shared Newton solve pays more than the coarser tail costs
+        ea.item = (ep.generator == 0 && (long long)n_cand >= 16LL * resident_ctas * wpc) ? EVAL_ITEM : 1;
         ea.ctas_per_scn = resident_ctas;
     }
     ea.inv_nW = 1.0f / (float)(h->nW > 0 ? h->nW : 1);

@@ -1252,15 +1252,28 @@ __global__ void __launch_bounds__(NW * 32, MINB) eval_kernel(EvalArgs a) {
                     }
                 }
             }
+            // lane-level broad phase: a lane's samples are consecutive points of the curve, so they
+            // lie within (IPL - 1) arc steps of its first one; an opponent farther than that plus
+            // the broad-phase radius from the first sample cannot pass any per-sample test.  (1 %
+            // and 1 mm of slack over the quadrature; only provably negative tests are skipped,
+            // the flags stay as they were.)
+            float lane_R2 = -1.0f;
+            if (opp_mask && nown > 0) {
+                const float R = fmaf(1.01f * (float)(IPL - 1), __fdividef(sp.sf, (float)(M - 1)), a.ep.reach_pad);
+                lane_R2 = R * R;
+            }
             for (unsigned m = opp_mask; m; m &= m - 1) {   // uniform; mostly empty
                 const float4 o = lds128(cbase + L::C_OPP + (__ffs(m) - 1) * 16);
+                const float ux = o.x - x[0], uy = o.y - y[0];
+                if (fmaf(ux, ux, uy * uy) <= lane_R2) {
 #pragma unroll
-                for (int j = 0; j < IPL; ++j) {
-                    if (j < nown) {
-                        const float tx = fs(o.x, x[j]), ty = fs(o.y, y[j]);
-                        const float d2 = fa(fm(tx, tx), fm(ty, ty));
-                        if (d2 <= a.ep.rc2 && sat_collide(tx, ty, cs[j], sn[j], o.z, o.w, hl, hw))
-                            hit_opp = true;
+                    for (int j = 0; j < IPL; ++j) {
+                        if (j < nown) {
+                            const float tx = fs(o.x, x[j]), ty = fs(o.y, y[j]);
+                            const float d2 = fa(fm(tx, tx), fm(ty, ty));
+                            if (d2 <= a.ep.rc2 && sat_collide(tx, ty, cs[j], sn[j], o.z, o.w, hl, hw))
+                                hit_opp = true;
+                        }
                     }
                 }
             }
