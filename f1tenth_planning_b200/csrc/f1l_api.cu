@@ -106,7 +106,9 @@ struct f1l_ctx {
     DevBuf m_in, m_in2, m_o0, m_o1, m_o2, m_o3, m_o4, m_o5, pp_key;
     // peer-memory exchange of candidate-sharded queries (f1l_xchg_*): the local block, the peers'
     // blocks as mapped by cudaIpcOpenMemHandle (own rank: the local pointer)
-    int pp_per_sm = 0;   // resident pp_scan_kernel CTAs per SM (pp_slots)
+    int pp_per_sm = 0, pp_per_sm_ct = 0;   // resident pp_scan_kernel CTAs per SM (pp_slots): global / constant table
+    unsigned long long ctab_key = 0;   // != 0: this handle's track sits in the constant-memory table
+                                       // (as long as it is still the device's owner, ctab_owner)
     DevBuf xchg;
     XchgView xview = {0, 0, {nullptr}};
     // template instance / CTA plan of the last eval_kernel launch (f1l_last_eval_shape)
@@ -403,28 +405,50 @@ CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count, bool cubic) {
     return best;
 }
 
+// owner of the constant-memory line-form table of each device (f1l_pp.cuh): the key of the handle
+// whose f1l_set_track filled it last
+static unsigned long long g_ctab_owner[64] = {0};
+static unsigned long long g_ctab_serial = 0;
+bool ctab_valid(f1l_handle h) {
+    return h->ctab_key != 0 && h->device >= 0 && h->device < 64 && g_ctab_owner[h->device] == h->ctab_key;
+}
+
 // resident one-warp scan CTAs on the handle's device, from the occupancy calculator (once)
 int pp_slots(f1l_handle h) {
-    if (h->pp_per_sm <= 0) {
+    const bool ct = ctab_valid(h);
+    int& per_sm = ct ? h->pp_per_sm_ct : h->pp_per_sm;
+    if (per_sm <= 0) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pp_scan_kernel, 32, 0) != cudaSuccess || n <= 0)
-            n = PP_TASK_MINB;
-        h->pp_per_sm = n;
+        const cudaError_t e = ct ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pp_scan_kernel<true>, 32, 0)
+                                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pp_scan_kernel<false>, 32, 0);
+        if (e != cudaSuccess || n <= 0) n = PP_TASK_MINB;
+        per_sm = n;
     }
-    return h->pp_per_sm * h->sm_count;
+    return per_sm * h->sm_count;
 }
 
 // K1 = key preset + scan + finish on one stream.  key: 8 bytes of scratch per pose; slots: one-warp
 // scan CTAs resident on the device (pp_slots)
 void launch_pp(const TrackView& tv, cudaStream_t stream, const double* poses, int pose_stride,
                int n_poses, double L, double wb, double max_reacquire, int front_axle, double k_path,
-               unsigned long long* key, int slots, const PPOut& o) {
+               unsigned long long* key, int slots, const PPOut& o, bool ctab) {
     const int n_groups = (n_poses + PP_CTA_POSES - 1) / PP_CTA_POSES;
     const int nblk = (tv.n - 1 + 31) >> 5;
-    const int n_parts = pp_task_parts(n_groups, nblk, slots);
+    int n_parts = pp_task_parts(n_groups, nblk, slots, ctab ? 16 : 6);
+    if (const char* e = getenv("F1L_PP_PARTS")) {   // tuning hook
+        const int v = atoi(e);
+        if (v >= 1 && v <= PP_MAX_PARTS && v <= nblk) n_parts = v;
+    }
     cudaMemsetAsync(key, 0xff, (size_t)n_poses * 8, stream);
-    pp_scan_kernel<<<n_groups * n_parts, 32, 0, stream>>>(tv, poses, pose_stride, n_poses,
-                                                         front_axle, wb, n_parts, key);
+    PPParts parts;
+    parts.n = n_parts;
+    parts.per = nblk / n_parts;
+    parts.rem = nblk - parts.per * n_parts;
+    const dim3 grid((unsigned)n_groups, (unsigned)n_parts);
+    if (ctab)
+        pp_scan_kernel<true><<<grid, 32, 0, stream>>>(tv, poses, pose_stride, n_poses, front_axle, wb, parts, key);
+    else
+        pp_scan_kernel<false><<<grid, 32, 0, stream>>>(tv, poses, pose_stride, n_poses, front_axle, wb, parts, key);
     pp_finish_kernel<<<(n_poses + PP_THREADS - 1) / PP_THREADS, PP_THREADS, 0, stream>>>(
         tv, poses, pose_stride, n_poses, L, wb, max_reacquire, front_axle, k_path, key, o);
 }
@@ -570,7 +594,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
         po.actuation = nullptr;
         po.status = nullptr;
         po.front = nullptr;
-        launch_pp(sa.tr, stream, poses, 4, S, -1.0, 0.33, 0.0, 0, 0.0, best, pp_slots(h), po);   // `best` doubles as K1's key scratch: the sampler resets it
+        launch_pp(sa.tr, stream, poses, 4, S, -1.0, 0.33, 0.0, 0, 0.0, best, pp_slots(h), po, ctab_valid(h));   // `best` doubles as K1's key scratch: the sampler resets it
         sample_warp_kernel<<<(S + SAMPLE_WARPS - 1) / SAMPLE_WARPS, SAMPLE_WARPS * 32, 0, stream>>>(
             sa, near_i, near4, S);
         h->launches += 2;
@@ -1009,6 +1033,25 @@ int f1l_set_track(f1l_handle h, const double* wpts, int n, int ncols) {
     CK(cudaMemcpy(h->segA.p, segA.data(), segA.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->segB.p, segB.data(), segB.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->blk.p, blk.data(), blk.size() * 8, cudaMemcpyHostToDevice));
+    // the scan's constant-memory copy: one table per device, taken over by the latest upload (no
+    // kernel of another handle may still be reading it: device-wide sync, this is the slow path)
+    h->ctab_key = 0;
+    static const bool ctab_off = getenv("F1L_CTAB") && atoi(getenv("F1L_CTAB")) == 0;
+    if (nblk * 32 <= F1L_CTAB_SEGS && h->device >= 0 && h->device < 64 && !ctab_off) {
+        CK(cudaDeviceSynchronize());
+        // padded to whole 32-segment blocks with entries no query point comes near (d^2 = 1e18 table
+        // units): the constant-memory scan has no partial-block path
+        std::vector<float> cA(segA), cB(segB);
+        for (int k = nseg; k < nblk * 32; ++k) {
+            const float far_a[4] = {1.0f, 0.0f, -1e9f, -1e9f}, far_b[2] = {-1.0f, -0.0f};
+            cA.insert(cA.end(), far_a, far_a + 4);
+            cB.insert(cB.end(), far_b, far_b + 2);
+        }
+        CK(cudaMemcpyToSymbol(c_segA, cA.data(), cA.size() * 4));
+        CK(cudaMemcpyToSymbol(c_segB, cB.data(), cB.size() * 4));
+        h->ctab_key = ++g_ctab_serial;
+        g_ctab_owner[h->device] = h->ctab_key;
+    }
     h->epoch++;
     h->n = n;
     h->ncols = ncols;
@@ -1639,7 +1682,7 @@ int f1l_pure_pursuit_batch_dev(f1l_handle h, const double* poses_dev, int n_pose
     o.front = nullptr;
     ENS(h->pp_key, (size_t)n_poses * 8);   // scan scratch (one call in flight per handle)
     launch_pp(track_view(h), (cudaStream_t)stream, poses_dev, 3, n_poses, L, h->cfg.wheelbase,
-              h->cfg.max_reacquire, 0, 0.0, (unsigned long long*)h->pp_key.p, pp_slots(h), o);
+              h->cfg.max_reacquire, 0, 0.0, (unsigned long long*)h->pp_key.p, pp_slots(h), o, ctab_valid(h));
     h->launches += 2;
     CK(cudaGetLastError());
     return F1L_OK;
@@ -1691,7 +1734,7 @@ int f1l_front_axle_batch_dev(f1l_handle h, const double* poses_dev, int n_poses,
     o.front = front_dev;
     ENS(h->pp_key, (size_t)n_poses * 8);
     launch_pp(track_view(h), (cudaStream_t)stream, poses_dev, 4, n_poses, 0.0, wheelbase, 0.0, 1,
-              k_path, (unsigned long long*)h->pp_key.p, pp_slots(h), o);
+              k_path, (unsigned long long*)h->pp_key.p, pp_slots(h), o, ctab_valid(h));
     h->launches += 2;
     CK(cudaGetLastError());
     return F1L_OK;

@@ -83,6 +83,16 @@ __device__ __forceinline__ f32x2 track_seg_d2_pair(f32x2 px, f32x2 py, float4 A,
     return ffma2(e, e, fmul2(n, n));
 }
 
+// The scan's copy of the line-form table in CONSTANT memory (tracks of up to F1L_CTAB_SEGS
+// segments; one table per device, owned by the handle that uploaded its track last -- others scan
+// the global-memory copy).  Every lane of a scan warp reads the same entry, so from constant memory
+// the segment constants arrive in UNIFORM registers (LDCU) and enter FFMA2 / FADD.SAT as uniform
+// operands (SASS: FFMA2 R14, R6.F32x2.HI_LO, UR13.F32, R12.F32; FADD.SAT R14, |R14|, UR14): they
+// no longer cost vector-register-file reads, which is what bounds this loop.
+#define F1L_CTAB_SEGS 2560
+__constant__ float4 c_segA[F1L_CTAB_SEGS];
+__constant__ float2 c_segB[F1L_CTAB_SEGS];
+
 #ifndef PP_TASK_MINB
 #define PP_TASK_MINB 24    // resident one-warp scan CTAs per SM asked of the compiler (80 registers)
 #endif
@@ -93,6 +103,7 @@ __device__ __forceinline__ f32x2 track_seg_d2_pair(f32x2 px, f32x2 py, float4 A,
 // FP32 scan of the 32-segment blocks [b0, b1) for the PP_LANE_POSES poses of this lane: the
 // running minimum of each block (no index bookkeeping in the inner loop) and the best block; the
 // exact index is recovered afterwards by re-scanning that one block.
+template <bool CT>
 __device__ __forceinline__ void pp_scan_blocks(const TrackView& tr, const double (&qx)[PP_LANE_POSES],
                                                const double (&qy)[PP_LANE_POSES], int b0, int b1,
                                                float (&best)[PP_LANE_POSES],
@@ -100,8 +111,14 @@ __device__ __forceinline__ void pp_scan_blocks(const TrackView& tr, const double
     const int nseg = tr.n - 1;
 #pragma unroll
     for (int p = 0; p < PP_LANE_POSES; ++p) { best[p] = CUDART_INF_F; bblk[p] = 0; }
-    for (int blk = b0; blk < b1; ++blk) {
-        const double2 o = tr.blk_origin[blk];
+    // `blk` only ever indexes the table, so that it stays a warp-uniform value to the compiler and
+    // the constant-memory entries arrive in uniform registers; everything that needs the block
+    // number in a vector register (the origin's address, the per-pose best block) uses an
+    // independent copy that the compiler cannot identify with it.
+    int blk_v = b0;
+    opaque(blk_v);
+    for (int blk = b0; blk < b1; ++blk, ++blk_v) {
+        const double2 o = tr.blk_origin[blk_v];
         f32x2 px[PP_LANE_POSES / 2], py[PP_LANE_POSES / 2];
 #pragma unroll
         for (int p = 0; p < PP_LANE_POSES / 2; ++p) {
@@ -109,16 +126,18 @@ __device__ __forceinline__ void pp_scan_blocks(const TrackView& tr, const double
             py[p] = pack2((float)(qy[2 * p] - o.y) * TRACK_SCALE, (float)(qy[2 * p + 1] - o.y) * TRACK_SCALE);
         }
         const int k0 = blk << 5;
-        const int kn = min(32, nseg - k0);   // the track's last block may be partial
+        const int kn = min(32, nseg - (blk_v << 5));   // the track's last block may be partial
         float m[PP_LANE_POSES];
 #pragma unroll
         for (int p = 0; p < PP_LANE_POSES; ++p) m[p] = CUDART_INF_F;
         constexpr int kUnroll = PP_UNROLL;
-        if (kn == 32) {
+        if (CT || kn == 32) {   // (the constant-memory table is padded to whole blocks with far-away entries)
 #pragma unroll kUnroll
             for (int j = 0; j < 32; j += 2) {   // two segments per trip, minima by FMNMX3
-                const float4 A0 = __ldg(tr.segA + k0 + j), A1 = __ldg(tr.segA + k0 + j + 1);
-                const float2 B0 = __ldg(tr.segB + k0 + j), B1 = __ldg(tr.segB + k0 + j + 1);
+                const float4 A0 = CT ? c_segA[k0 + j] : __ldg(tr.segA + k0 + j);
+                const float4 A1 = CT ? c_segA[k0 + j + 1] : __ldg(tr.segA + k0 + j + 1);
+                const float2 B0 = CT ? c_segB[k0 + j] : __ldg(tr.segB + k0 + j);
+                const float2 B1 = CT ? c_segB[k0 + j + 1] : __ldg(tr.segB + k0 + j + 1);
 #pragma unroll
                 for (int p = 0; p < PP_LANE_POSES / 2; ++p) {
                     float a0, a1, c0, c1;
@@ -130,8 +149,8 @@ __device__ __forceinline__ void pp_scan_blocks(const TrackView& tr, const double
             }
         } else {
             for (int j = 0; j < kn; ++j) {
-                const float4 A0 = __ldg(tr.segA + k0 + j);
-                const float2 B0 = __ldg(tr.segB + k0 + j);
+                const float4 A0 = CT ? c_segA[k0 + j] : __ldg(tr.segA + k0 + j);
+                const float2 B0 = CT ? c_segB[k0 + j] : __ldg(tr.segB + k0 + j);
 #pragma unroll
                 for (int p = 0; p < PP_LANE_POSES / 2; ++p) {
                     float a0, a1;
@@ -143,7 +162,7 @@ __device__ __forceinline__ void pp_scan_blocks(const TrackView& tr, const double
         }
 #pragma unroll
         for (int p = 0; p < PP_LANE_POSES; ++p)
-            if (m[p] < best[p]) { best[p] = m[p]; bblk[p] = blk; }
+            if (m[p] < best[p]) { best[p] = m[p]; bblk[p] = blk_v; }
     }
 }
 
@@ -167,11 +186,21 @@ __device__ __forceinline__ int pp_rescan_block(const TrackView& tr, double x, do
 // 64-bit atomicMin on (bits(d^2) << 32 | block): the smaller distance wins and, at equal
 // distance, the earlier block -- the first minimum in track order (utils.py:66).  `key` is
 // preset to all ones; the winning block is re-scanned for the segment index by pp_finish_kernel.
+// The track's 32-segment blocks are dealt to the parts as evenly as possible: part p gets
+// `per` blocks, the first `rem` parts one more.  Written without an integer division so that a
+// task's block range -- and with it every table index of its scan -- is a warp-uniform value to
+// the compiler (blockIdx and kernel parameters through uniform-datapath arithmetic only).
+#define PP_MAX_PARTS 24
+struct PPParts {
+    int n, per, rem;
+};
+template <bool CT>
 __global__ void __launch_bounds__(32, PP_TASK_MINB)
 pp_scan_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, int n_poses,
-               int front_axle, double wb, int n_parts, unsigned long long* __restrict__ key) {
+               int front_axle, double wb, PPParts parts, unsigned long long* __restrict__ key) {
     const int lane = threadIdx.x;
-    const int grp = blockIdx.x / n_parts, part = blockIdx.x - grp * n_parts;
+    const int grp = blockIdx.x, part = blockIdx.y;   // tasks of one part run together: they walk
+                                                     // the same slice of the table
     const int base = grp * PP_CTA_POSES;
     double qx[PP_LANE_POSES], qy[PP_LANE_POSES];
 #pragma unroll
@@ -180,16 +209,15 @@ pp_scan_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, 
         pp_query_point(poses, pose_stride, min(base + p * 32 + lane, n_poses - 1), front_axle, wb,
                        qx[p], qy[p], qth);
     }
-    const int nblk = (tr.n - 1 + 31) >> 5;
-    const int b0 = (int)((long long)nblk * part / n_parts);
-    const int b1 = (int)((long long)nblk * (part + 1) / n_parts);
+    const int b0 = part * parts.per + min(part, parts.rem);
+    const int b1 = b0 + parts.per + (part < parts.rem ? 1 : 0);
     float best[PP_LANE_POSES];
     int bblk[PP_LANE_POSES];
-    pp_scan_blocks(tr, qx, qy, b0, b1, best, bblk);
+    pp_scan_blocks<CT>(tr, qx, qy, b0, b1, best, bblk);
 #pragma unroll
     for (int p = 0; p < PP_LANE_POSES; ++p) {
         const int gid = base + p * 32 + lane;
-        if (gid < n_poses && b1 > b0)
+        if (gid < n_poses)   // (every part holds at least one block: pp_task_parts keeps parts <= blocks)
             atomicMin(key + gid, ((unsigned long long)__float_as_uint(best[p]) << 32) | (unsigned)bblk[p]);
     }
 }
@@ -197,10 +225,13 @@ pp_scan_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride, 
 // Parts of the track per pose group such that groups x parts one-warp tasks fill whole waves of
 // `slots` resident warps: the most efficient count in [6, 24] (fewer, longer tasks on ties); a
 // task pays a fixed prologue / epilogue of about 1.5 blocks' worth of work.
-static inline int pp_task_parts(int n_groups, int nblk, int slots) {
+// `min_parts`: the constant-memory scan (64 registers, 32 resident warps per SM) measured best
+// with 16 or more parts at config 2 (0.0883 ms against 0.0931 with 9), the global-memory one with 6+.
+static inline int pp_task_parts(int n_groups, int nblk, int slots, int min_parts = 6) {
     int best_p = 8;
     double best_eff = -1.0;
-    for (int p = 6; p <= 24 && p <= nblk; ++p) {
+    if (min_parts > nblk) min_parts = nblk > 0 ? nblk : 1;
+    for (int p = min_parts; p <= PP_MAX_PARTS && p <= nblk; ++p) {
         const double w = (double)n_groups * p / slots;
         const double waves = w <= 1.0 ? 1.0 : (double)(long long)(w + 0.999999);
         const double eff = (w / waves) * ((double)nblk / p) / ((double)nblk / p + 1.5);
