@@ -146,12 +146,18 @@ __device__ __forceinline__ Nearest64 refine_nearest64(const double2* __restrict_
     Nearest64 b;
     b.dist = CUDART_INF; b.i = 0; b.px = 0.0; b.py = 0.0; b.t = 0.0;
     const int lo = max(k - 2, 0), hi = min(k + 2, nseg - 1);
-    for (int s = lo; s <= hi; ++s) {
+    // the five evaluations are independent (a division and a square root each): computed side by
+    // side, then the first-minimum rule replayed in segment order
+    double px[5], py[5], d[5], t[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const int s = min(lo + j, hi);   // (slots beyond hi repeat the last segment and are not used)
         const double2 a = xy[s], c = xy[s + 1];
-        double px, py, d, t;
-        nearest_segment64(qx, qy, a.x, a.y, c.x, c.y, px, py, d, t);
-        if (d < b.dist) { b.dist = d; b.i = s; b.px = px; b.py = py; b.t = t; }
+        nearest_segment64(qx, qy, a.x, a.y, c.x, c.y, px[j], py[j], d[j], t[j]);
     }
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+        if (lo + j <= hi && d[j] < b.dist) { b.dist = d[j]; b.i = lo + j; b.px = px[j]; b.py = py[j]; b.t = t[j]; }
     return b;
 }
 
@@ -450,7 +456,9 @@ __device__ inline Intersect64 intersect_point_group(const P& pts, int n, double 
 // get_actuation (utils/utils.py:153-161): returns steer, passes speed through
 __device__ __forceinline__ double actuation_steer64(double pose_theta, double lx, double ly,
                                                     double qx, double qy, double L, double wb) {
-    const double wy = xadd(xmul(sin(-pose_theta), xsub(lx, qx)), xmul(cos(-pose_theta), xsub(ly, qy)));
+    double sn, cs;
+    sincos(-pose_theta, &sn, &cs);   // (one argument reduction; the values are those of sin() and cos())
+    const double wy = xadd(xmul(sn, xsub(lx, qx)), xmul(cs, xsub(ly, qy)));
     if (fabs(wy) < 1e-6) return 0.0;                                   // :157
     const double radius = __ddiv_rn(1.0, __ddiv_rn(xmul(2.0, wy), xmul(L, L)));  // :159
     return atan(__ddiv_rn(wb, radius));                                // :160

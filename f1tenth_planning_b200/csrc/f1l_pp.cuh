@@ -257,11 +257,23 @@ pp_finish_kernel(TrackView tr, const double* __restrict__ poses, int pose_stride
         const int lane = threadIdx.x & 31;
         const int my_blk = (int)(unsigned)(key[pid] & 0xffffffffull);
         const int n_live = min(32, n_poses - (gid - lane));   // warp-uniform
-        for (int i = 0; i < n_live; ++i) {
-            const int blk = __shfl_sync(F1L_FULL, my_blk, i);
-            const double x = __shfl_sync(F1L_FULL, qx, i), y = __shfl_sync(F1L_FULL, qy, i);
-            const int k = pp_rescan_block(tr, x, y, blk, lane);
-            if (lane == i) bk = k;
+        // four poses per trip: their (load -> distance -> warp minimum -> ballot) chains are
+        // independent and overlap (lanes beyond n_live hold the clamped last pose: harmless)
+#ifndef PP_RESCAN_UNROLL
+#define PP_RESCAN_UNROLL 4
+#endif
+        for (int i0 = 0; i0 < n_live; i0 += PP_RESCAN_UNROLL) {
+            int kk[PP_RESCAN_UNROLL];
+#pragma unroll
+            for (int u = 0; u < PP_RESCAN_UNROLL; ++u) {
+                const int i = i0 + u;
+                const int blk = __shfl_sync(F1L_FULL, my_blk, i);
+                const double x = __shfl_sync(F1L_FULL, qx, i), y = __shfl_sync(F1L_FULL, qy, i);
+                kk[u] = pp_rescan_block(tr, x, y, blk, lane);
+            }
+#pragma unroll
+            for (int u = 0; u < PP_RESCAN_UNROLL; ++u)
+                if (lane == i0 + u) bk = kk[u];
         }
     }
     if (gid >= n_poses) return;
