@@ -119,6 +119,35 @@ def test_no_feasible_and_off_track(ellipse):
     assert ((d.flags & 8) != 0).all()
 
 
+def test_lookahead_circles_clear_of_the_raceline(ellipse, corridor):
+    """Poses 0.45 .. 0.95 m off the raceline with lookaheads 0.4 .. 1.0 m: the rows whose circle
+    stays clear of the raceline skip the sampler's track scan (only the closing segment is
+    tested) and must come out exactly like the oracle's full intersect_point scan -- no centre,
+    flag 8 on all their candidates -- while the rows that do cross keep their goals.  Single
+    queries and the batch sampler (K1's distance) take the same shortcut."""
+    la, wd = synth.goal_grid(1)
+    eng, cfg, world = H.make_pair(ellipse, la, wd, grid=corridor)
+    i0 = [10, 500, 1234, 1999]
+    poses = []
+    for k, off in zip(i0, (0.45, 0.65, 0.85, 0.95)):
+        x, y, psi = ellipse[k, 0], ellipse[k, 1], ellipse[k, 3]
+        sgn = 1.0 if k % 2 else -1.0
+        poses.append([x - sgn * off * np.sin(psi), y + sgn * off * np.cos(psi), psi + 0.05, 4.0])
+    poses = np.array(poses)
+    n_missing = []
+    for pose in poses:
+        d, o, st = _run(eng, cfg, world, pose, None)
+        miss = (d.flags & 8) != 0
+        assert miss.tolist() == ((o["flags"] & 8) != 0).tolist()
+        n_missing.append(int(miss.sum()) // len(wd))
+    assert n_missing == [1, 2, 3, 3]   # lookaheads 0.4, 0.6, 0.8, 1.0 against the four offsets
+    b = eng.plan_batch(poses, want_flags=True)
+    for k, pose in enumerate(poses):
+        o = co.plan(cfg, world, pose, None)
+        assert ((b.flags[k] & 8) != 0).tolist() == ((o["flags"] & 8) != 0).tolist()
+        assert int(b.best_idx[k]) == int(o["best_idx"]) or not np.isfinite(o["best_cost"])
+
+
 def test_explicit_goals_and_generate(ellipse):
     la, wd = synth.goal_grid(1)
     eng, cfg, world = H.make_pair(ellipse, la, wd, kappa_max=0.0)

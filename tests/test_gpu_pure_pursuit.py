@@ -210,3 +210,29 @@ def test_lqr_control_points_match_reference(golden_spielberg):
         LQRPlanner().calc_control_points(np.zeros(4))
     with pytest.raises(ValueError):
         pl.calc_control_points(np.zeros(4), waypoints=np.zeros((5, 4)))
+
+
+def _oracle_check(eng, track, n, seed):
+    poses, _ = synth.random_poses(track, n, np.random.default_rng(seed))
+    r = eng.pure_pursuit_batch(poses[:, :3], 0.8)
+    o = co.pure_pursuit_batch(track, poses[:, :3], 0.8)
+    _check(r, o, track.shape[0])
+
+
+def test_constant_table_ownership_and_fallback():
+    """The scan's constant-memory copy of the line form belongs to the engine that uploaded its
+    track last (one table per device); an older engine scans its global-memory copy, a track too
+    long for the table never uses it, and a re-upload takes the table back.  All of them must give
+    the oracle's answers -- including a last 32-segment block that is partial (padded entries)."""
+    t_a = synth.ellipse_track(n=2000)            # 1999 segments: partial last block
+    t_b = synth.ellipse_track(n=1500, a=50.0, b=30.0)
+    t_c = synth.ellipse_track(n=3000)            # beyond the table: global-memory scan
+    eng_a, eng_b = _engine(t_a), _engine(t_b)    # B owns the table now
+    _oracle_check(eng_a, t_a, 1500, 1)           # A: global path
+    _oracle_check(eng_b, t_b, 1500, 2)           # B: constant path
+    eng_c = _engine(t_c)                         # too long: the table keeps B's entries
+    _oracle_check(eng_c, t_c, 1500, 3)
+    _oracle_check(eng_b, t_b, 700, 4)
+    eng_a.set_track(t_a)                         # A takes the table back
+    _oracle_check(eng_a, t_a, 1500, 5)
+    _oracle_check(eng_b, t_b, 700, 6)            # B: global path, same answers
