@@ -559,9 +559,11 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     // (the expensive candidates) first.  No wave quantisation, one window-table prologue per
     // resident CTA, and the cheap early-exit candidates fill the tail.
     const int resident_ctas = (wpc == 4 ? EVAL_MINB4 : wpc == 7 ? EVAL_MINB7 : EVAL_MINB8) * h->sm_count;
-    static const bool dyn_off = getenv("F1L_EVAL_DYNAMIC") && atoi(getenv("F1L_EVAL_DYNAMIC")) == 0;
-    const bool dyn = S == 1 && wpc != 4 && o.work_next && !o.empty_shard && !dyn_off &&
-                     (long long)cp.ctas_per_scn > resident_ctas;
+    // F1L_EVAL_DYNAMIC: 0 = never, 2 = whenever the query has more than one CTA (sanitizer runs at
+    // small sizes), default = when it needs more than one wave
+    static const int dyn_mode = getenv("F1L_EVAL_DYNAMIC") ? atoi(getenv("F1L_EVAL_DYNAMIC")) : 1;
+    const bool dyn = S == 1 && wpc != 4 && o.work_next && !o.empty_shard && dyn_mode != 0 &&
+                     ((long long)cp.ctas_per_scn > resident_ctas || (dyn_mode == 2 && cp.ctas_per_scn > 1));
 
     SampleArgs sa;
     sa.tr = track_view(h);
@@ -641,7 +643,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
         // single candidates per pull, unless every warp has at least four 4-candidate items to go
         // through: then the shared Newton solve pays more than the coarser tail costs
         ea.item = (ep.generator == 0 && (long long)n_cand >= 16LL * resident_ctas * wpc) ? EVAL_ITEM : 1;
-        ea.ctas_per_scn = resident_ctas;
+        ea.ctas_per_scn = cp.ctas_per_scn < resident_ctas ? cp.ctas_per_scn : resident_ctas;
     }
     ea.inv_nW = 1.0f / (float)(h->nW > 0 ? h->nW : 1);
     ea.nseg_pad = nseg_pad;
