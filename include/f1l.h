@@ -116,7 +116,11 @@ const char* f1l_last_cuda_error(f1l_handle h);
 
 /* Track upload.  wpts is [N, ncols] float64 row-major, columns x, y[, v, psi, kappa]
  * (examples/control/Spielberg_raceline.csv:1; pure_pursuit.py:101 uses col 2 as speed).
- * Replaces `self.waypoints = waypoints` (lattice_planner.py:49, pure_pursuit.py:54,103). */
+ * Replaces `self.waypoints = waypoints` (lattice_planner.py:49, pure_pursuit.py:54,103).
+ * Slow path: besides the device copies, a track of up to 2560 segments is also written into the
+ * device's constant-memory line-form table that the batched nearest_point scan prefers (one table
+ * per device, owned by the handle that uploaded last; other handles on the device scan their
+ * global-memory copy, same results).  The call synchronises the whole device first. */
 int f1l_set_track(f1l_handle h, const double* wpts, int n, int ncols);
 
 /* Occupancy grid upload: occ is [H, W] uint8 row-major, 0 = free, non-zero = occupied,
