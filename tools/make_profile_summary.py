@@ -69,6 +69,8 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__inst_executed.sum", "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed",
         "smsp__thread_inst_executed_per_inst_executed.ratio",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct", "lts__t_sector_op_read_hit_rate.pct",
+        "lts__t_sector_hit_rate.pct", "idc__request_hit_rate.pct",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.max",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
