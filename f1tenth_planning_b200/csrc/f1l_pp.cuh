@@ -130,7 +130,8 @@ __device__ __forceinline__ void pp_scan_blocks(const TrackView& tr, const double
         float m[PP_LANE_POSES];
 #pragma unroll
         for (int p = 0; p < PP_LANE_POSES; ++p) m[p] = CUDART_INF_F;
-        constexpr int kUnroll = PP_UNROLL;
+        constexpr int kUnroll = CT ? 2 * PP_UNROLL : PP_UNROLL;   // (constant table: more loads in flight
+                                                                  //  per trip cover its cache misses)
         if (CT || kn == 32) {   // (the constant-memory table is padded to whole blocks with far-away entries)
 #pragma unroll kUnroll
             for (int j = 0; j < 32; j += 2) {   // two segments per trip, minima by FMNMX3
