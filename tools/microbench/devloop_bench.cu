@@ -159,6 +159,75 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) loop_kernel(float* out, int
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// The same loop with every lane of the warp on the SAME segment (lanes = sample groups only) and
+// the segment constants in CONSTANT memory: the index is warp-uniform, the entries arrive in uniform
+// registers (LDCU) and enter FFMA2 / FADD.SAT as uniform operands -- no vector-register-file reads
+// for them.  This is what an "item-wide" eval loop (the 4 x 100 samples of an item on one warp
+// against the track's own table) or K1's scan look like.  Two segments per trip, FMNMX3 minima.
+__constant__ float4 cT[2 * (256 + 32)];
+template <int S>
+__global__ void __launch_bounds__(NWARPS * 32, MINB) loop_kernel_ct(float* out, int reps, int nq) {
+    constexpr int SP = S / 2;
+    const int lane = threadIdx.x & 31;
+    f32x2 sx2[SP], sy2[SP];
+    float bdx[SP], bdy[SP];
+#pragma unroll
+    for (int j = 0; j < SP; ++j) {
+        sx2[j] = pack2(out[j + lane], out[2 * j + lane]);
+        sy2[j] = pack2(out[3 * j + lane], out[j + 2 * lane]);
+        bdx[j] = CUDART_INF_F;
+        bdy[j] = CUDART_INF_F;
+    }
+    for (int r = 0; r < reps; ++r) {
+        for (int k = 0; k < nq; k += 2) {
+            const float4 T0 = cT[2 * k], T1 = cT[2 * k + 1], B0 = cT[2 * k + 2], B1 = cT[2 * k + 3];
+            f32x2 d[SP], e[SP];
+            seg_step<SP, 1, 0>(sx2, sy2, T0, T1, d);
+            seg_step<SP, 1, 0>(sx2, sy2, B0, B1, e);
+#pragma unroll
+            for (int j = 0; j < SP; ++j) {
+                float da, db, ea, eb;
+                unpack2(d[j], da, db);
+                unpack2(e[j], ea, eb);
+                bdx[j] = fmin3(bdx[j], da, ea);
+                bdy[j] = fmin3(bdy[j], db, eb);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < SP; ++j) sx2[j] = fadd2(sx2[j], pack2(1e-3f, 1e-3f));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < SP; ++j) s += bdx[j] + bdy[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int S>
+void run_ct(const char* name, float* out, int sms, double ghz) {
+    const int reps = 25, nq = 128;
+    const int blocks = sms * MINB * 8;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int it = 0; it < 4; ++it) {
+        cudaEventRecord(e0);
+        loop_kernel_ct<S><<<blocks, NWARPS * 32>>>(out, reps, nq);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (it && ms < best) best = ms;
+    }
+    const double warp_sample_seg = (double)blocks * NWARPS * reps * nq * S;
+    const double smsp_cycles = best * 1e-3 * ghz * 1e9 * sms * 4;
+    const double flops = warp_sample_seg * 32 * 17.0;
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, loop_kernel_ct<S>);
+    printf("%-44s regs %3d spill %3zu B  %7.3f ms  %6.3f SMSP-cycles per (sample, segment)  %6.2f algorithmic TFLOP/s\n",
+           name, fa.numRegs, fa.localSizeBytes, best, smsp_cycles / warp_sample_seg, flops / (best * 1e-3) / 1e12);
+}
+
 template <int S, int SG, int MATH, int ORDER, int MIN3>
 void run(const char* name, float* out, int sms, double ghz) {
     const int reps = 100, nq = 128;
@@ -207,6 +276,18 @@ int main() {
     run<8, 16, 1, 0, 0>("S=8 SG=16 FADD.SAT math, pair order", out, sms, ghz);
     run<8, 16, 1, 1, 1>("S=8 SG=16 FADD.SAT, op-major x3, min3", out, sms, ghz);
     run<6, 16, 1, 1, 1>("S=6 SG=16 FADD.SAT, op-major x3, min3", out, sms, ghz);
+    {
+        float4 hT[2 * (256 + 32)];
+        for (int k = 0; k < 256 + 32; ++k) {
+            const float ang = 0.01f * k;
+            hT[2 * k] = make_float4(cosf(ang), sinf(ang), -sinf(ang), 5.0f);
+            hT[2 * k + 1] = make_float4(-0.002f * k, 0.0001f * k, -0.002f, 0.0f);
+        }
+        cudaMemcpyToSymbol(cT, hT, sizeof(hT));
+    }
+    run_ct<12>("S=12 uniform operands (constant table), min3", out, sms, ghz);
+    run_ct<14>("S=14 uniform operands (constant table), min3", out, sms, ghz);
+    run_ct<8>("S=8 uniform operands (constant table), min3", out, sms, ghz);
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); return 1; }
     return 0;
