@@ -22,7 +22,6 @@ struct NvtxRange {
 
 #include "f1l_common.cuh"
 #include "f1l_lattice.cuh"
-#include "f1l_lattice_ws.cuh"
 #include "f1l_peaks.cuh"
 #include "f1l_pp.cuh"
 
@@ -454,32 +453,6 @@ void launch_pp(const TrackView& tv, cudaStream_t stream, const double* poses, in
         tv, poses, pose_stride, n_poses, L, wb, max_reacquire, front_axle, k_path, key, o);
 }
 
-// eval_ws_kernel (f1l_lattice_ws.cuh): shared memory (mirrors WsSmem) and whether this build may use
-// it at all -- the CTA's register pool (launch registers x threads) must cover what the setmaxnreg
-// pair redistributes, or the consumers' setmaxnreg.inc would wait forever
-size_t ws_smem_bytes(int nseg_pad, int M) {
-    const EvalShape sh = eval_shape(M);
-    const size_t pcap = (size_t)sh.s * sh.sg, slab = (size_t)((sh.s + 1) / 2) * sh.sg * 2;
-    size_t b = WS_PRODUCERS * (pcap * 32 + 128);
-    b += (size_t)WS_SLOTS * (32 + 2 * slab * 4);
-    b += 2 * WS_SLOTS * 8;
-    b += F1L_MAX_OPP * sizeof(float4) + 48;
-    b += (size_t)F1L_MAX_M * sizeof(float);
-    b += (size_t)(nseg_pad + EVAL_SEG_PAD) * (2 * sizeof(float4));
-    return b;
-}
-bool ws_usable() {
-    static int ok = -1;
-    if (ok < 0) {
-        cudaFuncAttributes fa;
-        ok = cudaFuncGetAttributes(&fa, eval_ws_kernel<4, EVAL_S104, EVAL_SG104>) == cudaSuccess &&
-             fa.numRegs >= WS_REGS_LAUNCH && fa.numRegs * WS_WARPS * 32 * WS_MINB <= 65536;
-        if (const char* e = getenv("F1L_EVAL_WS")) if (atoi(e) == 0) ok = 0;
-        cudaGetLastError();
-    }
-    return ok == 1;
-}
-
 size_t eval_smem_bytes(int nseg_pad, int warps, int M) {   // mirrors EvalSmem (f1l_lattice.cuh)
     const EvalShape sh = eval_shape(M);
     const size_t pcap = (size_t)sh.s * sh.sg, slab = (size_t)((sh.s + 1) / 2) * sh.sg * 2;
@@ -685,18 +658,11 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     ea.stats = h->stats_on ? (unsigned long long*)h->stats.p : nullptr;
     const long long n_ctas = (long long)S * ea.ctas_per_scn;
     if (n_ctas > 0x7fffffffLL) return F1L_ERR_TOO_LARGE;
-    // Batches of whole-scenario CTAs (the throughput regime) run the producer / consumer kernel:
-    // same arithmetic and results, the deviation loop in warps with their own register budget.
-    const bool ws = !o.empty_shard && !dyn && S >= 64 && wpc == 4 && ea.ctas_per_scn == 1 && ea.item == EVAL_ITEM &&
-                    ep.generator == 0 && !ep.prune && !h->stats_on && M > 64 && M <= 104 &&
-                    ea.row_step == 1 && ws_usable() && ws_smem_bytes(nseg_pad, M) <= 99 * 1024;
-    if (ws)
-        eval_ws_kernel<4, EVAL_S104, EVAL_SG104><<<(unsigned)S, WS_WARPS * 32, ws_smem_bytes(nseg_pad, M), stream>>>(ea);
-    else if (!o.empty_shard) eval_entry(M, wpc)<<<(unsigned)n_ctas, wpc * 32, smem, stream>>>(ea);
+    if (!o.empty_shard) eval_entry(M, wpc)<<<(unsigned)n_ctas, wpc * 32, smem, stream>>>(ea);
     {
         const EvalShape sh = eval_shape(M);
-        const int info[8] = {sh.ipl, sh.s, sh.sg, ws ? -WS_WARPS : wpc,
-                             ws ? WS_MINB : wpc == 4 ? EVAL_MINB4 : wpc == 7 ? EVAL_MINB7 : EVAL_MINB8,
+        const int info[8] = {sh.ipl, sh.s, sh.sg, wpc,
+                             wpc == 4 ? EVAL_MINB4 : wpc == 7 ? EVAL_MINB7 : EVAL_MINB8,
                              ea.chunk, ea.ctas_per_scn, ea.item};
         for (int i = 0; i < 8; ++i) h->eval_info[i] = info[i];
     }
@@ -972,9 +938,6 @@ int f1l_create(f1l_handle* out, int device, const f1l_config* cfg) {
                 if (e2 != cudaSuccess && e == cudaSuccess) e = e2;
             }
         }
-        cudaFuncSetAttribute(eval_ws_kernel<4, EVAL_S104, EVAL_SG104>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             100 * 1024);
-        cudaGetLastError();
     }
     if (e != cudaSuccess) {
         fail(h, e, "f1l_create");
