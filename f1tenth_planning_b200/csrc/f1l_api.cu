@@ -324,6 +324,14 @@ eval_fn eval_entry(int M, int nw) {
     if (M <= 208) return eval_kernel<7, 13, 16, 8, EVAL_MINB8>;
     return eval_kernel<8, 16, 16, 8, EVAL_MINB8>;
 }
+// M > 128 shapes at two 8-warp CTAs per SM (128 registers): the deviation loop gets the registers
+// it wants (tools/microbench/devloop_bench.cu), at the price of a third fewer resident warps.  Pays
+// for a dense query with many candidates per warp slot (the unsharded 65 536), not for its shards.
+#define EVAL_MINB8_WIDE 2
+eval_fn eval_entry_wide(int M) {
+    if (M <= 208) return eval_kernel<7, 13, 16, 8, EVAL_MINB8_WIDE>;
+    return eval_kernel<8, 16, 16, 8, EVAL_MINB8_WIDE>;
+}
 select_fn select_entry(int M) {
     if (M <= 32) return select_kernel<1>;
     if (M <= 64) return select_kernel<2>;
@@ -558,12 +566,19 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     // wave of CTAs whose warps pull single candidates from a device-wide counter, far lookahead rows
     // (the expensive candidates) first.  No wave quantisation, one window-table prologue per
     // resident CTA, and the cheap early-exit candidates fill the tail.
-    const int resident_ctas = (wpc == 4 ? EVAL_MINB4 : wpc == 7 ? EVAL_MINB7 : EVAL_MINB8) * h->sm_count;
+    int resident_ctas = (wpc == 4 ? EVAL_MINB4 : wpc == 7 ? EVAL_MINB7 : EVAL_MINB8) * h->sm_count;
     // F1L_EVAL_DYNAMIC: 0 = never, 2 = whenever the query has more than one CTA (sanitizer runs at
     // small sizes), default = when it needs more than one wave
     static const int dyn_mode = getenv("F1L_EVAL_DYNAMIC") ? atoi(getenv("F1L_EVAL_DYNAMIC")) : 1;
     const bool dyn = S == 1 && wpc != 4 && o.work_next && !o.empty_shard && dyn_mode != 0 &&
                      ((long long)cp.ctas_per_scn > resident_ctas || (dyn_mode == 2 && cp.ctas_per_scn > 1));
+    // ... and with at least F1L_EVAL_WIDE_MIN (default 4) candidates per resident warp it runs the
+    // 128-register build of the M > 128 shapes on two CTAs per SM (measured on config 5: 65 536
+    // candidates 471 -> 431 us, 32 768: 247 -> 234, 16 384: 134 -> 128, 8 192: 76 -> 100)
+    static const int wide_min = getenv("F1L_EVAL_WIDE_MIN") ? atoi(getenv("F1L_EVAL_WIDE_MIN")) : 4;
+    const bool wide = dyn && wpc == 8 && M > 128 && wide_min > 0 &&
+                      (long long)n_cand >= (long long)wide_min * resident_ctas * wpc;
+    if (wide) resident_ctas = EVAL_MINB8_WIDE * h->sm_count;
 
     SampleArgs sa;
     sa.tr = track_view(h);
@@ -658,11 +673,11 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     ea.stats = h->stats_on ? (unsigned long long*)h->stats.p : nullptr;
     const long long n_ctas = (long long)S * ea.ctas_per_scn;
     if (n_ctas > 0x7fffffffLL) return F1L_ERR_TOO_LARGE;
-    if (!o.empty_shard) eval_entry(M, wpc)<<<(unsigned)n_ctas, wpc * 32, smem, stream>>>(ea);
+    if (!o.empty_shard) (wide ? eval_entry_wide(M) : eval_entry(M, wpc))<<<(unsigned)n_ctas, wpc * 32, smem, stream>>>(ea);
     {
         const EvalShape sh = eval_shape(M);
         const int info[8] = {sh.ipl, sh.s, sh.sg, wpc,
-                             wpc == 4 ? EVAL_MINB4 : wpc == 7 ? EVAL_MINB7 : EVAL_MINB8,
+                             wide ? EVAL_MINB8_WIDE : wpc == 4 ? EVAL_MINB4 : wpc == 7 ? EVAL_MINB7 : EVAL_MINB8,
                              ea.chunk, ea.ctas_per_scn, ea.item};
         for (int i = 0; i < 8; ++i) h->eval_info[i] = info[i];
     }
@@ -937,6 +952,10 @@ int f1l_create(f1l_handle* out, int device, const f1l_config* cfg) {
                     eval_entry(m, nw), cudaFuncAttributeMaxDynamicSharedMemorySize, big);
                 if (e2 != cudaSuccess && e == cudaSuccess) e = e2;
             }
+        }
+        for (int m : {200, 256}) {
+            cudaError_t e2 = cudaFuncSetAttribute(eval_entry_wide(m), cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+            if (e2 != cudaSuccess && e == cudaSuccess) e = e2;
         }
     }
     if (e != cudaSuccess) {
