@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -415,8 +416,12 @@ CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count, bool cubic) {
 
 // owner of the constant-memory line-form table of each device (f1l_pp.cuh): the key of the handle
 // whose f1l_set_track filled it last
+// (host threads: a scan that uses the table is enqueued under g_ctab_mu after re-checking the
+// owner, and an upload first withdraws the ownership under the same mutex, then drains the device,
+// then writes -- so no enqueued scan can meet another track's entries)
 static unsigned long long g_ctab_owner[64] = {0};
 static unsigned long long g_ctab_serial = 0;
+static std::mutex g_ctab_mu;
 bool ctab_valid(f1l_handle h) {
     return h->ctab_key != 0 && h->device >= 0 && h->device < 64 && g_ctab_owner[h->device] == h->ctab_key;
 }
@@ -439,7 +444,7 @@ int pp_slots(f1l_handle h) {
 // scan CTAs resident on the device (pp_slots)
 void launch_pp(const TrackView& tv, cudaStream_t stream, const double* poses, int pose_stride,
                int n_poses, double L, double wb, double max_reacquire, int front_axle, double k_path,
-               unsigned long long* key, int slots, const PPOut& o, bool ctab) {
+               unsigned long long* key, int slots, const PPOut& o, bool ctab, f1l_handle owner = nullptr) {
     const int n_groups = (n_poses + PP_CTA_POSES - 1) / PP_CTA_POSES;
     const int nblk = (tv.n - 1 + 31) >> 5;
     int n_parts = pp_task_parts(n_groups, nblk, slots, ctab ? 16 : 6);
@@ -453,9 +458,13 @@ void launch_pp(const TrackView& tv, cudaStream_t stream, const double* poses, in
     parts.per = nblk / n_parts;
     parts.rem = nblk - parts.per * n_parts;
     const dim3 grid((unsigned)n_groups, (unsigned)n_parts);
-    if (ctab)
-        pp_scan_kernel<true><<<grid, 32, 0, stream>>>(tv, poses, pose_stride, n_poses, front_axle, wb, parts, key);
-    else
+    if (ctab) {
+        std::lock_guard<std::mutex> lk(g_ctab_mu);
+        ctab = owner && ctab_valid(owner);   // still ours?  (checked and enqueued under the mutex)
+        if (ctab)
+            pp_scan_kernel<true><<<grid, 32, 0, stream>>>(tv, poses, pose_stride, n_poses, front_axle, wb, parts, key);
+    }
+    if (!ctab)
         pp_scan_kernel<false><<<grid, 32, 0, stream>>>(tv, poses, pose_stride, n_poses, front_axle, wb, parts, key);
     pp_finish_kernel<<<(n_poses + PP_THREADS - 1) / PP_THREADS, PP_THREADS, 0, stream>>>(
         tv, poses, pose_stride, n_poses, L, wb, max_reacquire, front_axle, k_path, key, o);
@@ -611,7 +620,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
         po.actuation = nullptr;
         po.status = nullptr;
         po.front = nullptr;
-        launch_pp(sa.tr, stream, poses, 4, S, -1.0, 0.33, 0.0, 0, 0.0, best, pp_slots(h), po, ctab_valid(h));   // `best` doubles as K1's key scratch: the sampler resets it
+        launch_pp(sa.tr, stream, poses, 4, S, -1.0, 0.33, 0.0, 0, 0.0, best, pp_slots(h), po, ctab_valid(h), h);   // `best` doubles as K1's key scratch: the sampler resets it
         sample_warp_kernel<<<(S + SAMPLE_WARPS - 1) / SAMPLE_WARPS, SAMPLE_WARPS * 32, 0, stream>>>(
             sa, near_i, near4, S);
         h->launches += 2;
@@ -1059,6 +1068,10 @@ int f1l_set_track(f1l_handle h, const double* wpts, int n, int ncols) {
     h->ctab_key = 0;
     static const bool ctab_off = getenv("F1L_CTAB") && atoi(getenv("F1L_CTAB")) == 0;
     if (nblk * 32 <= F1L_CTAB_SEGS && h->device >= 0 && h->device < 64 && !ctab_off) {
+        {   // withdraw the table from whoever owns it, then wait for the scans already enqueued on it
+            std::lock_guard<std::mutex> lk(g_ctab_mu);
+            g_ctab_owner[h->device] = 0;
+        }
         CK(cudaDeviceSynchronize());
         // padded to whole 32-segment blocks with entries no query point comes near (d^2 = 1e18 table
         // units): the constant-memory scan has no partial-block path
@@ -1070,8 +1083,11 @@ int f1l_set_track(f1l_handle h, const double* wpts, int n, int ncols) {
         }
         CK(cudaMemcpyToSymbol(c_segA, cA.data(), cA.size() * 4));
         CK(cudaMemcpyToSymbol(c_segB, cB.data(), cB.size() * 4));
-        h->ctab_key = ++g_ctab_serial;
-        g_ctab_owner[h->device] = h->ctab_key;
+        {
+            std::lock_guard<std::mutex> lk(g_ctab_mu);
+            h->ctab_key = ++g_ctab_serial;
+            g_ctab_owner[h->device] = h->ctab_key;
+        }
     }
     h->epoch++;
     h->n = n;
@@ -1703,7 +1719,7 @@ int f1l_pure_pursuit_batch_dev(f1l_handle h, const double* poses_dev, int n_pose
     o.front = nullptr;
     ENS(h->pp_key, (size_t)n_poses * 8);   // scan scratch (one call in flight per handle)
     launch_pp(track_view(h), (cudaStream_t)stream, poses_dev, 3, n_poses, L, h->cfg.wheelbase,
-              h->cfg.max_reacquire, 0, 0.0, (unsigned long long*)h->pp_key.p, pp_slots(h), o, ctab_valid(h));
+              h->cfg.max_reacquire, 0, 0.0, (unsigned long long*)h->pp_key.p, pp_slots(h), o, ctab_valid(h), h);
     h->launches += 2;
     CK(cudaGetLastError());
     return F1L_OK;
@@ -1755,7 +1771,7 @@ int f1l_front_axle_batch_dev(f1l_handle h, const double* poses_dev, int n_poses,
     o.front = front_dev;
     ENS(h->pp_key, (size_t)n_poses * 8);
     launch_pp(track_view(h), (cudaStream_t)stream, poses_dev, 4, n_poses, 0.0, wheelbase, 0.0, 1,
-              k_path, (unsigned long long*)h->pp_key.p, pp_slots(h), o, ctab_valid(h));
+              k_path, (unsigned long long*)h->pp_key.p, pp_slots(h), o, ctab_valid(h), h);
     h->launches += 2;
     CK(cudaGetLastError());
     return F1L_OK;

@@ -236,3 +236,40 @@ def test_constant_table_ownership_and_fallback():
     eng_a.set_track(t_a)                         # A takes the table back
     _oracle_check(eng_a, t_a, 1500, 5)
     _oracle_check(eng_b, t_b, 700, 6)            # B: global path, same answers
+
+
+def test_constant_table_taken_over_by_another_thread():
+    """One host thread keeps scanning its track while another keeps uploading a different one on
+    the same device (each upload takes the constant-memory table over): every batch of the first
+    thread must still be its own track's answer, whichever copy of the table it was scanned on."""
+    import threading
+    t_a = synth.ellipse_track(n=2000)
+    t_b = synth.ellipse_track(n=1200, a=30.0, b=20.0)
+    eng_a, eng_b = _engine(t_a), _engine(t_b)
+    poses, _ = synth.random_poses(t_a, 4096, np.random.default_rng(11))
+    eng_a.set_track(t_a)
+    ref = eng_a.pure_pursuit_batch(poses[:, :3], 0.8)
+    stop = threading.Event()
+    errors = []
+
+    def uploader():
+        try:
+            while not stop.is_set():
+                eng_b.set_track(t_b)
+        except Exception as e:   # pragma: no cover
+            errors.append(e)
+
+    th = threading.Thread(target=uploader)
+    th.start()
+    try:
+        for k in range(60):
+            if k % 7 == 0:
+                eng_a.set_track(t_a)   # take the table back now and then
+            r = eng_a.pure_pursuit_batch(poses[:, :3], 0.8)
+            assert np.array_equal(r.nearest_i, ref.nearest_i)
+            assert np.array_equal(r.nearest, ref.nearest)
+            assert np.array_equal(r.actuation, ref.actuation)
+    finally:
+        stop.set()
+        th.join()
+    assert not errors
