@@ -301,11 +301,23 @@ typedef void (*generate_fn)(LutView, EvalParams, const float4*, int, float4*, fl
 #ifndef EVAL_MINB4
 #define EVAL_MINB4 7
 #endif
+// The M <= 104 shape on 4-warp CTAs (the batch regime of the 4x7 grid): FOUR CTAs per SM at 125
+// registers instead of seven at 72 -- the deviation loop gets the schedule it wants (no spill, 8.2
+// instead of 9.6 sub-partition cycles per (sample, segment) in isolation) and sixteen warps per SM
+// still cover the latency-bound stages: 11.10 -> 10.84 ms on the bench workload (five CTAs at 96
+// registers: 11.16, six at 80: 11.26, three at 161: 11.69; profiles/r2_microbench.md).
+#ifndef EVAL_MINB4_104
+#define EVAL_MINB4_104 4
+#endif
+static inline int eval_minb(int nw, int M) {
+    if (nw == 4) return (M > 64 && M <= 104) ? EVAL_MINB4_104 : EVAL_MINB4;
+    return nw == 7 ? EVAL_MINB7 : EVAL_MINB8;
+}
 eval_fn eval_entry(int M, int nw) {
     if (nw == 4) {
         if (M <= 32) return eval_kernel<1, 4, 8, 4, EVAL_MINB4>;
         if (M <= 64) return eval_kernel<2, 8, 8, 4, EVAL_MINB4>;
-        if (M <= 104) return eval_kernel<4, EVAL_S104, EVAL_SG104, 4, EVAL_MINB4>;
+        if (M <= 104) return eval_kernel<4, EVAL_S104, EVAL_SG104, 4, EVAL_MINB4_104>;
         if (M <= 128) return eval_kernel<4, 16, 8, 4, EVAL_MINB4>;
         if (M <= 208) return eval_kernel<7, 13, 16, 4, EVAL_MINB4>;
         return eval_kernel<8, 16, 16, 4, EVAL_MINB4>;
@@ -369,6 +381,16 @@ CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count, bool cubic) {
             chunk % nw == 0 && !(nw != 8 && M > 128))
             return CtaPlan{nw, chunk, (n_cand + chunk - 1) / chunk};
     }
+    // Throughput regime -- many waves of small scenarios (the 4x7 grid: 28 candidates) with shared
+    // Newton solves: one 4-warp CTA per scenario whose warps pull the scenario's 4-candidate items.
+    // Measured, not modelled (the wave model below counts CTAs and would always prefer the CTA with
+    // more warps at equal residency): 10.84 ms on the bench workload against 11.19 for 7-warp CTAs.
+    {
+        const int full4 = ((n_cand + 3) / 4) * 4;
+        if (cubic && M <= 128 && full4 >= 4 * EVAL_ITEM && n_cand <= 256 &&
+            (long long)S >= 8LL * eval_minb(4, M) * sm_count)
+            return CtaPlan{4, full4, 1};
+    }
     const int nws[3] = {4, 7, 8};
     for (int nw : nws) {
 #ifdef F1L_FORCE_NW
@@ -377,7 +399,7 @@ CtaPlan plan_ctas(int n_cand, int S, int M, int sm_count, bool cubic) {
 #ifndef F1L_ALLOW_SMALL_NW_BIG_M
         if (nw != 8 && M > 128) continue;   // the 72-register builds of the M = 200 shapes spill
 #endif
-        const int resident = (nw == 4 ? EVAL_MINB4 : nw == 7 ? EVAL_MINB7 : EVAL_MINB8) * sm_count;
+        const int resident = eval_minb(nw, M) * sm_count;
         const int full = ((n_cand + nw - 1) / nw) * nw;   // one CTA per scenario
         // chunk sizes worth a look: enough CTAs for ~8 waves (dense single queries), the smallest
         // chunk whose warps share Newton solves, and the whole scenario in one CTA
@@ -575,7 +597,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     // wave of CTAs whose warps pull single candidates from a device-wide counter, far lookahead rows
     // (the expensive candidates) first.  No wave quantisation, one window-table prologue per
     // resident CTA, and the cheap early-exit candidates fill the tail.
-    int resident_ctas = (wpc == 4 ? EVAL_MINB4 : wpc == 7 ? EVAL_MINB7 : EVAL_MINB8) * h->sm_count;
+    int resident_ctas = eval_minb(wpc, M) * h->sm_count;
     // F1L_EVAL_DYNAMIC: 0 = never, 2 = whenever the query has more than one CTA (sanitizer runs at
     // small sizes), default = when it needs more than one wave
     static const int dyn_mode = getenv("F1L_EVAL_DYNAMIC") ? atoi(getenv("F1L_EVAL_DYNAMIC")) : 1;
@@ -686,7 +708,7 @@ int launch_pipeline(f1l_handle h, cudaStream_t stream, const double* poses, cons
     {
         const EvalShape sh = eval_shape(M);
         const int info[8] = {sh.ipl, sh.s, sh.sg, wpc,
-                             wide ? EVAL_MINB8_WIDE : wpc == 4 ? EVAL_MINB4 : wpc == 7 ? EVAL_MINB7 : EVAL_MINB8,
+                             wide ? EVAL_MINB8_WIDE : eval_minb(wpc, M),
                              ea.chunk, ea.ctas_per_scn, ea.item};
         for (int i = 0; i < 8; ++i) h->eval_info[i] = info[i];
     }
