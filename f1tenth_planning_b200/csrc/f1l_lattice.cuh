@@ -762,7 +762,7 @@ __device__ __forceinline__ float fast_sqrt(float x) {
 #define EVAL_DEV_MODE 3
 #endif
 // order of the packed instructions of one segment step: 0 = sample pair after sample pair,
-// 1 = operation-major over groups of three pairs (consecutive instructions share their segment
+// 1 = operation-major over groups of EVAL_DEV_GROUP pairs (consecutive instructions share their segment
 // constants, which then come from the operand reuse cache instead of the register file)
 #ifndef EVAL_DEV_ORDER
 #define EVAL_DEV_ORDER 1
@@ -831,8 +831,12 @@ __device__ __forceinline__ float seg_dist2(float sx, float sy, const float4& T0,
     return fmaf(e, e, nn * nn);
 }
 
-// squared distances of the sample pairs [J0, J0 + 3) of a lane to one segment
+// squared distances of the sample pairs [J0, J0 + EVAL_DEV_GROUP) of a lane to one segment
+// (pairs per operation-major group, re-measured with the batch shape at 125 registers: 2 gives
+//  10.76 ms against 10.83 on the full scan but 6.50 against 6.35 with prune_window = 1; 6: 10.88)
+#ifndef EVAL_DEV_GROUP
 #define EVAL_DEV_GROUP 3
+#endif
 template <int SP, int J0>
 __device__ __forceinline__ void seg_group(const f32x2 (&sx2)[SP], const f32x2 (&sy2)[SP],
                                           const float4& T0, const float4& T1,
