@@ -22,6 +22,13 @@ def test_eval_plan_of_the_baseline_configs():
     # seven items of four candidates (shared Newton solve); measured faster than one 7-warp CTA
     p = eval_plan(28, 100000, 100)
     assert p == dict(nw=4, chunk=28, ctas_per_scenario=1, item=4), p
+    # ... also for the chunks of the host-buffer pipeline (8192 scenarios): the throughput-regime
+    # rule needs eight waves of the four resident 4-warp CTAs per SM, 4736 scenarios
+    assert eval_plan(28, 8192, 100) == p
+    assert eval_plan(28, 4736, 100) == p
+    assert eval_plan(28, 4735, 100)["nw"] != 4 or eval_plan(28, 4735, 100)["ctas_per_scenario"] != 1
+    # the G1-clothoid generator has no shared solve: the wave model decides, never items of four
+    assert eval_plan(28, 100000, 100, generator=1)["item"] == 1
     # ... a few scenarios (less than a wave) are a latency problem: one candidate per warp
     p = eval_plan(28, 64, 100)
     assert p == dict(nw=7, chunk=7, ctas_per_scenario=4, item=1), p
